@@ -1,0 +1,131 @@
+/*
+ * sfb_b200.h — C ABI of the B200-native (sm_100a) window coupling-matrix library.
+ *
+ * Drop-in boundary for the `power_win_mix` / `calc_Wr_lm` hot path of
+ * hsgg/SphericalFourierBesselDecompositions.jl (v0.5.19).  The reference has no FFI layer of its own
+ * (100 % Julia); these entry points are what thin Julia method bodies `ccall` (see INTEGRATION.md and
+ * julia/SFBB200.jl).  Citations are file:line in the reference checkout.
+ *
+ * Conventions
+ *   - every function returns 0 on success; nonzero => sfb_last_error() holds the message
+ *     (the Julia shim rethrows it as ErrorException, mirroring error()/@assert at
+ *     src/windows.jl:803,1013 and src/healpix_helpers.jl:60-63)
+ *   - all arrays are column-major (Julia), Int64 indices, Float64 / ComplexF64 (interleaved re,im)
+ *   - the caller owns every buffer; nothing is retained past return (wrap calls in GC.@preserve)
+ *   - functions without `_dev` take HOST pointers and do their own H2D/D2H;
+ *     `_dev` functions take DEVICE pointers on the current device and a cudaStream_t passed as void*
+ *   - the library never falls back to a CPU path: without a CUDA device every compute call fails
+ */
+#ifndef SFB_B200_H
+#define SFB_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SFB_B200_VERSION 100
+
+/* Wr_lm column orders (src/LMcalcStructs.jl:7-26) */
+#define SFB_LAYOUT_MMAJOR 0 /* HEALPix order, what calc_Wr_lm returns        (LMcalcStruct)      */
+#define SFB_LAYOUT_MFAST 1  /* what optimize_Wr_lm_layout returns             (LMcalcStructMfast) */
+
+typedef struct sfb_sht_plan sfb_sht_plan;   /* stage 1: ring tables, Legendre tables, workspaces */
+typedef struct sfb_cmix_plan sfb_cmix_plan; /* stage 2+3: mode tables, radial basis, 3j table     */
+
+/* ---- housekeeping ------------------------------------------------------------------------------ */
+int32_t sfb_version(void);
+const char* sfb_last_error(void);
+int32_t sfb_device_count(int32_t* count);
+int32_t sfb_set_device(int32_t device);
+/* times (ms, CUDA events) of the last call on this thread's plans:
+ *   [0] stage 1 total, [1] W_{L1} build, [2] 3j table, [3] Ŵ_{ℓL} build, [4] block kernel,
+ *   [5] executed DMMA flops of [4], [6] kernel launches of the last power_win_mix, [7] binned products */
+int32_t sfb_get_timings(double* out, int32_t n);
+
+/* ---- host-pointer entry points (what the Julia methods ccall) ------------------------------- */
+
+/* calc_Wr_lm(win, LMAX, Wnside)                                       src/windows.jl:528-537
+ *   win  : nr x npix_in Float64, leading dimension ld_win (>= nr); shell i is the strided row win[i,:]
+ *   per shell: udgrade to nside_out (src/healpix_helpers.jl:40-45), then
+ *   Healpix.map2alm(lmax=mmax=lmax, niter, uniform weights 4π/npix)   src/healpix_helpers.jl:59-71
+ *   out  : nr x lmsize ComplexF64, lmsize=(lmax+1)(lmax+2)/2, columns in `layout` order
+ *   errors: lmax > 4*nside_out ("lmax > 4*nside is a poor choice", src/healpix_helpers.jl:60-63)   */
+int32_t sfb_calc_wr_lm(const double* win, int64_t nr, int64_t npix_in, int64_t ld_win, int64_t nside_out,
+                       int64_t lmax, int64_t niter, int32_t layout, double* out);
+
+/* calc_Wr_lm(win::SeparableArray, LMAX, Wnside)                       src/windows.jl:540-545
+ *   one map2alm of the angular mask; out: lmsize ComplexF64 in m-major order (an `Alm`)            */
+int32_t sfb_calc_wlm_mask(const double* mask, int64_t npix_in, int64_t nside_out, int64_t lmax, int64_t niter,
+                          double* out);
+
+/* calc_Wrl_Wrl + calc_cmix given W_lm(r)                              src/windows.jl:682-746
+ *   w1r_lm, w2r_lm : nr x lmsize(LMAX) ComplexF64 in `layout` order; may alias (auto-correlation)
+ *   G              : rsdrgnlr, nr x nmax x (lmax+1) Float64 (NaN where n > nmax_l[l+1])  src/windows.jl:799
+ *   lnn            : 3 x lnnsize Int64 (ClnnModes.lnn, src/modes.jl:280-288), consumed as given
+ *   M_out          : (lnnsize-lnn_min+1)^2 Float64, [i,i'] = (l,n,n') row, (L,N,N') column         */
+int32_t sfb_power_win_mix_from_wrlm(const double* w1r_lm, const double* w2r_lm, int64_t nr, int64_t LMAX,
+                                    int32_t layout, const double* G, int64_t nmax, int64_t lmax,
+                                    const int64_t* lnn, int64_t lnnsize, int64_t lnn_min, int32_t div2Lp1,
+                                    int32_t interchange_NN, double* M_out);
+
+/* power_win_mix(win1, win2, wmodes, cmodes; div2Lp1, interchange_NN′, lnn_min)   src/windows.jl:781-805
+ *   win2 == NULL or win2 == win1 means win2 === win1.  nside = amodes.nside.                       */
+int32_t sfb_power_win_mix(const double* win1, const double* win2, int64_t nr, int64_t npix_in, int64_t ld_win,
+                          int64_t nside, const double* G, int64_t nmax, int64_t lmax, const int64_t* lnn,
+                          int64_t lnnsize, int64_t lnn_min, int32_t div2Lp1, int32_t interchange_NN,
+                          double* M_out);
+
+/* power_win_mix(win1, win2, w̃mat, vmat, wmodes, bcmodes; ...)         src/windows.jl:994-1015, 825-862
+ *   w̃ (LNN1 x lnnsize) and v (lnnsize x LNN2) as SparseMatrixCSC triplets (1-based colptr/rowval);
+ *   a NULL colptr stands for UniformScaling `I` (then LNN = lnnsize, src/windows.jl:829-830).
+ *   Like the reference (src/windows.jl:1005-1006) both transforms are taken from win1.
+ *   N_out : LNN1 x LNN2 Float64                                                                   */
+int32_t sfb_power_win_mix_binned(const double* win1, int64_t nr, int64_t npix_in, int64_t ld_win, int64_t nside,
+                                 const double* G, int64_t nmax, int64_t lmax, const int64_t* lnn,
+                                 int64_t lnnsize, const int64_t* wt_colptr, const int64_t* wt_rowval,
+                                 const double* wt_nzval, int64_t LNN1, const int64_t* v_colptr,
+                                 const int64_t* v_rowval, const double* v_nzval, int64_t LNN2, int32_t div2Lp1,
+                                 int32_t interchange_NN, double* N_out);
+
+/* separable window: power_win_mix(win1::SeparableArray, ..., w̃, v, ...)  src/windows.jl:809-814, 942-990
+ *   (calc_angular_mixing_matrix :866-878, calc_radial_mixing :924-938, calc_cmixii_separable :651-679)
+ *   phi : nr Float64, mask : npix_in Float64; binning arguments as above (NULL colptr = I)         */
+int32_t sfb_power_win_mix_separable(const double* phi, const double* mask, int64_t nr, int64_t npix_in,
+                                    int64_t nside, const double* G, int64_t nmax, int64_t lmax,
+                                    const int64_t* lnn, int64_t lnnsize, const int64_t* wt_colptr,
+                                    const int64_t* wt_rowval, const double* wt_nzval, int64_t LNN1,
+                                    const int64_t* v_colptr, const int64_t* v_rowval, const double* v_nzval,
+                                    int64_t LNN2, int32_t div2Lp1, int32_t interchange_NN, double* N_out);
+
+/* ---- device-resident entry points (plans; used for row-sharded multi-GPU runs and the bench) --- */
+
+/* stage-1 plan for maps of nside_in transformed at nside_out with lmax, batches of up to nr shells */
+int32_t sfb_sht_plan_create(sfb_sht_plan** plan, int64_t nside_in, int64_t nside_out, int64_t lmax, int64_t nr);
+int32_t sfb_sht_plan_destroy(sfb_sht_plan* plan);
+/* number of doubles of the planar W_lm(r) buffer: lmsize * 2 * nrp, nrp = nr rounded up to 8 */
+int64_t sfb_sht_alm_doubles(const sfb_sht_plan* plan);
+/* d_win: device, [pixel][shell] with pixel stride ld_win (the Julia nr x npix array as is);
+ * d_alm: device planar W_lm(r) [lm (m-major)][re,im][nrp]                                          */
+int32_t sfb_calc_wr_lm_dev(sfb_sht_plan* plan, const double* d_win, int64_t ld_win, int64_t niter, double* d_alm,
+                           void* stream);
+/* planar device W_lm(r) -> nr x lmsize ComplexF64 (device) in `layout` order */
+int32_t sfb_alm_to_complex_dev(const sfb_sht_plan* plan, const double* d_alm, int32_t layout, double* d_out,
+                               void* stream);
+
+int32_t sfb_cmix_plan_create(sfb_cmix_plan** plan, const int64_t* lnn, int64_t lnnsize, int64_t lnn_min,
+                             const double* G, int64_t nr, int64_t nmax, int64_t lmax);
+int32_t sfb_cmix_plan_destroy(sfb_cmix_plan* plan);
+/* rows [row_lo,row_hi) (0-based) of M into d_M (column-major, leading dimension ldM >= row_hi-row_lo).
+ * d_alm2 == d_alm1 selects the auto-correlation path.                                              */
+int32_t sfb_power_win_mix_dev(sfb_cmix_plan* plan, const double* d_alm1, const double* d_alm2, int32_t div2Lp1,
+                              int32_t interchange_NN, int64_t row_lo, int64_t row_hi, double* d_M, int64_t ldM,
+                              void* stream);
+/* cost model used to balance row shards: cost[i] for each of the nout rows (host array) */
+int32_t sfb_cmix_row_costs(const sfb_cmix_plan* plan, double* cost, int64_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SFB_B200_H */

@@ -1,0 +1,347 @@
+// extern "C" entry points declared in include/sfb_b200.h.
+#include "../../include/sfb_b200.h"
+
+#include "binned.cuh"
+#include "cmix.cuh"
+#include "common.cuh"
+#include "sht.cuh"
+
+#include <cstring>
+#include <mutex>
+
+namespace sfb {
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+
+static std::mutex g_mutex;  // one call at a time (the Julia side calls from one task and blocks)
+static double g_times[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
+// ---- cached stage-1 plan (tables depend only on nside/lmax/nr) ----
+static ShtPlan* g_sht = nullptr;
+static int g_sht_dev = -1;
+static int get_sht_plan(ShtPlan** out, int64_t nside_in, int64_t nside_out, int64_t lmax, int64_t nr) {
+    int dev = 0;
+    SFB_CUDA_OK(cudaGetDevice(&dev));
+    if (g_sht && g_sht_dev == dev && g_sht->nside_in == nside_in && g_sht->nside == nside_out && g_sht->lmax == lmax &&
+        g_sht->nr == nr) {
+        *out = g_sht;
+        return 0;
+    }
+    if (g_sht) {
+        sht_plan_destroy(g_sht);
+        g_sht = nullptr;
+    }
+    SFB_TRY(sht_plan_create(&g_sht, nside_in, nside_out, lmax, nr));
+    g_sht_dev = dev;
+    *out = g_sht;
+    return 0;
+}
+
+static int npix2nside(int64_t npix, int64_t* nside) {
+    int64_t ns = (int64_t)llround(std::sqrt((double)npix / 12.0));
+    SFB_REQUIRE(ns >= 1 && 12 * ns * ns == npix, "npix is not 12*nside^2");
+    *nside = ns;
+    return 0;
+}
+
+// H2D of the Julia array win (nr x npix, leading dimension ld) -> device [pixel][nr]
+static int upload_win(const double* win, int64_t nr, int64_t npix, int64_t ld, DevBuf<double>& d) {
+    SFB_REQUIRE(win, "win is null");
+    SFB_REQUIRE(ld >= nr, "ld_win < nr");
+    SFB_TRY(d.alloc((size_t)nr * npix));
+    SFB_CUDA_OK(cudaMemcpy2D(d.p, nr * sizeof(double), win, ld * sizeof(double), nr * sizeof(double), npix,
+                             cudaMemcpyHostToDevice));
+    return 0;
+}
+
+__global__ void finite_check_kernel(const double* __restrict__ x, size_t n, int* flag) {
+    int bad = 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        bad |= !isfinite(x[i]);
+    if (bad) atomicOr(flag, 1);
+}
+
+static int check_finite(const double* d, size_t n, const char* what) {
+    DevBuf<int> flag;
+    SFB_TRY(flag.alloc(1));
+    SFB_CUDA_OK(cudaMemset(flag.p, 0, sizeof(int)));
+    finite_check_kernel<<<1024, 256>>>(d, n, flag.p);
+    int h = 0;
+    SFB_CUDA_OK(cudaMemcpy(&h, flag.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (h) {  // @assert all(isfinite.(mix))  src/windows.jl:803,1013
+        set_error(std::string("AssertionError: all(isfinite.(") + what + "))");
+        return 4;
+    }
+    return 0;
+}
+
+static void record_cmix_times(const CmixPlan* p) {
+    g_times[1] = p->t_wl;
+    g_times[2] = p->t_w3j;
+    g_times[3] = p->t_what;
+    g_times[4] = p->t_block;
+    g_times[5] = p->flops_executed;
+    g_times[6] += p->launches;
+}
+
+struct PlanGuard {
+    CmixPlan* p = nullptr;
+    ~PlanGuard() {
+        if (p) cmix_plan_destroy(p);
+    }
+};
+
+// W_lm(r) of one or two windows on the device (planar), shared by the end-to-end entry points
+static int windows_to_alm(const double* win1, const double* win2, int64_t nr, int64_t npix_in, int64_t ld_win,
+                          int64_t nside, int64_t LMAX, DevBuf<double>& alm1, DevBuf<double>& alm2, bool* same) {
+    int64_t nside_in = 0;
+    SFB_TRY(npix2nside(npix_in, &nside_in));
+    ShtPlan* sp = nullptr;
+    SFB_TRY(get_sht_plan(&sp, nside_in, nside, LMAX, nr));
+    const size_t nalm = sp->lmsize * 2 * sp->nrp;
+    DevBuf<double> d_win;
+    SFB_TRY(upload_win(win1, nr, npix_in, ld_win, d_win));
+    SFB_TRY(alm1.alloc(nalm));
+    SFB_TRY(sht_map2alm(sp, d_win.p, nr, 3, alm1.p, 0));
+    g_times[0] = sp->t_total;
+    g_times[6] = sp->launches;
+    *same = (win2 == nullptr || win2 == win1);
+    if (!*same) {
+        SFB_TRY(upload_win(win2, nr, npix_in, ld_win, d_win));
+        SFB_TRY(alm2.alloc(nalm));
+        SFB_TRY(sht_map2alm(sp, d_win.p, nr, 3, alm2.p, 0));
+        g_times[0] += sp->t_total;
+        g_times[6] += sp->launches;
+    }
+    return 0;
+}
+}  // namespace sfb
+
+using namespace sfb;
+
+extern "C" {
+
+int32_t sfb_version(void) { return SFB_B200_VERSION; }
+const char* sfb_last_error(void) { return g_err.c_str(); }
+
+int32_t sfb_device_count(int32_t* count) {
+    SFB_REQUIRE(count, "count is null");
+    int n = 0;
+    SFB_CUDA_OK(cudaGetDeviceCount(&n));
+    *count = n;
+    return 0;
+}
+
+int32_t sfb_set_device(int32_t device) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    SFB_CUDA_OK(cudaSetDevice(device));
+    return 0;
+}
+
+int32_t sfb_get_timings(double* out, int32_t n) {
+    SFB_REQUIRE(out && n >= 0, "bad arguments");
+    for (int i = 0; i < n && i < 8; ++i) out[i] = g_times[i];
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+int32_t sfb_calc_wr_lm(const double* win, int64_t nr, int64_t npix_in, int64_t ld_win, int64_t nside_out,
+                       int64_t lmax, int64_t niter, int32_t layout, double* out) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    SFB_REQUIRE(win && out, "null pointer");
+    SFB_REQUIRE(nr >= 1, "nr < 1");
+    SFB_REQUIRE(layout == 0 || layout == 1, "bad layout");
+    int64_t nside_in = 0;
+    SFB_TRY(npix2nside(npix_in, &nside_in));
+    ShtPlan* sp = nullptr;
+    SFB_TRY(get_sht_plan(&sp, nside_in, nside_out, lmax, nr));
+    DevBuf<double> d_win, d_alm, d_out;
+    SFB_TRY(upload_win(win, nr, npix_in, ld_win, d_win));
+    SFB_TRY(d_alm.alloc(sp->lmsize * 2 * sp->nrp));
+    SFB_TRY(d_out.alloc(sp->lmsize * 2 * nr));
+    SFB_TRY(sht_map2alm(sp, d_win.p, nr, (int)niter, d_alm.p, 0));
+    g_times[0] = sp->t_total;
+    g_times[6] = sp->launches;
+    SFB_TRY(sht_alm_to_complex(sp, d_alm.p, layout, d_out.p, 0));
+    SFB_CUDA_OK(cudaMemcpy(out, d_out.p, sp->lmsize * 2 * nr * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int32_t sfb_calc_wlm_mask(const double* mask, int64_t npix_in, int64_t nside_out, int64_t lmax, int64_t niter,
+                          double* out) {
+    return sfb_calc_wr_lm(mask, 1, npix_in, 1, nside_out, lmax, niter, SFB_LAYOUT_MMAJOR, out);
+}
+
+int32_t sfb_power_win_mix_from_wrlm(const double* w1r_lm, const double* w2r_lm, int64_t nr, int64_t LMAX,
+                                    int32_t layout, const double* G, int64_t nmax, int64_t lmax,
+                                    const int64_t* lnn, int64_t lnnsize, int64_t lnn_min, int32_t div2Lp1,
+                                    int32_t interchange_NN, double* M_out) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    SFB_REQUIRE(w1r_lm && M_out, "null pointer");
+    SFB_REQUIRE(LMAX == 2 * lmax, "LMAX must equal 2*lmax (src/windows.jl:788)");
+    SFB_REQUIRE(layout == 0 || layout == 1, "bad layout");
+    PlanGuard pg;
+    SFB_TRY(cmix_plan_create(&pg.p, lnn, lnnsize, lnn_min, G, nr, nmax, lmax));
+    DevBuf<double> a1, a2, dM;
+    SFB_TRY(alm_from_host(w1r_lm, nr, (int)LMAX, layout, a1, pg.p->nrp, 0));
+    const bool same = (w2r_lm == nullptr || w2r_lm == w1r_lm);
+    if (!same) SFB_TRY(alm_from_host(w2r_lm, nr, (int)LMAX, layout, a2, pg.p->nrp, 0));
+    const int64_t n = pg.p->nout;
+    SFB_TRY(dM.alloc((size_t)n * n));
+    g_times[0] = 0;
+    g_times[6] = 0;
+    SFB_TRY(cmix_run(pg.p, a1.p, same ? a1.p : a2.p, div2Lp1, interchange_NN, 0, n, dM.p, n, 0));
+    record_cmix_times(pg.p);
+    SFB_TRY(check_finite(dM.p, (size_t)n * n, "mix"));
+    SFB_CUDA_OK(cudaMemcpy(M_out, dM.p, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int32_t sfb_power_win_mix(const double* win1, const double* win2, int64_t nr, int64_t npix_in, int64_t ld_win,
+                          int64_t nside, const double* G, int64_t nmax, int64_t lmax, const int64_t* lnn,
+                          int64_t lnnsize, int64_t lnn_min, int32_t div2Lp1, int32_t interchange_NN,
+                          double* M_out) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    SFB_REQUIRE(win1 && M_out, "null pointer");
+    PlanGuard pg;
+    SFB_TRY(cmix_plan_create(&pg.p, lnn, lnnsize, lnn_min, G, nr, nmax, lmax));
+    DevBuf<double> a1, a2, dM;
+    bool same = true;
+    SFB_TRY(windows_to_alm(win1, win2, nr, npix_in, ld_win, nside, 2 * lmax, a1, a2, &same));
+    const int64_t n = pg.p->nout;
+    SFB_TRY(dM.alloc((size_t)n * n));
+    SFB_TRY(cmix_run(pg.p, a1.p, same ? a1.p : a2.p, div2Lp1, interchange_NN, 0, n, dM.p, n, 0));
+    record_cmix_times(pg.p);
+    SFB_TRY(check_finite(dM.p, (size_t)n * n, "mix"));
+    SFB_CUDA_OK(cudaMemcpy(M_out, dM.p, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int32_t sfb_power_win_mix_binned(const double* win1, int64_t nr, int64_t npix_in, int64_t ld_win, int64_t nside,
+                                 const double* G, int64_t nmax, int64_t lmax, const int64_t* lnn,
+                                 int64_t lnnsize, const int64_t* wt_colptr, const int64_t* wt_rowval,
+                                 const double* wt_nzval, int64_t LNN1, const int64_t* v_colptr,
+                                 const int64_t* v_rowval, const double* v_nzval, int64_t LNN2, int32_t div2Lp1,
+                                 int32_t interchange_NN, double* N_out) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    SFB_REQUIRE(win1 && N_out, "null pointer");
+    PlanGuard pg;
+    SFB_TRY(cmix_plan_create(&pg.p, lnn, lnnsize, 1, G, nr, nmax, lmax));
+    DevBuf<double> a1, a2, dM;
+    bool same = true;
+    // like the reference, W2r_lm is computed from win1 as well (src/windows.jl:1005-1006)
+    SFB_TRY(windows_to_alm(win1, nullptr, nr, npix_in, ld_win, nside, 2 * lmax, a1, a2, &same));
+    const int64_t n = pg.p->nout;
+    SFB_TRY(dM.alloc((size_t)n * n));
+    SFB_TRY(cmix_run(pg.p, a1.p, a1.p, div2Lp1, interchange_NN, 0, n, dM.p, n, 0));
+    record_cmix_times(pg.p);
+    float t_bin = 0;
+    SFB_TRY(binned_product_to_host(dM.p, n, wt_colptr, wt_rowval, wt_nzval, LNN1, v_colptr, v_rowval, v_nzval, LNN2,
+                                   N_out, &t_bin));
+    g_times[7] = t_bin;
+    return 0;
+}
+
+int32_t sfb_power_win_mix_separable(const double* phi, const double* mask, int64_t nr, int64_t npix_in,
+                                    int64_t nside, const double* G, int64_t nmax, int64_t lmax,
+                                    const int64_t* lnn, int64_t lnnsize, const int64_t* wt_colptr,
+                                    const int64_t* wt_rowval, const double* wt_nzval, int64_t LNN1,
+                                    const int64_t* v_colptr, const int64_t* v_rowval, const double* v_nzval,
+                                    int64_t LNN2, int32_t div2Lp1, int32_t interchange_NN, double* N_out) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    SFB_REQUIRE(phi && mask && N_out, "null pointer");
+    int64_t nside_in = 0;
+    SFB_TRY(npix2nside(npix_in, &nside_in));
+    PlanGuard pg;
+    SFB_TRY(cmix_plan_create(&pg.p, lnn, lnnsize, 1, G, nr, nmax, lmax));
+    // one map2alm of the mask (src/windows.jl:540-545)
+    ShtPlan* sp = nullptr;
+    SFB_TRY(get_sht_plan(&sp, nside_in, nside, 2 * lmax, 1));
+    DevBuf<double> d_mask, d_wlm, dM;
+    SFB_TRY(upload_win(mask, 1, npix_in, 1, d_mask));
+    SFB_TRY(d_wlm.alloc(sp->lmsize * 2 * sp->nrp));
+    SFB_TRY(sht_map2alm(sp, d_mask.p, 1, 3, d_wlm.p, 0));
+    g_times[0] = sp->t_total;
+    g_times[6] = sp->launches;
+    const int64_t n = pg.p->nout;
+    SFB_TRY(dM.alloc((size_t)n * n));
+    SFB_TRY(separable_cmix(pg.p, d_wlm.p, sp->nrp, phi, div2Lp1, interchange_NN, dM.p));
+    SFB_TRY(check_finite(dM.p, (size_t)n * n, "mix"));
+    float t_bin = 0;
+    SFB_TRY(binned_product_to_host(dM.p, n, wt_colptr, wt_rowval, wt_nzval, LNN1, v_colptr, v_rowval, v_nzval, LNN2,
+                                   N_out, &t_bin));
+    g_times[7] = t_bin;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-resident API
+
+int32_t sfb_sht_plan_create(sfb_sht_plan** plan, int64_t nside_in, int64_t nside_out, int64_t lmax, int64_t nr) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    return sht_plan_create(reinterpret_cast<ShtPlan**>(plan), nside_in, nside_out, lmax, nr);
+}
+int32_t sfb_sht_plan_destroy(sfb_sht_plan* plan) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    sht_plan_destroy(reinterpret_cast<ShtPlan*>(plan));
+    return 0;
+}
+int64_t sfb_sht_alm_doubles(const sfb_sht_plan* plan) {
+    const auto* p = reinterpret_cast<const ShtPlan*>(plan);
+    return p ? (int64_t)(p->lmsize * 2 * p->nrp) : 0;
+}
+int32_t sfb_calc_wr_lm_dev(sfb_sht_plan* plan, const double* d_win, int64_t ld_win, int64_t niter, double* d_alm,
+                           void* stream) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    auto* p = reinterpret_cast<ShtPlan*>(plan);
+    SFB_TRY(sht_map2alm(p, d_win, ld_win, (int)niter, d_alm, (cudaStream_t)stream));
+    g_times[0] = p->t_total;
+    g_times[6] = p->launches;
+    return 0;
+}
+int32_t sfb_alm_to_complex_dev(const sfb_sht_plan* plan, const double* d_alm, int32_t layout, double* d_out,
+                               void* stream) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    return sht_alm_to_complex(reinterpret_cast<const ShtPlan*>(plan), d_alm, layout, d_out, (cudaStream_t)stream);
+}
+
+int32_t sfb_cmix_plan_create(sfb_cmix_plan** plan, const int64_t* lnn, int64_t lnnsize, int64_t lnn_min,
+                             const double* G, int64_t nr, int64_t nmax, int64_t lmax) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    return cmix_plan_create(reinterpret_cast<CmixPlan**>(plan), lnn, lnnsize, lnn_min, G, nr, nmax, lmax);
+}
+int32_t sfb_cmix_plan_destroy(sfb_cmix_plan* plan) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    cmix_plan_destroy(reinterpret_cast<CmixPlan*>(plan));
+    return 0;
+}
+int32_t sfb_power_win_mix_dev(sfb_cmix_plan* plan, const double* d_alm1, const double* d_alm2, int32_t div2Lp1,
+                              int32_t interchange_NN, int64_t row_lo, int64_t row_hi, double* d_M, int64_t ldM,
+                              void* stream) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    auto* p = reinterpret_cast<CmixPlan*>(plan);
+    const double t0 = g_times[6];
+    SFB_TRY(cmix_run(p, d_alm1, d_alm2, div2Lp1, interchange_NN, row_lo, row_hi, d_M, ldM, (cudaStream_t)stream));
+    record_cmix_times(p);
+    g_times[6] = t0 + p->launches;
+    return 0;
+}
+int32_t sfb_cmix_row_costs(const sfb_cmix_plan* plan, double* cost, int64_t n) {
+    const auto* p = reinterpret_cast<const CmixPlan*>(plan);
+    SFB_REQUIRE(p && cost && n == p->nout, "sfb_cmix_row_costs: bad arguments");
+    for (int l = 0; l <= p->lmax; ++l) {
+        const int rows = p->ell_ptr[l + 1] - p->ell_ptr[l];
+        if (!rows) continue;
+        const double ap = 8.0 * ((p->a_of_ell[l] + 7) / 8);
+        double c = 0;
+        for (int L = 0; L <= p->lmax; ++L) {
+            const double b = p->a_of_ell[L];
+            c += 2.0 * ap * p->nrp * p->nrp * b + 2.0 * ap * ap * p->nrp * b * (b + 1) / 2 +
+                 2.0 * p->nrp * p->nrp * (std::min(l, L) + 1);
+        }
+        for (int s = p->ell_ptr[l]; s < p->ell_ptr[l + 1]; ++s) cost[p->h_row_out[s]] = c / rows;
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,64 @@
+// Stage 2+3 of the window coupling matrix on sm_100a (FP64, DMMA).
+//
+// Replaces (reference hsgg/SphericalFourierBesselDecompositions.jl):
+//   calc_Wrl_Wrl        src/windows.jl:682-696   -> wl_build_kernel
+//   wigner3j000         src/windows.jl:421-431   -> w3j000sq_table_kernel (warp-cooperative recursion)
+//   calc_cmixlnnLNN!    src/windows.jl:613-627   -> what_build_kernel + cmix_block_kernel
+//   calc_cmix           src/windows.jl:700-746   -> cmix_block_kernel epilogue (N<->N' partner, flags)
+//   _power_win_mix      src/windows.jl:825-862   -> csr/csc products in binned.cu
+#pragma once
+#include "common.cuh"
+#include <vector>
+
+namespace sfb {
+
+struct CmixPlan {
+    // problem sizes
+    int lmax = 0, nmax = 0, LMAX = 0;
+    int nr = 0, nrp = 0, S = 0;  // shells, padded to 8, smem row stride (≡ 4 mod 16)
+    int64_t lnnsize = 0;         // size of the caller's lnn table
+    int64_t nout = 0;            // lnnsize - lnn_min + 1 : rows == cols of M
+    int64_t lnn_min = 1;
+    int nl = 0;                  // number of (L,N) pairs with a column
+    int amax_tiles = 0;
+
+    // host tables
+    std::vector<int> a_of_ell;        // max n (1-based) used by rows/cols of this ell, 0 if none
+    std::vector<int> ell_ptr;         // CSR over ell -> rows
+    std::vector<int> h_row_out, h_row_n, h_row_n2;
+
+    // device tables
+    DevBuf<double> d_G;               // [ell][n][nrp]
+    DevBuf<int> d_ell_ptr, d_row_out, d_row_n, d_row_n2, d_a;
+    DevBuf<int> d_pairidx;            // [L][N][N'] -> output column or -1
+    DevBuf<int> d_nl_L, d_nl_N;       // grid.x -> (L, N)
+    DevBuf<double> d_w2;              // [(lmax+1)^2][lmax+1] squared 3j symbols
+    DevBuf<double> d_W;               // [LMAX+1][nrp][nrp]
+    DevBuf<double> d_What;            // [ell chunk][L][nrp][nrp]
+    DevBuf<int> d_ell_list;           // per-launch list of ells
+    size_t what_budget_bytes = size_t(2) << 30;
+
+    // last-run stage times (ms): wl, w3j, what, block
+    float t_wl = 0, t_w3j = 0, t_what = 0, t_block = 0;
+    double flops_executed = 0;
+    int launches = 0;
+};
+
+// Build the plan from the caller's tables (host pointers).
+//   lnn: 3 x lnnsize Int64, column-major (Julia Matrix{Int}), 1-based n
+//   G:   nr x nmax x (lmax+1) Float64 column-major (rsdrgnlr, NaN where n > nmax_l)
+int cmix_plan_create(CmixPlan** out, const int64_t* lnn, int64_t lnnsize, int64_t lnn_min, const double* G,
+                     int64_t nr, int64_t nmax, int64_t lmax);
+void cmix_plan_destroy(CmixPlan* p);
+
+// alm layout (device): planar [lm (m-major, lmax2 = 2*lmax)][comp (re,im)][nrp], padded shells zero.
+// Writes rows [row_lo,row_hi) (0-based, of the nout x nout matrix) into d_M (column-major, leading dim ldM,
+// row row_lo at offset 0).
+int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp1, int interchange,
+             int64_t row_lo, int64_t row_hi, double* d_M, int64_t ldM, cudaStream_t stream);
+
+// Host complex (nr x lmsize, column-major, interleaved) -> device planar alm; layout 0 = m-major, 1 = m-fast.
+int alm_from_host(const double* h_wrlm, int64_t nr, int lmax2, int layout, DevBuf<double>& d_alm, int nrp,
+                  cudaStream_t stream);
+
+}  // namespace sfb

@@ -1,0 +1,641 @@
+// Stage 1 kernels: batched HEALPix ring transforms.  See sht.cuh for the reference functions replaced.
+//
+// Every step is a real GEMM whose N dimension is the shell batch, run on DMMA:
+//   ring analysis   F_m(ring)[c]   = Σ_j  e^{-imφ_j} f_j[shell]          A = twiddles (generated), B = map
+//   Legendre anal.  a_lm[c]        = w Σ_k λ_lm(θ_k) (F_N ± F_S)_m[k][c]  A = λ table,  B = F (parity-combined)
+//   Legendre synth. G_m(ring)[c]   = Σ_l λ_lm(θ_k) a_lm[c]  (E ± O)       A = λᵀ,       B = alm
+//   ring synthesis  f_j[shell]     = Σ_m (2-δ_m0) Re(G_m e^{imφ_j})       A = twiddles, B = G   (+ residual map - f)
+// c = comp*nrp + shell (re plane, then im plane).
+#include "sht.cuh"
+
+#include <cmath>
+
+namespace sfb {
+
+constexpr int kT = 256;      // threads per CTA (8 warps as 4 x 2 over a 64 x 64 tile)
+constexpr int kLdA = 36;     // 32 + 4  (≡ 4 mod 16)
+constexpr int kLdB = 68;     // 64 + 4  (≡ 4 mod 16)
+
+__device__ __forceinline__ size_t lm_mmajor(int lmax, int l, int m) {
+    return (size_t)l + ((size_t)m * (2 * lmax + 1 - m)) / 2;
+}
+
+// ---------------------------------------------------------------------------------------------
+// setup kernels
+
+__global__ void twiddle_table_kernel(double2* __restrict__ tw, int nside) {
+    // block i-1 of the table: ring length nφ = 4i, entries t in [0, 8i) at offset 4i(i-1)
+    const int i = blockIdx.x + 1;
+    double2* dst = tw + (size_t)4 * i * (i - 1);
+    for (int t = threadIdx.x; t < 8 * i; t += blockDim.x) {
+        double s, c;
+        sincospi((double)t / (double)(4 * i), &s, &c);
+        dst[t] = make_double2(c, s);
+    }
+}
+
+__device__ __forceinline__ void ring_z_sth(int nside, int k /*0-based north ring*/, double& z, double& sth) {
+    const int i = k + 1;
+    if (i < nside) {
+        const double omz = (double)i * i / (3.0 * nside * nside);
+        z = 1.0 - omz;
+        sth = sqrt(omz * (1.0 + z));
+    } else {
+        z = (2 * nside - i) * 2.0 / (3.0 * nside);
+        sth = sqrt((1.0 - z) * (1.0 + z));
+    }
+}
+
+// λ_lm(θ_k) for the northern rings (incl. equator); thread = (ring k, m), sequential three-term recurrence in l.
+__global__ void lambda_table_kernel(double* __restrict__ lam, int nside, int lmax, int nhalf) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int m = blockIdx.y;
+    if (k >= nhalf) return;
+    double z, sth;
+    ring_z_sth(nside, k, z, sth);
+    double lmm = 0.28209479177387814;  // sqrt(1/(4π))
+    for (int mm = 1; mm <= m; ++mm) lmm = -lmm * sth * sqrt((2.0 * mm + 1.0) / (2.0 * mm));
+    lam[lm_mmajor(lmax, m, m) * nhalf + k] = lmm;
+    if (m == lmax) return;
+    double l2 = lmm, l1 = z * sqrt(2.0 * m + 3.0) * lmm;
+    lam[lm_mmajor(lmax, m + 1, m) * nhalf + k] = l1;
+    const double m2 = (double)m * m;
+    for (int l = m + 2; l <= lmax; ++l) {
+        const double a = sqrt((4.0 * l * l - 1.0) / ((double)l * l - m2));
+        const double b = sqrt(((l - 1.0) * (l - 1.0) - m2) / (4.0 * (l - 1.0) * (l - 1.0) - 1.0));
+        const double ln = a * (z * l1 - b * l2);
+        lam[lm_mmajor(lmax, l, m) * nhalf + k] = ln;
+        l2 = l1;
+        l1 = ln;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// udgrade via the NESTED scheme
+
+__device__ __constant__ int c_jrll[12] = {2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4};
+__device__ __constant__ int c_jpll[12] = {1, 3, 5, 7, 0, 2, 4, 6, 1, 3, 5, 7};
+
+__device__ __forceinline__ unsigned spread_bits(unsigned v) {
+    v = (v | (v << 8)) & 0x00FF00FFu;
+    v = (v | (v << 4)) & 0x0F0F0F0Fu;
+    v = (v | (v << 2)) & 0x33333333u;
+    v = (v | (v << 1)) & 0x55555555u;
+    return v;
+}
+__device__ __forceinline__ unsigned compress_bits(unsigned v) {
+    v &= 0x55555555u;
+    v = (v | (v >> 1)) & 0x33333333u;
+    v = (v | (v >> 2)) & 0x0F0F0F0Fu;
+    v = (v | (v >> 4)) & 0x00FF00FFu;
+    v = (v | (v >> 8)) & 0x0000FFFFu;
+    return v;
+}
+__device__ __forceinline__ int isqrt_ll(long long v) {
+    long long r = (long long)sqrt((double)v + 0.5);
+    while (r * r > v) --r;
+    while ((r + 1) * (r + 1) <= v) ++r;
+    return (int)r;
+}
+
+__device__ long long ring2nest_dev(int nside, long long pix) {
+    const long long ncap = 2LL * nside * (nside - 1), npix = 12LL * nside * nside;
+    const int nl2 = 2 * nside;
+    int iring, iphi, kshift, nr, face;
+    if (pix < ncap) {
+        iring = (1 + isqrt_ll(1 + 2 * pix)) >> 1;
+        iphi = (int)(pix + 1 - 2LL * iring * (iring - 1));
+        kshift = 0;
+        nr = iring;
+        face = (iphi - 1) / nr;
+    } else if (pix < npix - ncap) {
+        const long long ip = pix - ncap;
+        const int tmp = (int)(ip / (4 * nside));
+        iring = tmp + nside;
+        iphi = (int)(ip - (long long)tmp * 4 * nside) + 1;
+        kshift = (iring + nside) & 1;
+        nr = nside;
+        const int ire = tmp + 1, irm = nl2 + 1 - tmp;
+        const int ifm = (iphi - ire / 2 + nside - 1) / nside;
+        const int ifp = (iphi - irm / 2 + nside - 1) / nside;
+        face = (ifp == ifm) ? (ifp | 4) : ((ifp < ifm) ? ifp : (ifm + 8));
+    } else {
+        const long long ip = npix - pix;
+        iring = (1 + isqrt_ll(2 * ip - 1)) >> 1;
+        iphi = 4 * iring + 1 - (int)(ip - 2LL * iring * (iring - 1));
+        kshift = 0;
+        nr = iring;
+        iring = 2 * nl2 - iring;
+        face = 8 + (iphi - 1) / nr;
+    }
+    const int irt = iring - c_jrll[face] * nside + 1;
+    int ipt = 2 * iphi - c_jpll[face] * nr - kshift - 1;
+    if (ipt >= nl2) ipt -= 8 * nside;
+    const int ix = (ipt - irt) >> 1, iy = (-ipt - irt) >> 1;
+    return (long long)face * nside * nside + (spread_bits((unsigned)ix) | (spread_bits((unsigned)iy) << 1));
+}
+
+__device__ long long nest2ring_dev(int nside, long long ipnest) {
+    const long long npface = (long long)nside * nside, npix = 12 * npface, ncap = 2LL * nside * (nside - 1);
+    const int nl4 = 4 * nside;
+    const int face = (int)(ipnest / npface);
+    const unsigned ipf = (unsigned)(ipnest % npface);
+    const int ix = (int)compress_bits(ipf), iy = (int)compress_bits(ipf >> 1);
+    const int jrt = ix + iy, jpt = ix - iy;
+    const int jr = c_jrll[face] * nside - jrt - 1;
+    int nr, kshift;
+    long long n_before;
+    if (jr < nside) {
+        nr = jr;
+        n_before = 2LL * nr * (nr - 1);
+        kshift = 0;
+    } else if (jr > 3 * nside) {
+        nr = nl4 - jr;
+        n_before = npix - 2LL * (nr + 1) * nr;
+        kshift = 0;
+    } else {
+        nr = nside;
+        n_before = ncap + (long long)(jr - nside) * nl4;
+        kshift = (jr - nside) & 1;
+    }
+    int jp = (c_jpll[face] * nr + jpt + 1 + kshift) / 2;
+    if (jp > nl4) jp -= nl4;
+    if (jp < 1) jp += nl4;
+    return n_before + jp - 1;
+}
+
+// out[pix_out][shell] (stride nrp, padded shells zeroed) from in[pix_in][shell] (stride ldw)
+__global__ void udgrade_kernel(const double* __restrict__ in, long long ldw, int nside_in, double* __restrict__ out,
+                               int nside_out, int nr, int nrp) {
+    const long long npix_out = 12LL * nside_out * nside_out;
+    const long long total = npix_out * nrp;
+    for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < total;
+         x += (long long)gridDim.x * blockDim.x) {
+        const long long po = x / nrp;
+        const int sh = (int)(x - po * nrp);
+        double v = 0.0;
+        if (sh < nr) {
+            const long long nest_o = ring2nest_dev(nside_out, po);
+            if (nside_out >= nside_in) {
+                const long long ratio = (long long)(nside_out / nside_in) * (nside_out / nside_in);
+                v = in[nest2ring_dev(nside_in, nest_o / ratio) * ldw + sh];
+            } else {
+                const long long ratio = (long long)(nside_in / nside_out) * (nside_in / nside_out);
+                double s = 0.0;
+                for (long long c = 0; c < ratio; ++c) s += in[nest2ring_dev(nside_in, nest_o * ratio + c) * ldw + sh];
+                v = s / (double)ratio;
+            }
+        }
+        out[x] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+struct RingTabs {
+    const int* nphi;
+    const int* start;
+    const int* shift;
+    const int* twoff;
+    const double2* tw;
+};
+
+// F[m][ring][c] = Σ_j e^{-imφ_j} f_j      CTA = (ring, 32 m's, 64 shells); rows 0-31 -> Re, 32-63 -> Im
+__global__ void __launch_bounds__(kT) ring_analysis_kernel(const double* __restrict__ map, long long ldw, int nr, int nrp,
+                                                           RingTabs rt, int nrings, int lmax, double* __restrict__ F) {
+    __shared__ double As[64 * kLdA];
+    __shared__ double Bs[32 * kLdB];
+    const int ring = blockIdx.x, m0 = blockIdx.y * 32, sh0 = blockIdx.z * 64;
+    const int nphi = rt.nphi[ring], start = rt.start[ring], s = rt.shift[ring];
+    const double2* tw = rt.tw + rt.twoff[ring];
+    const unsigned two_nphi = 2u * nphi;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int wm = warp >> 1, wn = warp & 1;
+    double acc[2][4][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    for (int j0 = 0; j0 < nphi; j0 += 32) {
+        {
+            const int kk = tid & 31, j = j0 + kk;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int mrow = (tid >> 5) + 8 * q, m = m0 + mrow;
+                double c = 0.0, sn = 0.0;
+                if (j < nphi && m <= lmax) {
+                    const unsigned tt = ((unsigned)m * (unsigned)(2 * j + s)) % two_nphi;
+                    const double2 w = tw[tt];
+                    c = w.x;
+                    sn = -w.y;
+                }
+                As[mrow * kLdA + kk] = c;
+                As[(mrow + 32) * kLdA + kk] = sn;
+            }
+            const int c = tid & 63;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int k2 = (tid >> 6) + 4 * q;
+                double v = 0.0;
+                if (j0 + k2 < nphi && sh0 + c < nr) v = map[(size_t)(start + j0 + k2) * ldw + sh0 + c];
+                Bs[k2 * kLdB + c] = v;
+            }
+        }
+        __syncthreads();
+        warp_gemm_ss<2, 4>(acc, As + wm * 16 * kLdA, kLdA, Bs + wn * 32, kLdB, 32);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int row = wm * 16 + i * 8 + g;
+        const int m = m0 + (row & 31), comp = row >> 5;
+        if (m > lmax) continue;
+        double* dst = F + ((size_t)m * nrings + ring) * 2 * nrp + (size_t)comp * nrp + sh0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int col = wn * 32 + j * 8 + 2 * t;
+            if (sh0 + col < nrp) {
+                dst[col] = acc[i][j][0];
+                dst[col + 1] = acc[i][j][1];
+            }
+        }
+    }
+}
+
+// f_j = Σ_m (2-δ_m0) (Re G_m cos mφ_j - Im G_m sin mφ_j);  out = residual ? map - f : f
+// CTA = (tile = (ring, 64 pixels), 64 shells)
+__global__ void __launch_bounds__(kT) ring_synthesis_kernel(const double* __restrict__ G, RingTabs rt,
+                                                            const int* __restrict__ tile_ring,
+                                                            const int* __restrict__ tile_j0, int nrings, int lmax,
+                                                            int nr, int nrp, const double* __restrict__ map,
+                                                            long long ldw, int residual, double* __restrict__ out) {
+    __shared__ double As[64 * kLdA];
+    __shared__ double Bs[32 * kLdB];
+    const int ring = tile_ring[blockIdx.x], j0 = tile_j0[blockIdx.x], sh0 = blockIdx.y * 64;
+    const int nphi = rt.nphi[ring], start = rt.start[ring], s = rt.shift[ring];
+    const double2* tw = rt.tw + rt.twoff[ring];
+    const unsigned two_nphi = 2u * nphi;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int wm = warp >> 1, wn = warp & 1;
+    double acc[2][4][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    for (int m0 = 0; m0 <= lmax; m0 += 16) {
+        {
+            const int row = tid & 63, j = j0 + row;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int mm = (tid >> 6) + 4 * q, m = m0 + mm;
+                double c = 0.0, sn = 0.0;
+                if (j < nphi && m <= lmax) {
+                    const unsigned tt = ((unsigned)m * (unsigned)(2 * j + s)) % two_nphi;
+                    const double2 w = tw[tt];
+                    const double cm = (m == 0) ? 1.0 : 2.0;
+                    c = cm * w.x;
+                    sn = -cm * w.y;
+                }
+                As[row * kLdA + mm] = c;
+                As[row * kLdA + 16 + mm] = sn;
+            }
+            const int c = tid & 63;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int k2 = (tid >> 6) + 4 * q;
+                const int m = m0 + (k2 & 15), part = k2 >> 4;
+                double v = 0.0;
+                if (m <= lmax && sh0 + c < nrp) v = G[((size_t)m * nrings + ring) * 2 * nrp + (size_t)part * nrp + sh0 + c];
+                Bs[k2 * kLdB + c] = v;
+            }
+        }
+        __syncthreads();
+        warp_gemm_ss<2, 4>(acc, As + wm * 16 * kLdA, kLdA, Bs + wn * 32, kLdB, 32);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int j = j0 + wm * 16 + i * 8 + g;
+        if (j >= nphi) continue;
+        const size_t pix = (size_t)start + j;
+#pragma unroll
+        for (int jn = 0; jn < 4; ++jn) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int sh = sh0 + wn * 32 + jn * 8 + 2 * t + e;
+                if (sh >= nrp) continue;
+                double v = 0.0;
+                if (sh < nr) {
+                    v = acc[i][jn][e];
+                    if (residual) v = map[pix * ldw + sh] - v;
+                }
+                out[pix * nrp + sh] = v;
+            }
+        }
+    }
+}
+
+// a_lm[c] (+)= w Σ_k λ_lm(θ_k) (F_N ± F_S)[k][c]   CTA = (m, 64 columns, 64 l's: 32 of each parity)
+__global__ void __launch_bounds__(kT) legendre_analysis_kernel(const double* __restrict__ F,
+                                                               const double* __restrict__ lam, int nrings, int nhalf,
+                                                               int lmax, int nrp, double w, int accumulate,
+                                                               double* __restrict__ alm) {
+    extern __shared__ double la_smem[];
+    double* As = la_smem;              // [64][kLdA]
+    double* Bp = As + 64 * kLdA;       // [32][kLdB]  F_N + F_S
+    double* Bm = Bp + 32 * kLdB;       // [32][kLdB]  F_N - F_S
+    const int m = blockIdx.x, c0 = blockIdx.y * 64, l0 = m + blockIdx.z * 64;
+    if (l0 > lmax) return;
+    const int ncol = 2 * nrp;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int wm = warp >> 1, wn = warp & 1;
+    const double* Bsel = (wm >> 1) ? Bm : Bp;
+    double acc[2][4][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    const double* Fm = F + (size_t)m * nrings * ncol;
+
+    for (int k0 = 0; k0 < nhalf; k0 += 32) {
+        {
+            const int kk = tid & 31;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int row = (tid >> 5) + 8 * q;
+                const int l = l0 + ((row < 32) ? 2 * row : 2 * (row - 32) + 1);
+                double v = 0.0;
+                if (l <= lmax && k0 + kk < nhalf) v = lam[lm_mmajor(lmax, l, m) * nhalf + k0 + kk];
+                As[row * kLdA + kk] = v;
+            }
+            const int c = tid & 63;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int k2 = (tid >> 6) + 4 * q, k = k0 + k2;
+                double fn = 0.0, fs = 0.0;
+                if (k < nhalf && c0 + c < ncol) {
+                    fn = Fm[(size_t)k * ncol + c0 + c];
+                    if (k != nhalf - 1) fs = Fm[(size_t)(nrings - 1 - k) * ncol + c0 + c];
+                }
+                Bp[k2 * kLdB + c] = fn + fs;
+                Bm[k2 * kLdB + c] = fn - fs;
+            }
+        }
+        __syncthreads();
+        warp_gemm_ss<2, 4>(acc, As + wm * 16 * kLdA, kLdA, Bsel + wn * 32, kLdB, 32);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int row = wm * 16 + i * 8 + g;
+        const int l = l0 + ((row < 32) ? 2 * row : 2 * (row - 32) + 1);
+        if (l > lmax) continue;
+        double* dst = alm + lm_mmajor(lmax, l, m) * ncol + c0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int col = wn * 32 + j * 8 + 2 * t;
+            if (c0 + col < ncol) {
+                if (accumulate) {
+                    dst[col] += w * acc[i][j][0];
+                    dst[col + 1] += w * acc[i][j][1];
+                } else {
+                    dst[col] = w * acc[i][j][0];
+                    dst[col + 1] = w * acc[i][j][1];
+                }
+            }
+        }
+    }
+}
+
+// G_m(ring)[c] = Σ_l λ_lm(θ) a_lm[c]: north = E + O, south = E - O    CTA = (m, 64 north rings, 64 columns)
+__global__ void __launch_bounds__(kT) legendre_synthesis_kernel(const double* __restrict__ alm,
+                                                                const double* __restrict__ lam, int nrings, int nhalf,
+                                                                int lmax, int nrp, double* __restrict__ G) {
+    __shared__ double Ls[32 * kLdB];  // [l (16 even-parity, 16 odd-parity)][ring]
+    __shared__ double Bs[32 * kLdB];
+    const int m = blockIdx.x, k0 = blockIdx.y * 64, c0 = blockIdx.z * 64;
+    const int ncol = 2 * nrp;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int wm = warp >> 1, wn = warp & 1;
+    double accE[2][4][2], accO[2][4][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) accE[i][j][0] = accE[i][j][1] = accO[i][j][0] = accO[i][j][1] = 0.0;
+
+    for (int l0 = m; l0 <= lmax; l0 += 32) {
+        {
+            const int x = tid & 63;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int k2 = (tid >> 6) + 4 * q;
+                const int l = l0 + ((k2 < 16) ? 2 * k2 : 2 * (k2 - 16) + 1);
+                double lv = 0.0, av = 0.0;
+                if (l <= lmax) {
+                    const size_t lm = lm_mmajor(lmax, l, m);
+                    if (k0 + x < nhalf) lv = lam[lm * nhalf + k0 + x];
+                    if (c0 + x < ncol) av = alm[lm * ncol + c0 + x];
+                }
+                Ls[k2 * kLdB + x] = lv;
+                Bs[k2 * kLdB + x] = av;
+            }
+        }
+        __syncthreads();
+        warp_gemm_ts<2, 4>(accE, Ls + wm * 16, kLdB, Bs + wn * 32, kLdB, 16);
+        warp_gemm_ts<2, 4>(accO, Ls + 16 * kLdB + wm * 16, kLdB, Bs + 16 * kLdB + wn * 32, kLdB, 16);
+        __syncthreads();
+    }
+    double* Gm = G + (size_t)m * nrings * ncol;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int k = k0 + wm * 16 + i * 8 + g;
+        if (k >= nhalf) continue;
+        double* dn = Gm + (size_t)k * ncol + c0;
+        double* ds = Gm + (size_t)(nrings - 1 - k) * ncol + c0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int col = wn * 32 + j * 8 + 2 * t;
+            if (c0 + col < ncol) {
+                dn[col] = accE[i][j][0] + accO[i][j][0];
+                dn[col + 1] = accE[i][j][1] + accO[i][j][1];
+                if (k != nhalf - 1) {
+                    ds[col] = accE[i][j][0] - accO[i][j][0];
+                    ds[col + 1] = accE[i][j][1] - accO[i][j][1];
+                }
+            }
+        }
+    }
+}
+
+// planar [lm m-major][comp][nrp] -> interleaved complex, column-major nr x lmsize, requested column order
+__global__ void alm_to_complex_kernel(const double* __restrict__ alm, int lmax, int nr, int nrp, int layout,
+                                      double* __restrict__ out) {
+    const int l = blockIdx.x, m = blockIdx.y;
+    if (m > l) return;
+    const size_t src = lm_mmajor(lmax, l, m);
+    const size_t dst = layout ? ((size_t)l * (l + 1) / 2 + m) : src;
+    for (int r = threadIdx.x; r < nr; r += blockDim.x) {
+        out[2 * (dst * nr + r)] = alm[src * 2 * nrp + r];
+        out[2 * (dst * nr + r) + 1] = alm[src * 2 * nrp + nrp + r];
+    }
+}
+
+// =============================================================================================
+// host side
+
+int sht_plan_create(ShtPlan** out, int64_t nside_in, int64_t nside_out, int64_t lmax, int64_t nr) {
+    SFB_REQUIRE(out, "sht_plan_create: null pointer");
+    auto pow2 = [](int64_t v) { return v >= 1 && (v & (v - 1)) == 0; };
+    SFB_REQUIRE(nside_out >= 1 && nside_in >= 1 && nside_out <= 8192 && nside_in <= 8192,
+                "sht_plan_create: nside out of range");
+    SFB_REQUIRE(nside_in == nside_out || (pow2(nside_in) && pow2(nside_out)),
+                "udgrade: nside must be a power of two when the resolution changes");
+    SFB_REQUIRE(lmax >= 0 && nr >= 1, "sht_plan_create: bad sizes");
+    if (lmax > 4 * nside_out) {  // src/healpix_helpers.jl:60-63
+        set_error("lmax > 4*nside is a poor choice (lmax=" + std::to_string(lmax) + ", 4*nside=" +
+                  std::to_string(4 * nside_out) + ")");
+        return 3;
+    }
+    SFB_REQUIRE(lmax <= 1500, "sht_plan_create: lmax > 1500 needs a scaled Legendre recurrence (not in this build)");
+    auto* p = new ShtPlan();
+    p->nside_in = (int)nside_in;
+    p->nside = (int)nside_out;
+    p->lmax = (int)lmax;
+    p->nr = (int)nr;
+    p->nrp = (int)round_up(nr, 8);
+    p->npix_in = 12 * nside_in * nside_in;
+    p->npix = 12 * nside_out * nside_out;
+    p->nrings = 4 * p->nside - 1;
+    p->nhalf = 2 * p->nside;
+    p->lmsize = (size_t)(lmax + 1) * (lmax + 2) / 2;
+
+    const int ns = p->nside;
+    std::vector<int> nphi(p->nrings), start(p->nrings), shift(p->nrings), twoff(p->nrings), tile_ring, tile_j0;
+    const int64_t ncap = 2LL * ns * (ns - 1);
+    for (int idx = 0; idx < p->nrings; ++idx) {
+        const int i = idx + 1, north = (i <= 2 * ns) ? i : 4 * ns - i;
+        int64_t st;
+        int np, sh, slot;
+        if (north < ns) {
+            np = 4 * north;
+            st = 2LL * north * (north - 1);
+            sh = 1;
+            slot = north;
+        } else {
+            np = 4 * ns;
+            st = ncap + (int64_t)(north - ns) * 4 * ns;
+            sh = (((north - ns) & 1) == 0) ? 1 : 0;
+            slot = ns;
+        }
+        if (i > 2 * ns) st = p->npix - st - np;
+        nphi[idx] = np;
+        start[idx] = (int)st;
+        shift[idx] = sh;
+        twoff[idx] = 4 * slot * (slot - 1);
+        for (int j0 = 0; j0 < np; j0 += 64) {
+            tile_ring.push_back(idx);
+            tile_j0.push_back(j0);
+        }
+    }
+    p->ntiles = (int)tile_ring.size();
+    auto up = [&](DevBuf<int>& d, const std::vector<int>& h) -> int {
+        SFB_TRY(d.alloc(h.size()));
+        SFB_CUDA_OK(cudaMemcpy(d.p, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice));
+        return 0;
+    };
+    int rc = 0;
+    rc = rc ? rc : up(p->d_nphi, nphi);
+    rc = rc ? rc : up(p->d_start, start);
+    rc = rc ? rc : up(p->d_shift, shift);
+    rc = rc ? rc : up(p->d_twoff, twoff);
+    rc = rc ? rc : up(p->d_tile_ring, tile_ring);
+    rc = rc ? rc : up(p->d_tile_j0, tile_j0);
+    rc = rc ? rc : p->d_tw.alloc((size_t)4 * ns * (ns + 1));
+    rc = rc ? rc : p->d_lam.alloc(p->lmsize * p->nhalf);
+    rc = rc ? rc : p->d_FG.alloc((size_t)(lmax + 1) * p->nrings * 2 * p->nrp);
+    rc = rc ? rc : p->d_resid.alloc((size_t)p->npix * p->nrp);
+    if (!rc && nside_in != nside_out) rc = p->d_map.alloc((size_t)p->npix * p->nrp);
+    if (rc) {
+        delete p;
+        return rc;
+    }
+    twiddle_table_kernel<<<ns, 256>>>(p->d_tw.p, ns);
+    lambda_table_kernel<<<dim3((unsigned)ceil_div(p->nhalf, 128), (unsigned)(lmax + 1)), 128>>>(p->d_lam.p, ns, (int)lmax,
+                                                                                              p->nhalf);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        set_error(std::string("sht_plan_create setup kernels: ") + cudaGetErrorString(e));
+        delete p;
+        return 1;
+    }
+    *out = p;
+    return 0;
+}
+
+void sht_plan_destroy(ShtPlan* p) { delete p; }
+
+static int run_analysis(ShtPlan* p, const double* map, int64_t ldw, int accumulate, double* d_alm, cudaStream_t st) {
+    RingTabs rt{p->d_nphi.p, p->d_start.p, p->d_shift.p, p->d_twoff.p, p->d_tw.p};
+    const int lmax = p->lmax, nrp = p->nrp;
+    dim3 g1(p->nrings, (unsigned)ceil_div(lmax + 1, 32), (unsigned)ceil_div(nrp, 64));
+    ring_analysis_kernel<<<g1, kT, 0, st>>>(map, ldw, p->nr, nrp, rt, p->nrings, lmax, p->d_FG.p);
+    SFB_CUDA_OK(cudaGetLastError());
+    dim3 g2(lmax + 1, (unsigned)ceil_div(2 * nrp, 64), (unsigned)ceil_div(lmax + 1, 64));
+    const double w = 4.0 * 3.14159265358979323846 / (double)p->npix;
+    constexpr int la_smem_bytes = (64 * kLdA + 2 * 32 * kLdB) * (int)sizeof(double);
+    SFB_CUDA_OK(cudaFuncSetAttribute(legendre_analysis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, la_smem_bytes));
+    legendre_analysis_kernel<<<g2, kT, la_smem_bytes, st>>>(p->d_FG.p, p->d_lam.p, p->nrings, p->nhalf, lmax, nrp, w, accumulate,
+                                                d_alm);
+    SFB_CUDA_OK(cudaGetLastError());
+    p->launches += 2;
+    return 0;
+}
+
+int sht_map2alm(ShtPlan* p, const double* d_win, int64_t ldw, int niter, double* d_alm, cudaStream_t st) {
+    SFB_REQUIRE(p && d_win && d_alm, "sht_map2alm: null pointer");
+    SFB_REQUIRE(ldw >= p->nr, "sht_map2alm: ld_win < nr");
+    SFB_REQUIRE(niter >= 0, "sht_map2alm: niter < 0");
+    cudaEvent_t e0, e1;
+    SFB_CUDA_OK(cudaEventCreate(&e0));
+    SFB_CUDA_OK(cudaEventCreate(&e1));
+    SFB_CUDA_OK(cudaEventRecord(e0, st));
+    p->launches = 0;
+    const double* map = d_win;
+    int64_t ldm = ldw;
+    if (p->nside_in != p->nside) {
+        udgrade_kernel<<<2048, 256, 0, st>>>(d_win, ldw, p->nside_in, p->d_map.p, p->nside, p->nr, p->nrp);
+        SFB_CUDA_OK(cudaGetLastError());
+        p->launches++;
+        map = p->d_map.p;
+        ldm = p->nrp;
+    }
+    RingTabs rt{p->d_nphi.p, p->d_start.p, p->d_shift.p, p->d_twoff.p, p->d_tw.p};
+    SFB_TRY(run_analysis(p, map, ldm, 0, d_alm, st));
+    for (int it = 0; it < niter; ++it) {
+        dim3 gs(p->lmax + 1, (unsigned)ceil_div(p->nhalf, 64), (unsigned)ceil_div(2 * p->nrp, 64));
+        legendre_synthesis_kernel<<<gs, kT, 0, st>>>(d_alm, p->d_lam.p, p->nrings, p->nhalf, p->lmax, p->nrp, p->d_FG.p);
+        SFB_CUDA_OK(cudaGetLastError());
+        dim3 gr(p->ntiles, (unsigned)ceil_div(p->nrp, 64));
+        ring_synthesis_kernel<<<gr, kT, 0, st>>>(p->d_FG.p, rt, p->d_tile_ring.p, p->d_tile_j0.p, p->nrings, p->lmax,
+                                                 p->nr, p->nrp, map, ldm, 1, p->d_resid.p);
+        SFB_CUDA_OK(cudaGetLastError());
+        p->launches += 2;
+        SFB_TRY(run_analysis(p, p->d_resid.p, p->nrp, 1, d_alm, st));
+    }
+    SFB_CUDA_OK(cudaEventRecord(e1, st));
+    SFB_CUDA_OK(cudaEventSynchronize(e1));
+    cudaEventElapsedTime(&p->t_total, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return 0;
+}
+
+int sht_alm_to_complex(const ShtPlan* p, const double* d_alm, int layout, double* d_out, cudaStream_t st) {
+    SFB_REQUIRE(p && d_alm && d_out, "sht_alm_to_complex: null pointer");
+    alm_to_complex_kernel<<<dim3(p->lmax + 1, p->lmax + 1), 64, 0, st>>>(d_alm, p->lmax, p->nr, p->nrp, layout, d_out);
+    SFB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace sfb

@@ -1,0 +1,41 @@
+// Stage 1: batched HEALPix map2alm (niter Jacobi refinements) for all radial shells at once, sm_100a FP64.
+//
+// Replaces (reference hsgg/SphericalFourierBesselDecompositions.jl):
+//   calc_Wr_lm                      src/windows.jl:528-545
+//   udgrade(::Vector, nside)        src/healpix_helpers.jl:40-45   (Healpix.jl udgrade)
+//   mymap2alm(map; lmax)            src/healpix_helpers.jl:59-71   (Healpix.jl map2alm -> libsharp2)
+//   optimize_Wr_lm_layout           src/windows.jl:589-605         (folded into the output conversion)
+#pragma once
+#include "common.cuh"
+#include <vector>
+
+namespace sfb {
+
+struct ShtPlan {
+    int nside_in = 0, nside = 0, lmax = 0, nr = 0, nrp = 0;
+    int64_t npix_in = 0, npix = 0;
+    int nrings = 0, nhalf = 0;
+    size_t lmsize = 0;
+    int ntiles = 0;  // synthesis (ring, pixel-chunk) tiles
+
+    DevBuf<int> d_nphi, d_start, d_shift, d_twoff;
+    DevBuf<int> d_tile_ring, d_tile_j0;
+    DevBuf<double2> d_tw;    // (cos, sin)(π t / nφ), t in [0, 2nφ), one block per distinct ring length
+    DevBuf<double> d_lam;    // λ_lm(θ_k): [lm (m-major)][nhalf]
+    DevBuf<double> d_FG;     // ring-space intermediates [m][ring][2*nrp]
+    DevBuf<double> d_map;    // udgraded maps [npix][nrp] (only if nside_in != nside)
+    DevBuf<double> d_resid;  // residual maps [npix][nrp]
+
+    float t_total = 0;
+    int launches = 0;
+};
+
+int sht_plan_create(ShtPlan** out, int64_t nside_in, int64_t nside_out, int64_t lmax, int64_t nr);
+void sht_plan_destroy(ShtPlan* p);
+
+// d_win: [pixel][shell], pixel stride ldw (>= nr).  d_alm: planar [lm (m-major)][re,im][nrp].
+int sht_map2alm(ShtPlan* p, const double* d_win, int64_t ldw, int niter, double* d_alm, cudaStream_t stream);
+// planar -> ComplexF64 nr x lmsize (device), layout 0 = m-major, 1 = m-fast
+int sht_alm_to_complex(const ShtPlan* p, const double* d_alm, int layout, double* d_out, cudaStream_t stream);
+
+}  // namespace sfb

@@ -1,0 +1,154 @@
+"""Device-resident pipeline and multi-GPU row sharding.
+
+torch is plumbing only (device memory, streams, `torch.distributed`); every kernel is in libsfb_b200.so.
+
+The coupling matrix shards by output rows (l,n,n'): each (i,i') element is an independent closure call in the
+reference (src/windows.jl:717-738).  Rank g computes the contiguous row range [lo_g, hi_g) chosen on l-block
+boundaries by a cost prefix sum, as a compact (hi_g-lo_g) x nout column-major slab, and an NCCL all-gather
+assembles the full matrix on every rank (the reference's only analogue is the pmap gather, src/windows.jl:841-861).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .modes import getlmsize
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def shard_rows(costs, ell_of_row, world):
+    """Contiguous row ranges [lo, hi) per rank, cut only where `ell_of_row` changes, balancing `costs`.
+    Returns a list of `world` (lo, hi) tuples covering [0, n)."""
+    costs = np.asarray(costs, dtype=np.float64)
+    n = costs.size
+    cuts = [0] + [i for i in range(1, n) if ell_of_row[i] != ell_of_row[i - 1]] + [n]
+    cum = np.concatenate([[0.0], np.cumsum(costs)])
+    total = cum[-1]
+    bounds = [0]
+    for g in range(1, world):
+        target = total * g / world
+        best = min(cuts, key=lambda c: abs(cum[c] - target))
+        bounds.append(max(best, bounds[-1]))
+    bounds.append(n)
+    return [(bounds[g], bounds[g + 1]) for g in range(world)]
+
+
+class DevicePipeline:
+    """Plans + device buffers for repeated power_win_mix calls on one GPU (one process per GPU)."""
+
+    def __init__(self, wmodes, cmodes, G, nside_win=None, lnn_min=1, device=None):
+        torch = _torch()
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        torch.cuda.set_device(self.device)
+        _lib.check(self.lib.sfb_set_device(self.device.index))
+        amodes = cmodes.amodes
+        self.amodes, self.cmodes, self.wmodes = amodes, cmodes, wmodes
+        self.nr = wmodes.nr
+        self.LMAX = 2 * amodes.lmax
+        self.lmsize = getlmsize(self.LMAX)
+        self.nside_in = wmodes.nside if nside_win is None else nside_win
+        self.lnn = np.asfortranarray(cmodes.lnn, dtype=np.int64)
+        self.lnnsize = self.lnn.shape[1]
+        self.nout = self.lnnsize - lnn_min + 1
+        G = np.asfortranarray(G, dtype=np.float64)
+        self._sht = C.c_void_p()
+        self._cmix = C.c_void_p()
+        _lib.check(self.lib.sfb_sht_plan_create(C.byref(self._sht), self.nside_in, amodes.nside, self.LMAX, self.nr))
+        _lib.check(self.lib.sfb_cmix_plan_create(C.byref(self._cmix), _lib.ptr(self.lnn), self.lnnsize, lnn_min,
+                                                 _lib.ptr(G), self.nr, amodes.nmax, amodes.lmax))
+        nalm = self.lib.sfb_sht_alm_doubles(self._sht)
+        self.alm = torch.empty(nalm, dtype=torch.float64, device=self.device)
+        costs = np.zeros(self.nout)
+        _lib.check(self.lib.sfb_cmix_row_costs(self._cmix, _lib.ptr(costs), self.nout))
+        self.row_costs = costs
+        self.ell_of_row = self.lnn[0, lnn_min - 1:]
+
+    def close(self):
+        if self._sht:
+            self.lib.sfb_sht_plan_destroy(self._sht)
+            self._sht = C.c_void_p()
+        if self._cmix:
+            self.lib.sfb_cmix_plan_destroy(self._cmix)
+            self._cmix = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(_torch().cuda.current_stream().cuda_stream)
+
+    # ---- stage 1 -------------------------------------------------------------------------------
+    def calc_wr_lm(self, d_win, niter=3):
+        """d_win: torch float64 CUDA tensor holding the Julia (nr, npix) array in memory order, i.e. shape
+        (npix, nr) contiguous.  Fills and returns the planar W_lm(r) buffer."""
+        assert d_win.is_cuda and d_win.dtype == _torch().float64 and d_win.is_contiguous()
+        assert d_win.shape == (12 * self.nside_in ** 2, self.nr)
+        _lib.check(self.lib.sfb_calc_wr_lm_dev(self._sht, d_win.data_ptr(), self.nr, niter, self.alm.data_ptr(),
+                                               self._stream()))
+        return self.alm
+
+    def wr_lm_complex(self, layout=0):
+        torch = _torch()
+        out = torch.empty((self.lmsize, self.nr), dtype=torch.complex128, device=self.device)
+        _lib.check(self.lib.sfb_alm_to_complex_dev(self._sht, self.alm.data_ptr(), layout, out.data_ptr(),
+                                                   self._stream()))
+        return out  # out.T is the Julia (nr, lmsize) matrix
+
+    # ---- stage 2+3 -----------------------------------------------------------------------------
+    def power_win_mix_rows(self, lo, hi, out=None, alm2=None, div2Lp1=False, interchange_NN=False):
+        """Rows [lo, hi) of M as a torch tensor of shape (nout, hi-lo) (memory = column-major (hi-lo) x nout)."""
+        torch = _torch()
+        if out is None:
+            out = torch.empty((self.nout, hi - lo), dtype=torch.float64, device=self.device)
+        a2 = self.alm if alm2 is None else alm2
+        _lib.check(self.lib.sfb_power_win_mix_dev(self._cmix, self.alm.data_ptr(), a2.data_ptr(), int(div2Lp1),
+                                                  int(interchange_NN), lo, hi, out.data_ptr(), hi - lo,
+                                                  self._stream()))
+        return out
+
+    def power_win_mix(self, d_win, **kw):
+        self.calc_wr_lm(d_win)
+        return self.power_win_mix_rows(0, self.nout, **kw)
+
+    # ---- multi-GPU -----------------------------------------------------------------------------
+    def power_win_mix_sharded(self, d_win, group=None, gather=True, **kw):
+        """Row-sharded coupling matrix over the ranks of `group`; with gather=True every rank returns the
+        full matrix as a (nout, nout) tensor holding Mᵀ in C order (= M in Julia's column-major order)."""
+        torch = _torch()
+        import torch.distributed as dist
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.calc_wr_lm(d_win)
+        ranges = shard_rows(self.row_costs, self.ell_of_row, world)
+        lo, hi = ranges[rank]
+        slab = self.power_win_mix_rows(lo, hi, **kw)  # (nout, hi-lo)
+        if world == 1 or not gather:
+            return slab, ranges
+        return gather_row_slabs(slab, ranges, self.nout, group), ranges
+
+
+def gather_row_slabs(slab, ranges, nout, group=None):
+    """All-gather variable-height row slabs into the full matrix.  `slab` has shape (nout, rows_g); the result
+    has shape (nout, nout) with result[i', i] = M[i, i'] (C order), i.e. Julia's column-major M."""
+    torch = _torch()
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    hmax = max(hi - lo for lo, hi in ranges)
+    send = slab if slab.shape[1] == hmax else torch.nn.functional.pad(slab, (0, hmax - slab.shape[1]))
+    send = send.contiguous()
+    recv = torch.empty((world, nout, hmax), dtype=slab.dtype, device=slab.device)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    full = torch.empty((nout, nout), dtype=slab.dtype, device=slab.device)
+    for g, (lo, hi) in enumerate(ranges):
+        full[:, lo:hi] = recv[g, :, :hi - lo]
+    return full

@@ -1,0 +1,208 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+
+Tolerance: north_star asks <= 1e-10 relative (FP64), norm-wise like the reference's `≈ rtol=1e-10`
+(test/test_windows.jl:408-409,434,440-442); index tables bit-exact.
+"""
+import numpy as np
+import pytest
+
+from conftest import relerr
+from oracle import healpix as ohp
+from oracle import modes as om
+from oracle import windows as ow
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-10
+
+
+def _setup(nmax=2, lmax=5, nr=100, dnmax=1, seed=5, kmax=None):
+    import sfb_b200 as sfb
+    if kmax is None:
+        oa, a = om.AnlmModes(nmax, lmax, 500.0, 1000.0), sfb.AnlmModes(nmax, lmax, 500.0, 1000.0)
+    else:
+        oa, a = om.AnlmModes(kmax, 500.0, 1000.0), sfb.AnlmModes(kmax, 500.0, 1000.0)
+    owm = ow.ConfigurationSpaceModes(500.0, 1000.0, nr, oa.nside)
+    wm = sfb.ConfigurationSpaceModes(500.0, 1000.0, nr, a.nside)
+    oc = om.ClnnModes(oa, dnmax=dnmax) if dnmax is not None else om.ClnnModes(oa)
+    c = sfb.ClnnModes(a, dnmax=dnmax)
+    assert np.array_equal(oc.lnn, c.lnn)
+    rng = np.random.default_rng(seed)
+    return sfb, oa, a, owm, wm, oc, c, rng
+
+
+def _random_window(rng, owm, smooth=True):
+    mask = rng.random(owm.npix)
+    mask[: owm.npix // 2] *= 0.5
+    phi = np.exp(-(owm.r / (0.55 * owm.rmax)) ** 2)
+    win = np.outer(phi, mask)
+    if not smooth:
+        win *= 1 + 0.3 * rng.random(win.shape)
+    return win / win.max(), phi, mask
+
+
+# --------------------------------------------------------------------------------------------- stage 1
+
+@pytest.mark.parametrize("nside,lmax,nr", [(4, 8, 3), (8, 16, 10), (8, 32, 8), (16, 40, 17), (32, 64, 5)])
+def test_calc_wr_lm_matches_oracle(nside, lmax, nr):
+    import sfb_b200 as sfb
+    rng = np.random.default_rng(nside + lmax)
+    win = rng.random((nr, 12 * nside * nside))
+    win[:, ::3] = 0.0
+    ref = ow.calc_Wr_lm(win, lmax, nside)
+    got = sfb.calc_Wr_lm(win, lmax, nside)
+    assert got.shape == ref.shape
+    assert relerr(got, ref) < RTOL
+    got_fast = sfb.calc_Wr_lm(win, lmax, nside, layout=1)
+    assert relerr(got_fast, ow.optimize_Wr_lm_layout(ref, lmax)) < RTOL
+    assert np.array_equal(sfb.optimize_Wr_lm_layout(got, lmax), got_fast)
+
+
+@pytest.mark.parametrize("niter", [0, 1, 3])
+def test_calc_wr_lm_niter(niter):
+    import sfb_b200 as sfb
+    rng = np.random.default_rng(11)
+    win = rng.random((4, 12 * 8 * 8))
+    ref = ow.calc_Wr_lm(win, 16, 8, niter=niter)
+    assert relerr(sfb.calc_Wr_lm(win, 16, 8, niter=niter), ref) < RTOL
+
+
+@pytest.mark.parametrize("nside_in,nside_out", [(4, 16), (16, 8), (8, 8), (2, 32)])
+def test_calc_wr_lm_udgrade(nside_in, nside_out):
+    import sfb_b200 as sfb
+    rng = np.random.default_rng(nside_in * 100 + nside_out)
+    win = rng.random((3, 12 * nside_in * nside_in))
+    lmax = 2 * nside_out
+    ref = ow.calc_Wr_lm(win, lmax, nside_out)
+    assert relerr(sfb.calc_Wr_lm(win, lmax, nside_out), ref) < RTOL
+
+
+def test_calc_wr_lm_full_sky_and_monopole():
+    # test/test_windows.jl:19-37: Wr_lm[:,1] ≈ sqrt(4π) mean(win, dims=2), atol 1e-3
+    import sfb_b200 as sfb
+    nside, nr = 16, 12
+    wm = ow.ConfigurationSpaceModes(500.0, 1000.0, nr, nside)
+    win = ow.make_window(wm, "ang_quarter", "radial")
+    got = sfb.calc_Wr_lm(win, 2 * nside, nside)
+    assert np.allclose(got[:, 0].real, np.sqrt(4 * np.pi) * win.mean(axis=1), atol=1e-3)
+    full = sfb.calc_Wr_lm(np.ones((2, 12 * nside * nside)), 2 * nside, nside)
+    assert abs(full[0, 0] - np.sqrt(4 * np.pi)) < 1e-4 and np.abs(full[:, 1:]).max() < 1e-3
+
+
+def test_calc_wr_lm_separable_and_errors():
+    import sfb_b200 as sfb
+    from sfb_b200 import _lib
+    rng = np.random.default_rng(3)
+    mask, phi = rng.random(12 * 8 * 8), rng.random(6)
+    out = sfb.calc_Wr_lm(sfb.SeparableArray(phi, mask), 16, 8)
+    _, ref = ow.calc_Wr_lm(ow.SeparableArray(phi, mask), 16, 8)
+    assert relerr(out.wlm, ref) < RTOL and np.array_equal(out.phi, phi)
+    with pytest.raises(_lib.SFBError, match="poor choice"):   # src/healpix_helpers.jl:60-63
+        sfb.calc_Wr_lm(np.ones((2, 12 * 8 * 8)), 4 * 8 + 1, 8)
+    with pytest.raises(_lib.SFBError):
+        sfb.calc_Wr_lm(np.ones((2, 100)), 4, 8)
+
+
+# --------------------------------------------------------------------------------------------- stage 2+3
+
+@pytest.mark.parametrize("kw", [dict(), dict(div2Lp1=True), dict(interchange_NN=True), dict(lnn_min=5),
+                                dict(div2Lp1=True, interchange_NN=True, lnn_min=3)])
+def test_cmix_from_wrlm_matches_oracle(kw):
+    sfb, oa, a, owm, wm, oc, c, rng = _setup()
+    win, _, _ = _random_window(rng, owm)
+    LMAX = 2 * oa.lmax
+    W = ow.optimize_Wr_lm_layout(ow.calc_Wr_lm(win, LMAX, oa.nside), LMAX)
+    okw = dict(div2Lp1=kw.get("div2Lp1", False), interchange=kw.get("interchange_NN", False), lnn_min=kw.get("lnn_min", 1))
+    ref = ow.calc_cmix(oc, ow.rsdrgnlr(oa, owm), ow.calc_Wrl_Wrl(W, W, LMAX), **okw)
+    got = sfb.power_win_mix_from_wrlm(W, None, wm, c, layout=1, **kw)
+    assert got.shape == ref.shape
+    assert relerr(got, ref) < RTOL
+
+
+@pytest.mark.parametrize("interchange", [False, True])
+def test_cmix_two_windows(interchange):
+    sfb, oa, a, owm, wm, oc, c, rng = _setup(nmax=3, lmax=4, nr=37, dnmax=None)
+    win1, _, _ = _random_window(rng, owm, smooth=False)
+    win2, _, _ = _random_window(rng, owm, smooth=False)
+    LMAX = 2 * oa.lmax
+    W1 = ow.calc_Wr_lm(win1, LMAX, oa.nside)
+    W2 = ow.calc_Wr_lm(win2, LMAX, oa.nside)
+    Wl = ow.calc_Wrl_Wrl(ow.optimize_Wr_lm_layout(W1, LMAX), ow.optimize_Wr_lm_layout(W2, LMAX), LMAX)
+    ref = ow.calc_cmix(oc, ow.rsdrgnlr(oa, owm), Wl, interchange=interchange)
+    got = sfb.power_win_mix_from_wrlm(W1, W2, wm, c, layout=0, interchange_NN=interchange)
+    assert relerr(got, ref) < RTOL
+
+
+def test_power_win_mix_end_to_end_kmax():
+    # kmax-selected modes: ragged nmax_l, several a-tile classes
+    sfb, oa, a, owm, wm, oc, c, rng = _setup(kmax=0.03, nr=24, dnmax=None)
+    win, _, _ = _random_window(rng, owm, smooth=False)
+    ref = ow.power_win_mix(win, win, owm, oc)
+    with pytest.warns(RuntimeWarning):   # nr < 8(n+N): the reference only warns (src/windows.jl:916-919)
+        got = sfb.power_win_mix(win, wm, c)
+    assert relerr(got, ref) < RTOL
+    s = 1 + (c.lnn[1] != c.lnn[2])
+    K = got / ((2 * c.lnn[0] + 1) * s)[None, :]
+    assert np.abs(K - K.T).max() / np.abs(K).max() < 1e-11   # symmetry identity, SURVEY §8c.5
+
+
+def test_no_window_is_identity():
+    # test/test_windows.jl:181-213: full sky => M ≈ I, atol 1e-3
+    sfb, oa, a, owm, wm, oc, c, rng = _setup(nmax=3, lmax=5, nr=1000)
+    win = np.ones((owm.nr, owm.npix))
+    M = sfb.power_win_mix(win, wm, c)
+    assert np.allclose(M, np.eye(M.shape[0]), atol=1e-3)
+    assert relerr(M, ow.power_win_mix(win, win, owm, oc)) < RTOL
+
+
+def test_sep_insep_binned():
+    # test/test_windows.jl:365-443: M(dense) ≈ M(separable), binned variants, rtol 1e-10
+    sfb, oa, a, owm, wm, oc, c, rng = _setup()
+    win, phi, mask = _random_window(rng, owm)
+    phi = phi / win.max() if False else phi
+    swin = sfb.SeparableArray(phi, mask)
+    dense = swin.dense()
+    M1 = sfb.power_win_mix(swin, swin, wm, c)
+    M2 = sfb.power_win_mix(dense, wm, c)
+    ref = ow.power_win_mix(dense, dense, owm, oc)
+    assert relerr(M2, ref) < RTOL
+    assert relerr(M1, M2) < RTOL
+    for kw in (dict(div2Lp1=True), dict(interchange_NN=True)):
+        assert relerr(sfb.power_win_mix(swin, swin, wm, c, **kw), sfb.power_win_mix(dense, wm, c, **kw)) < RTOL
+    wt, v = sfb.bandpower_binning_weights(c, dl=2)
+    bc = sfb.ClnnBinnedModes(wt, v, c)
+    N1 = sfb.power_win_mix(swin, wt, v, wm, bc)
+    N2 = sfb.power_win_mix(dense, wt, v, wm, bc)
+    assert N1.shape == (wt.shape[0], v.shape[1])
+    assert relerr(N2, wt @ M2 @ v) < RTOL           # test/test_windows.jl:578-579
+    assert relerr(N1, N2) < RTOL
+    assert relerr(sfb.power_win_mix(dense, wt, None, wm, bc), wt @ M2) < RTOL     # w̃M, test/test_windows.jl:582
+    assert relerr(sfb.power_win_mix(dense, None, v, wm, bc), M2 @ v) < RTOL
+    assert relerr(sfb.power_win_mix(swin, wt, None, wm, bc), wt @ M2) < RTOL
+    oref = ow.power_win_mix_binned(dense, dense, wt.toarray(), v.toarray(), owm, om.ClnnBinnedModes(wt.toarray(), v.toarray(), oc))
+    assert relerr(N2, oref) < RTOL
+
+
+def test_device_pipeline_row_shards():
+    import torch
+    from sfb_b200.device import DevicePipeline, shard_rows
+    sfb, oa, a, owm, wm, oc, c, rng = _setup(kmax=0.03, nr=24, dnmax=None)
+    win, _, _ = _random_window(rng, owm, smooth=False)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        G = sfb.rsdrgnlr(a, wm)
+        full = sfb.power_win_mix(win, wm, c)
+    pipe = DevicePipeline(wm, c, G)
+    d_win = torch.from_numpy(np.ascontiguousarray(win.T)).cuda()
+    M = pipe.power_win_mix(d_win).cpu().numpy().T
+    assert relerr(M, full) < 1e-13
+    ranges = shard_rows(pipe.row_costs, pipe.ell_of_row, 3)
+    assert ranges[0][0] == 0 and ranges[-1][1] == pipe.nout
+    parts = [pipe.power_win_mix_rows(lo, hi).cpu().numpy().T for lo, hi in ranges]
+    assert np.array_equal(np.concatenate(parts, axis=0), M)
+    # an arbitrary range that cuts through an l-block
+    lo, hi = 7, pipe.nout - 5
+    assert np.array_equal(pipe.power_win_mix_rows(lo, hi).cpu().numpy().T, M[lo:hi])
+    wc = pipe.wr_lm_complex().cpu().numpy().T
+    assert relerr(wc, sfb.calc_Wr_lm(win, 2 * a.lmax, a.nside)) < 1e-13
+    pipe.close()
