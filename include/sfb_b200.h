@@ -44,6 +44,10 @@ int32_t sfb_set_device(int32_t device);
  *   [5] executed DMMA flops of [4], [6] kernel launches of the last power_win_mix, [7] binned products */
 int32_t sfb_get_timings(double* out, int32_t n);
 
+/* FP64 tensor-pipe (DMMA) throughput of the current device in TFLOP/s, measured by an in-register probe:
+ * the roofline denominator for the DMMA kernels (bench.py) */
+int32_t sfb_probe_dmma_tflops(double* tflops);
+
 /* ---- host-pointer entry points (what the Julia methods ccall) ------------------------------- */
 
 /* calc_Wr_lm(win, LMAX, Wnside)                                       src/windows.jl:528-537

@@ -20,6 +20,7 @@ SIGNATURES = {
     "sfb_device_count": (_i32, [C.POINTER(_i32)]),
     "sfb_set_device": (_i32, [_i32]),
     "sfb_get_timings": (_i32, [_f64p, _i32]),
+    "sfb_probe_dmma_tflops": (_i32, [_f64p]),
     "sfb_calc_wr_lm": (_i32, [_f64p, _i64, _i64, _i64, _i64, _i64, _i64, _i32, _f64p]),
     "sfb_calc_wlm_mask": (_i32, [_f64p, _i64, _i64, _i64, _i64, _f64p]),
     "sfb_power_win_mix_from_wrlm": (_i32, [_f64p, _f64p, _i64, _i64, _i32, _f64p, _i64, _i64, _i64p, _i64, _i64,

@@ -75,6 +75,23 @@ static int check_finite(const double* d, size_t n, const char* what) {
     return 0;
 }
 
+// FP64 tensor-pipe probe: independent DMMA chains, no memory traffic.  Gives the roofline denominator for the
+// DMMA kernels (MEASURED_PEAKS.json only carries HBM and bf16 figures).
+__global__ void __launch_bounds__(256) dmma_probe_kernel(double* out, int iters, double seed) {
+    double acc[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = 0.0;
+    double a = seed + threadIdx.x * 1e-9, b = 1.0 - seed;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dmma884(acc[i], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += acc[i][0] + acc[i][1];
+    if (s == 12345.678) out[0] = s;  // keep the chain alive
+}
+
 static void record_cmix_times(const CmixPlan* p) {
     g_times[1] = p->t_wl;
     g_times[2] = p->t_w3j;
@@ -271,6 +288,35 @@ int32_t sfb_power_win_mix_separable(const double* phi, const double* mask, int64
     SFB_TRY(binned_product_to_host(dM.p, n, wt_colptr, wt_rowval, wt_nzval, LNN1, v_colptr, v_rowval, v_nzval, LNN2,
                                    N_out, &t_bin));
     g_times[7] = t_bin;
+    return 0;
+}
+
+int32_t sfb_probe_dmma_tflops(double* tflops) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    SFB_REQUIRE(tflops, "null pointer");
+    int dev = 0, sms = 0;
+    SFB_CUDA_OK(cudaGetDevice(&dev));
+    SFB_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    DevBuf<double> d;
+    SFB_TRY(d.alloc(1));
+    const int blocks = sms * 4, iters = 20000;
+    cudaEvent_t e0, e1;
+    SFB_CUDA_OK(cudaEventCreate(&e0));
+    SFB_CUDA_OK(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        SFB_CUDA_OK(cudaEventRecord(e0));
+        dmma_probe_kernel<<<blocks, 256>>>(d.p, iters, 0.25);
+        SFB_CUDA_OK(cudaEventRecord(e1));
+        SFB_CUDA_OK(cudaEventSynchronize(e1));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double fl = (double)blocks * 8 /*warps*/ * iters * 8.0 * 512.0;
+        if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tflops = best;
     return 0;
 }
 

@@ -145,8 +145,17 @@ def _csc_args(mat, n_rows_expected=None, n_cols_expected=None):
     return colptr, rowval, nzval, m.shape[0], m.shape[1]
 
 
-def power_win_mix(*args, div2Lp1=False, interchange_NN=False, lnn_min=1):
-    """Coupling matrix M (unbinned) or N = w̃ M v (binned); see the module docstring for the methods."""
+def _result_buffer(shape, out):
+    if out is None:
+        return np.empty(shape, dtype=np.float64, order="F")
+    if out.shape != shape or out.dtype != np.float64 or not out.flags.f_contiguous:
+        raise ValueError(f"out must be a Fortran-ordered float64 array of shape {shape}")
+    return out
+
+
+def power_win_mix(*args, div2Lp1=False, interchange_NN=False, lnn_min=1, out=None):
+    """Coupling matrix M (unbinned) or N = w̃ M v (binned); see the module docstring for the methods.
+    `out` (not in the reference): optional preallocated Fortran-ordered result buffer, e.g. pinned memory."""
     if len(args) == 3:
         win, wmodes, cmodes = args
         args = (win, win, wmodes, cmodes)
@@ -162,15 +171,15 @@ def power_win_mix(*args, div2Lp1=False, interchange_NN=False, lnn_min=1):
             if lnn_min != 1:
                 raise TypeError("power_win_mix(::SeparableArray, ...) got unsupported keyword argument lnn_min")
             return _power_win_mix_binned(win1, win2, None, None, wmodes, ClnnBinnedModes(None, None, cmodes),
-                                         div2Lp1, interchange_NN)
-        return _power_win_mix_dense(win1, win2, wmodes, cmodes, div2Lp1, interchange_NN, lnn_min)
+                                         div2Lp1, interchange_NN, out)
+        return _power_win_mix_dense(win1, win2, wmodes, cmodes, div2Lp1, interchange_NN, lnn_min, out)
     if len(args) == 6:
         win1, win2, wt, v, wmodes, bcmodes = args
         if not isinstance(bcmodes, ClnnBinnedModes):
             raise TypeError("power_win_mix(win1, win2, w̃, v, wmodes, bcmodes::ClnnBinnedModes)")
         if lnn_min != 1:
             raise TypeError("power_win_mix(..., bcmodes) got unsupported keyword argument lnn_min")
-        return _power_win_mix_binned(win1, win2, wt, v, wmodes, bcmodes, div2Lp1, interchange_NN)
+        return _power_win_mix_binned(win1, win2, wt, v, wmodes, bcmodes, div2Lp1, interchange_NN, out)
     raise TypeError("no method matching power_win_mix with %d positional arguments" % len(args))
 
 
@@ -181,7 +190,7 @@ def _mode_tables(cmodes, wmodes):
     return amodes, G, lnn
 
 
-def _power_win_mix_dense(win1, win2, wmodes, cmodes, div2Lp1, interchange_NN, lnn_min):
+def _power_win_mix_dense(win1, win2, wmodes, cmodes, div2Lp1, interchange_NN, lnn_min, out=None):
     lib = _lib.load()
     amodes, G, lnn = _mode_tables(cmodes, wmodes)
     w1 = _as_julia_matrix(win1)
@@ -190,14 +199,14 @@ def _power_win_mix_dense(win1, win2, wmodes, cmodes, div2Lp1, interchange_NN, ln
         raise ValueError("window shape does not match wmodes")
     lnnsize = lnn.shape[1]
     n = lnnsize - lnn_min + 1
-    M = np.empty((n, n), dtype=np.float64, order="F")
+    M = _result_buffer((n, n), out)
     _lib.check(lib.sfb_power_win_mix(_lib.ptr(w1), None if w2 is w1 else _lib.ptr(w2), w1.shape[0], w1.shape[1],
                                      w1.shape[0], amodes.nside, _lib.ptr(G), amodes.nmax, amodes.lmax, _lib.ptr(lnn),
                                      lnnsize, lnn_min, int(bool(div2Lp1)), int(bool(interchange_NN)), _lib.ptr(M)))
     return M
 
 
-def _power_win_mix_binned(win1, win2, wt, v, wmodes, bcmodes, div2Lp1, interchange_NN):
+def _power_win_mix_binned(win1, win2, wt, v, wmodes, bcmodes, div2Lp1, interchange_NN, out=None):
     lib = _lib.load()
     cmodes = bcmodes.cmodes
     amodes, G, lnn = _mode_tables(cmodes, wmodes)
@@ -206,7 +215,7 @@ def _power_win_mix_binned(win1, win2, wt, v, wmodes, bcmodes, div2Lp1, interchan
     vc, vr, vv, _, LNN2 = _csc_args(v, n_rows_expected=lnnsize)
     LNN1 = lnnsize if LNN1 is None else LNN1   # src/windows.jl:829-830
     LNN2 = lnnsize if LNN2 is None else LNN2
-    N = np.empty((LNN1, LNN2), dtype=np.float64, order="F")
+    N = _result_buffer((LNN1, LNN2), out)
     common = (_lib.ptr(G), amodes.nmax, amodes.lmax, _lib.ptr(lnn), lnnsize, _lib.ptr(wc), _lib.ptr(wr), _lib.ptr(wv),
               LNN1, _lib.ptr(vc), _lib.ptr(vr), _lib.ptr(vv), LNN2, int(bool(div2Lp1)), int(bool(interchange_NN)),
               _lib.ptr(N))
