@@ -1,0 +1,129 @@
+"""Oracle coupling matrix against the reference's identities and analytic results."""
+import math
+
+import numpy as np
+import pytest
+
+from conftest import relerr
+from oracle import cref
+from oracle import modes as om
+from oracle import windows as ow
+
+
+def test_wigner3j000():
+    from sympy.physics.wigner import wigner_3j
+    for (l, lp, L) in [(0, 0, 0), (1, 1, 2), (3, 5, 4), (6, 4, 2), (10, 10, 20), (2, 3, 4)]:
+        assert abs(ow.wigner3j000(l, lp, L) - float(wigner_3j(l, lp, L, 0, 0, 0))) < 1e-14
+        assert abs(cref.wigner3j000(l, lp, L) - ow.wigner3j000(l, lp, L)) < 1e-15
+    assert ow.wigner3j000(2, 2, 5) == 0.0 and ow.wigner3j000(2, 2, 3) == 0.0
+    for (l, L) in [(5, 7), (40, 43), (100, 7)]:   # Σ (2L1+1) w² = 1
+        s = sum((2 * L1 + 1) * ow.wigner3j000(l, L, L1) ** 2 for L1 in range(abs(l - L), l + L + 1))
+        assert abs(s - 1) < 1e-12
+
+
+@pytest.fixture(scope="module")
+def small():
+    a = om.AnlmModes(2, 5, 500.0, 1000.0)
+    wm = ow.ConfigurationSpaceModes(500.0, 1000.0, 100, a.nside)
+    c = om.ClnnModes(a, dnmax=1)
+    rng = np.random.default_rng(5)
+    win = ow.make_window(wm, "ang_75", "radial", "separable")
+    win.mask = rng.random(win.mask.size)
+    win.mask[: win.mask.size // 2] *= 0.5
+    return a, wm, c, win
+
+
+def test_no_window_gives_identity():
+    # test/test_windows.jl:181-213 (atol 1e-3)
+    a = om.AnlmModes(3, 5, 500.0, 1000.0)
+    wm = ow.ConfigurationSpaceModes(500.0, 1000.0, 1000, a.nside)
+    c = om.ClnnModes(a, dnmax=1)
+    win = np.ones((wm.nr, wm.npix))
+    M = ow.power_win_mix(win, win, wm, c)
+    assert np.allclose(M, np.eye(M.shape[0]), atol=1e-3)
+    W = ow.calc_Wr_lm(win, 2 * a.lmax, a.nside)
+    assert np.allclose(W[:, 0], math.sqrt(4 * math.pi), atol=1e-3) and np.abs(W[:, 1:]).max() < 1e-3
+
+
+def test_literal_blocked_separable_agree(small):
+    # test/test_windows.jl:403-409: independent routes agree to rtol 1e-10
+    a, wm, c, win = small
+    d = win.dense()
+    Ml = ow.power_win_mix(d, d, wm, c, literal=True)
+    assert relerr(ow.power_win_mix(d, d, wm, c), Ml) < 1e-13
+    assert relerr(ow.power_win_mix(win, win, wm, c), Ml) < 1e-10
+    for kw in (dict(div2Lp1=True), dict(interchange=True), dict(lnn_min=4)):
+        assert relerr(ow.power_win_mix(d, d, wm, c, **kw), ow.power_win_mix(d, d, wm, c, literal=True, **kw)) < 1e-13
+    s = 1 + (c.lnn[1] != c.lnn[2])
+    K = Ml / ((2 * c.lnn[0] + 1) * s)[None, :]
+    assert np.abs(K - K.T).max() / np.abs(K).max() < 1e-13
+
+
+def test_c_port_matches_numpy(small):
+    a, wm, c, win = small
+    d = win.dense() * (1 + 0.1 * np.random.default_rng(1).random((wm.nr, wm.npix)))
+    LMAX = 2 * a.lmax
+    W = ow.optimize_Wr_lm_layout(ow.calc_Wr_lm(d, LMAX, a.nside), LMAX)
+    Wl, Wc = ow.calc_Wrl_Wrl(W, W, LMAX), cref.calc_wrl_wrl(W, W, LMAX)
+    assert np.abs(Wl - np.transpose(Wc, (0, 2, 1))).max() < 1e-14 * np.abs(Wl).max()
+    G = ow.rsdrgnlr(a, wm)
+    n = c.lnn.shape[1]
+    for kw in (dict(), dict(div2Lp1=True), dict(interchange=True)):
+        got = cref.calc_cmix_rows(c.lnn, np.arange(1, n + 1), G, Wc, **kw)
+        assert relerr(got, ow.calc_cmix(c, G, Wl, **kw)) < 1e-13
+    rows = np.array([2, 7, n])
+    assert np.array_equal(cref.calc_cmix_rows(c.lnn, rows, G, Wc, nthreads=2),
+                          cref.calc_cmix_rows(c.lnn, np.arange(1, n + 1), G, Wc)[rows - 1])
+
+
+def test_binned(small):
+    # test/test_windows.jl:578-584
+    a, wm, c, win = small
+    d = win.dense()
+    M = ow.power_win_mix(d, d, wm, c)
+    wt, v = om.bandpower_binning_weights(c, dl=2)
+    bc = om.ClnnBinnedModes(wt, v, c)
+    assert relerr(ow.power_win_mix_binned(d, d, wt, v, wm, bc), wt @ M @ v) < 1e-14
+    assert relerr(ow.power_win_mix_binned(win, win, wt, None, wm, bc), wt @ M) < 1e-10
+
+
+def _W0nn_expmrr0(wm, amodes):
+    # src/utils.jl:13-41 with r0sign=-1
+    rmax = wm.rmax
+    r0 = -rmax / 2 / 3
+    norm = math.exp(-wm.r[0] / r0)
+    eR = math.exp(rmax / r0)
+    nmax = amodes.nmax
+    out = np.zeros((nmax, nmax))
+    for n1 in range(1, nmax + 1):
+        for n2 in range(1, nmax + 1):
+            k1, k2 = amodes.knl[n1 - 1, 0], amodes.knl[n2 - 1, 0]
+            s = (-1) ** (n1 + n2)
+            p1 = r0 / (1 + (k1 + k2) ** 2 * r0 ** 2)
+            p2 = r0 / (1 + (k1 - k2) ** 2 * r0 ** 2)
+            out[n1 - 1, n2 - 1] = norm * (p1 * (s + eR) - p2 * (s - eR)) / rmax
+    return out
+
+
+def test_analytic_ell0_expmrr0():
+    # test/test_windows.jl:259-300 + src/utils.jl:141-168: rmin=0, phi = exp(-r/r0), l=L=0 block analytic, rtol 1.1e-6
+    a = om.AnlmModes(0.01, 0.0, 1000.0)
+    wm = ow.ConfigurationSpaceModes(0.0, 1000.0, 2032, a.nside)
+    c = om.ClnnModes(a)
+    win = ow.make_window(wm, "radial_expmrr0", "fullsky")
+    M = ow.power_win_mix(win, win, wm, c)
+    W0 = _W0nn_expmrr0(wm, a)
+    idx0 = np.flatnonzero(c.lnn[0] == 0)
+    T1 = np.zeros((idx0.size, idx0.size))
+    for x, i in enumerate(idx0):
+        for y, j in enumerate(idx0):
+            n1, n2 = c.lnn[1, i], c.lnn[2, i]
+            N1, N2 = c.lnn[1, j], c.lnn[2, j]
+            T1[x, y] = W0[n1 - 1, N1 - 1] * W0[N2 - 1, n2 - 1]
+            if N1 != N2:
+                T1[x, y] += W0[n1 - 1, N2 - 1] * W0[N1 - 1, n2 - 1]
+    # like set_T1_ell0_expmrr0!: overwrite the l=L=0 block of a copy and compare the whole matrices
+    M0 = M.copy()
+    M0[np.ix_(idx0, idx0)] = T1
+    assert relerr(M, M0) < 1.1e-6
+    assert relerr(M[np.ix_(idx0, idx0)], T1) < 2e-6
