@@ -8,6 +8,7 @@
 // c = comp*nrp + shell (re plane, then im plane).
 #include "sht.cuh"
 
+#include <algorithm>
 #include <cmath>
 
 namespace sfb {
@@ -201,10 +202,11 @@ struct RingTabs {
 
 // F[m][ring][c] = Σ_j e^{-imφ_j} f_j      CTA = (ring, 32 m's, 64 shells); rows 0-31 -> Re, 32-63 -> Im
 __global__ void __launch_bounds__(kT) ring_analysis_kernel(const double* __restrict__ map, long long ldw, int nr, int nrp,
-                                                           RingTabs rt, int nrings, int lmax, double* __restrict__ F) {
+                                                           RingTabs rt, const int* __restrict__ ring_list, int nrings,
+                                                           int lmax, double* __restrict__ F) {
     __shared__ double As[64 * kLdA];
     __shared__ double Bs[32 * kLdB];
-    const int ring = blockIdx.x, m0 = blockIdx.y * 32, sh0 = blockIdx.z * 64;
+    const int ring = ring_list[blockIdx.x], m0 = blockIdx.y * 32, sh0 = blockIdx.z * 64;
     const int nphi = rt.nphi[ring], start = rt.start[ring], s = rt.shift[ring];
     const double2* tw = rt.tw + rt.twoff[ring];
     const unsigned two_nphi = 2u * nphi;
@@ -333,6 +335,122 @@ __global__ void __launch_bounds__(kT) ring_synthesis_kernel(const double* __rest
                 out[pix * nrp + sh] = v;
             }
         }
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Equatorial-belt rings (nφ = 4 nside, a power of two): shared-memory radix-2 FFT, two real shells packed into
+// one complex sequence.  Z holds n x SCH complex values; input in bit-reversed order, output in natural order.
+template <int DIR>  // -1: forward e^{-iθ}, +1: backward e^{+iθ}
+__device__ __forceinline__ void fft_smem(double2* Z, int n, int log2n, int sch, const double2* __restrict__ tw) {
+    const int nbf = (n >> 1) * sch;
+    for (int s = 0; s < log2n; ++s) {
+        const int half = 1 << s;
+        for (int x = threadIdx.x; x < nbf; x += blockDim.x) {
+            const int lane = x % sch, b = x / sch;
+            const int k = b & (half - 1);
+            const int i0 = ((b >> s) << (s + 1)) + k, i1 = i0 + half;
+            const double2 w = tw[k * (n >> s)];  // (cos, sin)(π k / half)
+            const double wr = w.x, wi = DIR * w.y;
+            const double2 u = Z[i0 * sch + lane], v = Z[i1 * sch + lane];
+            const double2 vw = make_double2(v.x * wr - v.y * wi, v.x * wi + v.y * wr);
+            Z[i0 * sch + lane] = make_double2(u.x + vw.x, u.y + vw.y);
+            Z[i1 * sch + lane] = make_double2(u.x - vw.x, u.y - vw.y);
+        }
+        __syncthreads();
+    }
+}
+
+// F_m = e^{-imφ0} X[m mod n] for one belt ring and 2*sch shells     CTA = (belt ring, shell chunk)
+__global__ void __launch_bounds__(kT) belt_analysis_fft_kernel(const double* __restrict__ map, long long ldw, int nr,
+                                                               int nrp, RingTabs rt, const int* __restrict__ ring_list,
+                                                               int nrings, int lmax, int log2n, int sch,
+                                                               double* __restrict__ F) {
+    extern __shared__ double2 Zs[];
+    const int ring = ring_list[blockIdx.x], sh0 = blockIdx.y * 2 * sch;
+    const int n = rt.nphi[ring], start = rt.start[ring], s = rt.shift[ring];
+    const double2* tw = rt.tw + rt.twoff[ring];
+    const int nsh = 2 * sch;
+    for (int x = threadIdx.x; x < n * sch; x += blockDim.x) {
+        const int lane = x % sch, j = x / sch;
+        const int sa = sh0 + 2 * lane;
+        const double* src = map + (size_t)(start + j) * ldw + sa;
+        const double a = (sa < nr) ? src[0] : 0.0, b = (sa + 1 < nr) ? src[1] : 0.0;
+        Zs[(__brev((unsigned)j) >> (32 - log2n)) * sch + lane] = make_double2(a, b);
+    }
+    __syncthreads();
+    fft_smem<-1>(Zs, n, log2n, sch, tw);
+    for (int x = threadIdx.x; x <= lmax * sch + sch - 1; x += blockDim.x) {
+        const int lane = x % sch, m = x / sch;
+        const int k = m % n, kc = (n - k) % n;
+        const double2 z1 = Zs[k * sch + lane], z2 = Zs[kc * sch + lane];
+        // X_a = (z1 + conj z2)/2, X_b = (z1 - conj z2)/(2i)
+        const double ar = 0.5 * (z1.x + z2.x), ai = 0.5 * (z1.y - z2.y);
+        const double br = 0.5 * (z1.y + z2.y), bi = -0.5 * (z1.x - z2.x);
+        const double2 w = tw[(unsigned)(m * s) % (2u * n)];  // e^{-imφ0} = (cos, -sin)(π m s / n)
+        const double c = w.x, sn = -w.y;
+        double* dst = F + ((size_t)m * nrings + ring) * 2 * nrp + sh0 + 2 * lane;
+        if (sh0 + 2 * lane < nrp) {
+            dst[0] = ar * c - ai * sn;
+            dst[1] = br * c - bi * sn;
+            dst[nrp] = ar * sn + ai * c;
+            dst[nrp + 1] = br * sn + bi * c;
+        }
+    }
+    (void)nsh;
+}
+
+// f_j = Σ_m (2-δ_m0) Re(G_m e^{imφ_j}) for one belt ring and 2*sch shells, out = residual ? map - f : f
+__global__ void __launch_bounds__(kT) belt_synthesis_fft_kernel(const double* __restrict__ G, RingTabs rt,
+                                                                const int* __restrict__ ring_list, int nrings, int lmax,
+                                                                int log2n, int sch, int nr, int nrp,
+                                                                const double* __restrict__ map, long long ldw,
+                                                                int residual, double* __restrict__ out) {
+    extern __shared__ double2 Zs[];
+    const int ring = ring_list[blockIdx.x], sh0 = blockIdx.y * 2 * sch;
+    const int n = rt.nphi[ring], start = rt.start[ring], s = rt.shift[ring];
+    const double2* tw = rt.tw + rt.twoff[ring];
+    // Hermitian-symmetrised spectrum H_a + i H_b, H[k] = ½ Σ_{m≡k} v_m + ½ conj Σ_{m≡-k} v_m, v_m = c_m G_m e^{imφ0}
+    for (int x = threadIdx.x; x < n * sch; x += blockDim.x) {
+        const int lane = x % sch, k = x / sch;
+        const int sa = sh0 + 2 * lane;
+        double hr = 0.0, hi = 0.0;  // accumulates (H_a + i H_b)[k]
+        if (sa < nrp) {
+            for (int pass = 0; pass < 2; ++pass) {
+                // pass 0: m ≡ k (direct), pass 1: m ≡ -k (conjugated)
+                for (int m = pass ? (n - k) % n : k; m <= lmax; m += n) {
+                    const double2 w = tw[(unsigned)(m * s) % (2u * n)];
+                    const double cm = (m == 0) ? 0.5 : 1.0;  // ½ (2-δ_m0)
+                    const double* g = G + ((size_t)m * nrings + ring) * 2 * nrp + sa;
+                    // v = cm * G * e^{+imφ0}
+                    const double var = cm * (g[0] * w.x - g[nrp] * w.y), vai = cm * (g[0] * w.y + g[nrp] * w.x);
+                    const double vbr = cm * (g[1] * w.x - g[nrp + 1] * w.y), vbi = cm * (g[1] * w.y + g[nrp + 1] * w.x);
+                    if (pass == 0) {  // v_a + i v_b
+                        hr += var - vbi;
+                        hi += vai + vbr;
+                    } else {  // conj(v_a) + i conj(v_b)
+                        hr += var + vbi;
+                        hi += -vai + vbr;
+                    }
+                }
+            }
+        }
+        Zs[(__brev((unsigned)k) >> (32 - log2n)) * sch + lane] = make_double2(hr, hi);
+    }
+    __syncthreads();
+    fft_smem<+1>(Zs, n, log2n, sch, tw);
+    for (int x = threadIdx.x; x < n * sch; x += blockDim.x) {
+        const int lane = x % sch, j = x / sch;
+        const int sa = sh0 + 2 * lane;
+        if (sa >= nrp) continue;
+        const double2 z = Zs[j * sch + lane];
+        const size_t pix = (size_t)start + j;
+        double va = 0.0, vb = 0.0;
+        if (sa < nr) va = residual ? map[pix * ldw + sa] - z.x : z.x;
+        if (sa + 1 < nr) vb = residual ? map[pix * ldw + sa + 1] - z.y : z.y;
+        out[pix * nrp + sa] = va;
+        out[pix * nrp + sa + 1] = vb;
     }
 }
 
@@ -512,6 +630,11 @@ int sht_plan_create(ShtPlan** out, int64_t nside_in, int64_t nside_out, int64_t 
 
     const int ns = p->nside;
     std::vector<int> nphi(p->nrings), start(p->nrings), shift(p->nrings), twoff(p->nrings), tile_ring, tile_j0;
+    std::vector<int> gemm_rings, fft_rings;
+    // belt rings (nφ = 4 nside) go through the shared-memory FFT when nside is a power of two
+    p->use_fft = pow2(nside_out) && (4 * nside_out >= 8);
+    p->log2n = 0;
+    while ((1 << p->log2n) < 4 * p->nside) p->log2n++;
     const int64_t ncap = 2LL * ns * (ns - 1);
     for (int idx = 0; idx < p->nrings; ++idx) {
         const int i = idx + 1, north = (i <= 2 * ns) ? i : 4 * ns - i;
@@ -533,12 +656,25 @@ int sht_plan_create(ShtPlan** out, int64_t nside_in, int64_t nside_out, int64_t 
         start[idx] = (int)st;
         shift[idx] = sh;
         twoff[idx] = 4 * slot * (slot - 1);
-        for (int j0 = 0; j0 < np; j0 += 64) {
-            tile_ring.push_back(idx);
-            tile_j0.push_back(j0);
-        }
+        const bool fft = p->use_fft && north >= ns;
+        (fft ? fft_rings : gemm_rings).push_back(idx);
+        if (!fft)
+            for (int j0 = 0; j0 < np; j0 += 64) {
+                tile_ring.push_back(idx);
+                tile_j0.push_back(j0);
+            }
     }
     p->ntiles = (int)tile_ring.size();
+    p->n_gemm_rings = (int)gemm_rings.size();
+    p->n_fft_rings = (int)fft_rings.size();
+    {
+        // complex lanes per CTA: n * sch * 16 B <= 64 KB, a power of two dividing nrp/2
+        int bound = std::max(1, 4096 / (4 * p->nside));
+        bound = std::min(bound, 16);
+        int sch = 1;
+        while (sch * 2 <= bound && (p->nrp / 2) % (sch * 2) == 0) sch *= 2;
+        p->fft_sch = sch;
+    }
     auto up = [&](DevBuf<int>& d, const std::vector<int>& h) -> int {
         SFB_TRY(d.alloc(h.size()));
         SFB_CUDA_OK(cudaMemcpy(d.p, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice));
@@ -550,6 +686,8 @@ int sht_plan_create(ShtPlan** out, int64_t nside_in, int64_t nside_out, int64_t 
     rc = rc ? rc : up(p->d_shift, shift);
     rc = rc ? rc : up(p->d_twoff, twoff);
     rc = rc ? rc : up(p->d_tile_ring, tile_ring);
+    rc = rc ? rc : up(p->d_gemm_rings, gemm_rings);
+    rc = rc ? rc : up(p->d_fft_rings, fft_rings);
     rc = rc ? rc : up(p->d_tile_j0, tile_j0);
     rc = rc ? rc : p->d_tw.alloc((size_t)4 * ns * (ns + 1));
     rc = rc ? rc : p->d_lam.alloc(p->lmsize * p->nhalf);
@@ -578,9 +716,22 @@ void sht_plan_destroy(ShtPlan* p) { delete p; }
 static int run_analysis(ShtPlan* p, const double* map, int64_t ldw, int accumulate, double* d_alm, cudaStream_t st) {
     RingTabs rt{p->d_nphi.p, p->d_start.p, p->d_shift.p, p->d_twoff.p, p->d_tw.p};
     const int lmax = p->lmax, nrp = p->nrp;
-    dim3 g1(p->nrings, (unsigned)ceil_div(lmax + 1, 32), (unsigned)ceil_div(nrp, 64));
-    ring_analysis_kernel<<<g1, kT, 0, st>>>(map, ldw, p->nr, nrp, rt, p->nrings, lmax, p->d_FG.p);
-    SFB_CUDA_OK(cudaGetLastError());
+    if (p->n_gemm_rings > 0) {
+        dim3 g1(p->n_gemm_rings, (unsigned)ceil_div(lmax + 1, 32), (unsigned)ceil_div(nrp, 64));
+        ring_analysis_kernel<<<g1, kT, 0, st>>>(map, ldw, p->nr, nrp, rt, p->d_gemm_rings.p, p->nrings, lmax, p->d_FG.p);
+        SFB_CUDA_OK(cudaGetLastError());
+        p->launches++;
+    }
+    if (p->n_fft_rings > 0) {
+        const int n = 4 * p->nside, sch = p->fft_sch;
+        const int smem = n * sch * (int)sizeof(double2);
+        SFB_CUDA_OK(cudaFuncSetAttribute(belt_analysis_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        dim3 gf(p->n_fft_rings, (unsigned)ceil_div(nrp, 2 * sch));
+        belt_analysis_fft_kernel<<<gf, kT, smem, st>>>(map, ldw, p->nr, nrp, rt, p->d_fft_rings.p, p->nrings, lmax,
+                                                       p->log2n, sch, p->d_FG.p);
+        SFB_CUDA_OK(cudaGetLastError());
+        p->launches++;
+    }
     dim3 g2(lmax + 1, (unsigned)ceil_div(2 * nrp, 64), (unsigned)ceil_div(lmax + 1, 64));
     const double w = 4.0 * 3.14159265358979323846 / (double)p->npix;
     constexpr int la_smem_bytes = (64 * kLdA + 2 * 32 * kLdB) * (int)sizeof(double);
@@ -588,7 +739,7 @@ static int run_analysis(ShtPlan* p, const double* map, int64_t ldw, int accumula
     legendre_analysis_kernel<<<g2, kT, la_smem_bytes, st>>>(p->d_FG.p, p->d_lam.p, p->nrings, p->nhalf, lmax, nrp, w, accumulate,
                                                 d_alm);
     SFB_CUDA_OK(cudaGetLastError());
-    p->launches += 2;
+    p->launches += 1;
     return 0;
 }
 
@@ -616,11 +767,25 @@ int sht_map2alm(ShtPlan* p, const double* d_win, int64_t ldw, int niter, double*
         dim3 gs(p->lmax + 1, (unsigned)ceil_div(p->nhalf, 64), (unsigned)ceil_div(2 * p->nrp, 64));
         legendre_synthesis_kernel<<<gs, kT, 0, st>>>(d_alm, p->d_lam.p, p->nrings, p->nhalf, p->lmax, p->nrp, p->d_FG.p);
         SFB_CUDA_OK(cudaGetLastError());
-        dim3 gr(p->ntiles, (unsigned)ceil_div(p->nrp, 64));
-        ring_synthesis_kernel<<<gr, kT, 0, st>>>(p->d_FG.p, rt, p->d_tile_ring.p, p->d_tile_j0.p, p->nrings, p->lmax,
-                                                 p->nr, p->nrp, map, ldm, 1, p->d_resid.p);
-        SFB_CUDA_OK(cudaGetLastError());
-        p->launches += 2;
+        p->launches += 1;
+        if (p->ntiles > 0) {
+            dim3 gr(p->ntiles, (unsigned)ceil_div(p->nrp, 64));
+            ring_synthesis_kernel<<<gr, kT, 0, st>>>(p->d_FG.p, rt, p->d_tile_ring.p, p->d_tile_j0.p, p->nrings,
+                                                     p->lmax, p->nr, p->nrp, map, ldm, 1, p->d_resid.p);
+            SFB_CUDA_OK(cudaGetLastError());
+            p->launches++;
+        }
+        if (p->n_fft_rings > 0) {
+            const int n = 4 * p->nside, sch = p->fft_sch;
+            const int smem = n * sch * (int)sizeof(double2);
+            SFB_CUDA_OK(
+                cudaFuncSetAttribute(belt_synthesis_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            dim3 gf(p->n_fft_rings, (unsigned)ceil_div(p->nrp, 2 * sch));
+            belt_synthesis_fft_kernel<<<gf, kT, smem, st>>>(p->d_FG.p, rt, p->d_fft_rings.p, p->nrings, p->lmax, p->log2n,
+                                                            sch, p->nr, p->nrp, map, ldm, 1, p->d_resid.p);
+            SFB_CUDA_OK(cudaGetLastError());
+            p->launches++;
+        }
         SFB_TRY(run_analysis(p, p->d_resid.p, p->nrp, 1, d_alm, st));
     }
     SFB_CUDA_OK(cudaEventRecord(e1, st));

@@ -20,6 +20,9 @@ struct ShtPlan {
 
     DevBuf<int> d_nphi, d_start, d_shift, d_twoff;
     DevBuf<int> d_tile_ring, d_tile_j0;
+    DevBuf<int> d_gemm_rings, d_fft_rings;  // rings transformed by DFT-as-GEMM (polar caps) / by the smem FFT (belt)
+    bool use_fft = false;
+    int n_gemm_rings = 0, n_fft_rings = 0, log2n = 0, fft_sch = 1;
     DevBuf<double2> d_tw;    // (cos, sin)(π t / nφ), t in [0, 2nφ), one block per distinct ring length
     DevBuf<double> d_lam;    // λ_lm(θ_k): [lm (m-major)][nhalf]
     DevBuf<double> d_FG;     // ring-space intermediates [m][ring][2*nrp]
