@@ -1,0 +1,129 @@
+# SFBB200.jl — reference-side binding of libsfb_b200.so (include/sfb_b200.h).
+#
+# NOT EXECUTED IN THIS REPOSITORY'S CI: the build image has no Julia.  It is the thin `ccall` layer a
+# maintainer of hsgg/SphericalFourierBesselDecompositions.jl would add so that `calc_Wr_lm` and
+# `power_win_mix` keep their signatures (src/windows.jl:528,540,750,751,781,809,994) and run on the GPU.
+# Argument marshalling is deliberately trivial: column-major arrays, Int64 sizes, ComplexF64 interleaved.
+module SFBB200
+
+using SparseArrays
+using LinearAlgebra: I, UniformScaling
+import SphericalFourierBesselDecompositions as SFB
+using SphericalFourierBesselDecompositions: AnlmModes, ClnnModes, ClnnBinnedModes, ConfigurationSpaceModes,
+    SeparableArray, getlmsize, getlnnsize, window_r
+using Healpix: Alm
+
+const libsfb = get(ENV, "SFB_B200_LIB", "libsfb_b200.so")
+
+function check(status::Integer)
+    status == 0 && return nothing
+    msg = unsafe_string(ccall((:sfb_last_error, libsfb), Cstring, ()))
+    error(msg)                      # ErrorException, like error()/@assert in the reference
+end
+
+# r .* √Δr .* precompute_gnlr(amodes, wmodes)   (src/windows.jl:799) — stays in Julia (input of the path)
+function rsdrgnlr(amodes, wmodes)
+    r, Δr = window_r(wmodes)
+    return r .* .√Δr .* SFB.Windows.precompute_gnlr(amodes, wmodes)
+end
+
+############################## calc_Wr_lm ##############################
+
+# src/windows.jl:528-537
+function calc_Wr_lm(win::AbstractMatrix{Float64}, LMAX::Integer, Wnside::Integer; niter=3)
+    win = win isa Matrix{Float64} ? win : Matrix{Float64}(win)
+    nr, npix = size(win)
+    Wr_lm = Matrix{ComplexF64}(undef, nr, getlmsize(LMAX))
+    GC.@preserve win Wr_lm check(ccall((:sfb_calc_wr_lm, libsfb), Int32,
+        (Ptr{Float64}, Int64, Int64, Int64, Int64, Int64, Int64, Int32, Ptr{ComplexF64}),
+        win, nr, npix, stride(win, 2), Wnside, LMAX, niter, 0, Wr_lm))
+    return Wr_lm
+end
+
+# src/windows.jl:540-545
+function calc_Wr_lm(win::SeparableArray, LMAX::Integer, Wnside::Integer; niter=3)
+    mask = Vector{Float64}(win.mask)
+    wlm = Alm(LMAX, LMAX)
+    GC.@preserve mask wlm check(ccall((:sfb_calc_wlm_mask, libsfb), Int32,
+        (Ptr{Float64}, Int64, Int64, Int64, Int64, Ptr{ComplexF64}),
+        mask, length(mask), Wnside, LMAX, niter, wlm.alm))
+    return SeparableArray(win.phi, wlm, name1=:phi, name2=:wlm)
+end
+
+############################## power_win_mix ##############################
+
+power_win_mix(win, wmodes::ConfigurationSpaceModes, cmodes::ClnnModes; kwargs...) =
+    power_win_mix(win, win, wmodes, cmodes; kwargs...)                                   # src/windows.jl:750
+power_win_mix(win, w̃, v, wmodes::ConfigurationSpaceModes, bcmodes::ClnnBinnedModes; kwargs...) =
+    power_win_mix(win, win, w̃, v, wmodes, bcmodes; kwargs...)                            # src/windows.jl:751
+
+# src/windows.jl:781-805
+function power_win_mix(win1::AbstractMatrix{Float64}, win2::AbstractMatrix{Float64},
+                       wmodes::ConfigurationSpaceModes, cmodes::ClnnModes;
+                       div2Lp1=false, interchange_NN′=false, lnn_min=1)
+    amodes = cmodes.amodes
+    G = rsdrgnlr(amodes, wmodes)
+    lnn = cmodes.lnn
+    lnnsize = getlnnsize(cmodes)
+    n = lnnsize - lnn_min + 1
+    mix = Matrix{Float64}(undef, n, n)
+    w1 = win1 isa Matrix{Float64} ? win1 : Matrix{Float64}(win1)
+    w2 = win2 === win1 ? w1 : (win2 isa Matrix{Float64} ? win2 : Matrix{Float64}(win2))
+    nr, npix = size(w1)
+    p2 = win2 === win1 ? Ptr{Float64}(C_NULL) : pointer(w2)
+    GC.@preserve w1 w2 G lnn mix check(ccall((:sfb_power_win_mix, libsfb), Int32,
+        (Ptr{Float64}, Ptr{Float64}, Int64, Int64, Int64, Int64, Ptr{Float64}, Int64, Int64, Ptr{Int64}, Int64,
+         Int64, Int32, Int32, Ptr{Float64}),
+        w1, p2, nr, npix, stride(w1, 2), amodes.nside, G, amodes.nmax, amodes.lmax, lnn, lnnsize, lnn_min,
+        div2Lp1, interchange_NN′, mix))
+    return mix
+end
+
+# src/windows.jl:809-814
+function power_win_mix(win1::SeparableArray, win2::SeparableArray, wmodes::ConfigurationSpaceModes,
+                       cmodes::ClnnModes; kwargs...)
+    bcmodes = ClnnBinnedModes(I, I, cmodes)
+    return power_win_mix(win1, win2, I, I, wmodes, bcmodes; kwargs...)
+end
+
+# SparseMatrixCSC -> (colptr, rowval, nzval, size); UniformScaling -> NULLs (src/windows.jl:829-830)
+csc(m::UniformScaling, n, dim) = (Ptr{Int64}(C_NULL), Ptr{Int64}(C_NULL), Ptr{Float64}(C_NULL), n, nothing)
+function csc(m::AbstractMatrix, n, dim)
+    s = SparseMatrixCSC{Float64,Int64}(sparse(m))
+    return (pointer(s.colptr), pointer(s.rowval), pointer(s.nzval), size(s, dim), s)
+end
+
+# src/windows.jl:994-1015 (dense, :825-862) and the separable specialisation (:942-990)
+function power_win_mix(win1, win2, w̃mat, vmat, wmodes::ConfigurationSpaceModes, bcmodes::ClnnBinnedModes;
+                       div2Lp1=false, interchange_NN′=false)
+    cmodes = bcmodes.cmodes
+    amodes = cmodes.amodes
+    G = rsdrgnlr(amodes, wmodes)
+    lnn = cmodes.lnn
+    lnnsize = getlnnsize(cmodes)
+    wc, wr, wv, LNN1, wkeep = csc(w̃mat, lnnsize, 1)
+    vc, vr, vv, LNN2, vkeep = csc(vmat, lnnsize, 2)
+    mix = Matrix{Float64}(undef, LNN1, LNN2)
+    if win1 isa SeparableArray
+        phi = Vector{Float64}(win1.phi); mask = Vector{Float64}(win1.mask)
+        GC.@preserve phi mask G lnn wkeep vkeep mix check(ccall((:sfb_power_win_mix_separable, libsfb), Int32,
+            (Ptr{Float64}, Ptr{Float64}, Int64, Int64, Int64, Ptr{Float64}, Int64, Int64, Ptr{Int64}, Int64,
+             Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Int64, Int32, Int32,
+             Ptr{Float64}),
+            phi, mask, length(phi), length(mask), amodes.nside, G, amodes.nmax, amodes.lmax, lnn, lnnsize,
+            wc, wr, wv, LNN1, vc, vr, vv, LNN2, div2Lp1, interchange_NN′, mix))
+    else
+        w1 = win1 isa Matrix{Float64} ? win1 : Matrix{Float64}(win1)
+        nr, npix = size(w1)
+        # like the reference, the second transform is also taken from win1 (src/windows.jl:1005-1006)
+        GC.@preserve w1 G lnn wkeep vkeep mix check(ccall((:sfb_power_win_mix_binned, libsfb), Int32,
+            (Ptr{Float64}, Int64, Int64, Int64, Int64, Ptr{Float64}, Int64, Int64, Ptr{Int64}, Int64,
+             Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Int64, Int32, Int32,
+             Ptr{Float64}),
+            w1, nr, npix, stride(w1, 2), amodes.nside, G, amodes.nmax, amodes.lmax, lnn, lnnsize,
+            wc, wr, wv, LNN1, vc, vr, vv, LNN2, div2Lp1, interchange_NN′, mix))
+    end
+    return mix
+end
+
+end # module

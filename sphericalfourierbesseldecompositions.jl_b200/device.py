@@ -146,8 +146,9 @@ def gather_row_slabs(slab, ranges, nout, group=None):
     hmax = max(hi - lo for lo, hi in ranges)
     send = slab if slab.shape[1] == hmax else torch.nn.functional.pad(slab, (0, hmax - slab.shape[1]))
     send = send.contiguous()
-    recv = torch.empty((world, nout, hmax), dtype=slab.dtype, device=slab.device)
-    dist.all_gather_into_tensor(recv, send, group=group)
+    recv = torch.empty(world * nout * hmax, dtype=slab.dtype, device=slab.device)
+    dist.all_gather_into_tensor(recv, send.view(-1), group=group)
+    recv = recv.view(world, nout, hmax)
     full = torch.empty((nout, nout), dtype=slab.dtype, device=slab.device)
     for g, (lo, hi) in enumerate(ranges):
         full[:, lo:hi] = recv[g, :, :hi - lo]

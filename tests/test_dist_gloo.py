@@ -1,0 +1,47 @@
+"""world_size-2 gloo test (CPU) of the multi-GPU host logic: row shards -> all-gather -> full matrix."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sfb_b200.device import gather_row_slabs, shard_rows
+    n = 37
+    rng = np.random.default_rng(3)
+    M = rng.random((n, n))                       # M[i, i']
+    ell = np.repeat(np.arange(8), [3, 5, 4, 6, 2, 7, 5, 5])
+    cost = (10.0 - ell) * np.ones(n)
+    ranges = shard_rows(cost, ell, world)
+    lo, hi = ranges[rank]
+    slab = torch.from_numpy(np.ascontiguousarray(M[lo:hi, :].T))   # (nout, rows) like DevicePipeline
+    full = gather_row_slabs(slab, ranges, n)
+    ok = np.array_equal(full.numpy().T, M)
+    out = torch.tensor([1.0 if ok else 0.0])
+    dist.all_reduce(out, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        ret.put((float(out.item()), ranges))
+    dist.destroy_process_group()
+
+
+def test_row_shard_allgather_world2():
+    ctx = mp.get_context("spawn")
+    ret = ctx.SimpleQueue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    ok, ranges = ret.get()
+    assert ok == 1.0 and ranges[0][1] == ranges[1][0] and ranges[0][1] not in (0, 37)
