@@ -114,10 +114,11 @@ __global__ void __launch_bounds__(256) what_build_kernel(const double* __restric
 }
 
 // =============================================================================================
-// Coupling-matrix block kernel.  One CTA = (ℓ, L, N):
-//   Z_N[n][r']   = Σ_r  G_ℓn[r] G_LN[r] Ŵ_ℓL[r][r']                       (DMMA,  a × nr × nr)
-//   T_N'[n][n']  = Σ_r' Z_N[n][r'] G_LN'[r'] G_ℓn'[r']   for N' >= N       (DMMA,  a × a × nr, one warp per N')
-//   M[(ℓ,n,n'),(L,N,N')] = c_L · ( T_N'[n][n'] + [N≠N'] T_N'[n'][n] )      (src/windows.jl:727-736)
+// Coupling-matrix block kernel.  One CTA = (ℓ, L, chunk of N values [N0,N1)), 8 warps:
+//   Z_N[n][r']   = Σ_r  G_ℓn[r] G_LN[r] Ŵ_ℓL[r][r']   for every N of the chunk     (DMMA, kept in shared memory)
+//   T_N,N'[n][n'] = Σ_r' Z_N[n][r'] G_LN'[r'] G_ℓn'[r']  for N' >= N               (DMMA, a × a × nr tiles; the
+//                   (N,N') tiles of the chunk are dealt round-robin to the warps, two N' per pass share loads)
+//   M[(ℓ,n,n'),(L,N,N')] = c_L · ( T[n][n'] + [N≠N'] T[n'][n] )                     (src/windows.jl:727-736)
 // With win1 ≢ win2 (SYM=false) Ŵ is not symmetric and the N<->N' partner uses Zt_N = (G_ℓ ⊙ G_LN)ᵀ Ŵᵀ instead.
 struct CmixArgs {
     const double* G;        // [ell][nmax][nrp]
@@ -129,164 +130,299 @@ struct CmixArgs {
     const int* row_n2;      // 0-based n'
     const int* a_of_ell;
     const int* pairidx;     // [L][nmax][nmax] -> output column or -1
-    const int* nl_L;
-    const int* nl_N;
+    const int* ch_L;        // blockIdx.x -> (L, N0, N1)
+    const int* ch_N0;
+    const int* ch_N1;
     double* M;
     long long ldM;
-    int ell0, lmax, nmax, nrp, S;
+    int ell0, lmax, nmax, nrp, S, NC;
     int div2Lp1, interchange;
 };
 
-constexpr int kCmixThreads = 128;
+constexpr int kCmixThreads = 256;
 constexpr int kCmixWarps = kCmixThreads / 32;
 
+__host__ __device__ constexpr int cmix_tld(int AP) { return (AP % 16 == 8) ? AP : AP + 8; }  // ≡ 8 (mod 16)
+
 template <int AT, bool SYM>
-__global__ void __launch_bounds__(kCmixThreads) cmix_block_kernel(CmixArgs p) {
+__global__ void __launch_bounds__(kCmixThreads, 1) cmix_block_kernel(CmixArgs p) {
     extern __shared__ double sm[];
     const int ell = p.ell_list[blockIdx.y];
-    const int L = p.nl_L[blockIdx.x], N = p.nl_N[blockIdx.x];
+    const int L = p.ch_L[blockIdx.x], N0 = p.ch_N0[blockIdx.x], N1 = p.ch_N1[blockIdx.x];
     const int a = p.a_of_ell[ell], b = p.a_of_ell[L];
-    if (a == 0 || N >= b) return;
+    if (a == 0 || N0 >= b) return;
     constexpr int AP = AT * 8;
-    const int S = p.S, nrp = p.nrp;
+    constexpr int TLD = cmix_tld(AP);       // staging leading dimension: double2 stores are conflict free
+    constexpr int P = SYM ? 2 : 1;          // N' tiles per warp pass (shares the Z and G_l fragment loads)
+    constexpr int NZ = SYM ? 1 : 2;
+    const int S = p.S, nrp = p.nrp, nN = N1 - N0;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-
-    double* Gl = sm;                   // [AP][S]   G_ℓn[r]
-    double* GL = Gl + AP * S;          // [nmax][S] G_LN[r]
-    double* Zs = GL + p.nmax * S;      // [AP][S]
-    double* Zt = Zs + AP * S;          // [AP][S] (only if !SYM)
-    double* Ts = Zt + (SYM ? 0 : AP * S);  // [warps][(SYM?1:2)][AP][AP+1]
-
-    // ---- stage G_ℓ and G_L rows (zero-padded) ------------------------------------------------
-    for (int x = tid; x < AP * S; x += kCmixThreads) {
-        const int n = x / S, r = x - n * S;
-        Gl[x] = (n < a && r < nrp) ? p.G[((size_t)ell * p.nmax + n) * nrp + r] : 0.0;
-    }
-    for (int x = tid; x < b * S; x += kCmixThreads) {
-        const int n = x / S, r = x - n * S;
-        GL[x] = (r < nrp) ? p.G[((size_t)L * p.nmax + n) * nrp + r] : 0.0;
-    }
-    __syncthreads();
-
-    // ---- Z phase -------------------------------------------------------------------------------
-    const double* Wh = p.What + ((size_t)(ell - p.ell0) * (p.lmax + 1) + L) * nrp * nrp;
-    const double* glN = GL + N * S;
-    for (int jt = warp; jt < nrp / 8; jt += kCmixWarps) {
-        double acc[AT][2], acct[AT][2];
-#pragma unroll
-        for (int i = 0; i < AT; ++i) acc[i][0] = acc[i][1] = acct[i][0] = acct[i][1] = 0.0;
-        for (int k0 = 0; k0 < nrp; k0 += 4) {
-            const double s = glN[k0 + t];
-            const double bw = __ldg(Wh + (size_t)(k0 + t) * nrp + jt * 8 + g);
-            double bt = 0.0;
-            if (!SYM) bt = __ldg(Wh + (size_t)(jt * 8 + g) * nrp + k0 + t);
-#pragma unroll
-            for (int i = 0; i < AT; ++i) {
-                const double av = Gl[(i * 8 + g) * S + k0 + t] * s;
-                dmma884(acc[i], av, bw);
-                if (!SYM) dmma884(acct[i], av, bt);
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < AT; ++i) {
-            double* z = Zs + (i * 8 + g) * S + jt * 8 + 2 * t;
-            z[0] = acc[i][0];
-            z[1] = acc[i][1];
-            if (!SYM) {
-                double* zt = Zt + (i * 8 + g) * S + jt * 8 + 2 * t;
-                zt[0] = acct[i][0];
-                zt[1] = acct[i][1];
-            }
-        }
-    }
-    __syncthreads();
-
-    // ---- T phase: one warp per N' ----------------------------------------------------------------
     const int r0 = p.ell_ptr[ell], nrows = p.ell_ptr[ell + 1] - r0;
+
+    double* Gl = sm;                            // [AP][S]        G_ln[r]
+    double* GL = Gl + AP * S;                   // [nmax][S]      G_LN[r]
+    double* Zs = GL + p.nmax * S;               // [NC][AP][S]
+    double* Zt = Zs + (size_t)p.NC * AP * S;    // [NC][AP][S] (only if !SYM)
+    double* Ts = Zs + (size_t)NZ * p.NC * AP * S;  // [warps][NZ][AP][TLD]
+    int* coltab = reinterpret_cast<int*>(Ts + kCmixWarps * NZ * AP * TLD);  // [NC][nmax] output column of (N, N') or -1
+    int* rowtab = coltab + p.NC * p.nmax;                                   // [nrows] orow, [nrows] n | n'<<16
+
+    // ---- stage G_l, G_L rows (zero padded) and this l-block's row table ------------------------------
+    for (int n = warp; n < AP; n += kCmixWarps) {
+        const double* src = p.G + ((size_t)ell * p.nmax + n) * nrp;
+        for (int r = lane; r < S; r += 32) Gl[n * S + r] = (n < a && r < nrp) ? src[r] : 0.0;
+    }
+    for (int n = warp; n < b; n += kCmixWarps) {
+        const double* src = p.G + ((size_t)L * p.nmax + n) * nrp;
+        for (int r = lane; r < S; r += 32) GL[n * S + r] = (r < nrp) ? src[r] : 0.0;
+    }
+    for (int x = tid; x < nrows; x += kCmixThreads) {
+        rowtab[x] = p.row_out[r0 + x];
+        rowtab[nrows + x] = p.row_n[r0 + x] | (p.row_n2[r0 + x] << 16);
+    }
+    for (int x = tid; x < nN * p.nmax; x += kCmixThreads) {
+        const int Nloc = x / p.nmax, N2 = x - Nloc * p.nmax;
+        coltab[x] = (N2 < b) ? p.pairidx[((size_t)L * p.nmax + N0 + Nloc) * p.nmax + N2] : -1;
+    }
+    __syncthreads();
+
+    // ---- Z phase: each warp owns a pair of 8-wide r' tiles (B fragments of Ŵ) and sweeps the N of the chunk --
+    const double* Wh = p.What + ((size_t)(ell - p.ell0) * (p.lmax + 1) + L) * nrp * nrp;
+    const int ntile = nrp / 8, njp = (ntile + 1) / 2;
+    const int wgrp = min(njp, kCmixWarps), nlane = kCmixWarps / wgrp;
+    const int wj = warp % wgrp, wn = warp / wgrp;
+    if (wn < nlane) {
+        for (int jtp = wj; jtp < njp; jtp += wgrp) {
+            const int jt = 2 * jtp;
+            const bool two = (jt + 1 < ntile);
+            if (SYM && nrp <= 64) {
+                // fast path: all B fragments of this tile pair live in registers, so the L2 latency of Ŵ is paid
+                // once per warp instead of once per k-step
+                double bw[16][2];
+#pragma unroll
+                for (int ks = 0; ks < 16; ++ks) {
+                    bw[ks][0] = bw[ks][1] = 0.0;
+                    if (4 * ks < nrp) {
+                        const double* wrow = Wh + (size_t)(4 * ks + t) * nrp + jt * 8 + g;
+                        bw[ks][0] = __ldg(wrow);
+                        if (two) bw[ks][1] = __ldg(wrow + 8);
+                    }
+                }
+                for (int Nloc = wn; Nloc < nN; Nloc += nlane) {
+                    const double* glN = GL + (N0 + Nloc) * S;
+                    double acc[AT][2][2];
+#pragma unroll
+                    for (int i = 0; i < AT; ++i) acc[i][0][0] = acc[i][0][1] = acc[i][1][0] = acc[i][1][1] = 0.0;
+#pragma unroll
+                    for (int ks = 0; ks < 16; ++ks) {
+                        if (4 * ks < nrp) {
+                            const double sN = glN[4 * ks + t];
+#pragma unroll
+                            for (int i = 0; i < AT; ++i) {
+                                const double av = Gl[(i * 8 + g) * S + 4 * ks + t] * sN;
+                                dmma884(acc[i][0], av, bw[ks][0]);
+                                dmma884(acc[i][1], av, bw[ks][1]);
+                            }
+                        }
+                    }
+                    double* zdst = Zs + (size_t)Nloc * AP * S;
+#pragma unroll
+                    for (int i = 0; i < AT; ++i)
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            if (j == 1 && !two) continue;
+                            const int off = (i * 8 + g) * S + (jt + j) * 8 + 2 * t;
+                            *reinterpret_cast<double2*>(zdst + off) = make_double2(acc[i][j][0], acc[i][j][1]);
+                        }
+                }
+            } else {
+                for (int Nloc = wn; Nloc < nN; Nloc += nlane) {
+                    const double* glN = GL + (N0 + Nloc) * S;
+                    double acc[AT][2][2], acct[AT][2][2];
+#pragma unroll
+                    for (int i = 0; i < AT; ++i)
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = acct[i][j][0] = acct[i][j][1] = 0.0;
+#pragma unroll 2
+                    for (int k0 = 0; k0 < nrp; k0 += 4) {
+                        const double sN = glN[k0 + t];
+                        const double* wrow = Wh + (size_t)(k0 + t) * nrp + jt * 8 + g;
+                        const double bw0 = __ldg(wrow), bw1 = two ? __ldg(wrow + 8) : 0.0;
+                        double bt0 = 0.0, bt1 = 0.0;
+                        if (!SYM) {
+                            bt0 = __ldg(Wh + (size_t)(jt * 8 + g) * nrp + k0 + t);
+                            bt1 = two ? __ldg(Wh + (size_t)(jt * 8 + 8 + g) * nrp + k0 + t) : 0.0;
+                        }
+#pragma unroll
+                        for (int i = 0; i < AT; ++i) {
+                            const double av = Gl[(i * 8 + g) * S + k0 + t] * sN;
+                            dmma884(acc[i][0], av, bw0);
+                            dmma884(acc[i][1], av, bw1);
+                            if (!SYM) {
+                                dmma884(acct[i][0], av, bt0);
+                                dmma884(acct[i][1], av, bt1);
+                            }
+                        }
+                    }
+                    double* zdst = Zs + (size_t)Nloc * AP * S;
+                    double* ztdst = Zt + (size_t)Nloc * AP * S;
+#pragma unroll
+                    for (int i = 0; i < AT; ++i)
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            if (j == 1 && !two) continue;
+                            const int off = (i * 8 + g) * S + (jt + j) * 8 + 2 * t;
+                            *reinterpret_cast<double2*>(zdst + off) = make_double2(acc[i][j][0], acc[i][j][1]);
+                            if (!SYM)
+                                *reinterpret_cast<double2*>(ztdst + off) = make_double2(acct[i][j][0], acct[i][j][1]);
+                        }
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- T phase: (N, N') tiles of the chunk dealt round-robin, P consecutive N' per pass -----------------
     const double scale = (p.div2Lp1 ? 1.0 : (2.0 * L + 1.0)) * 0.07957747154594767;  // 1/(4π)
-    double* Tw = Ts + warp * (SYM ? 1 : 2) * AP * (AP + 1);
-    const int* prow = p.pairidx + ((size_t)L * p.nmax + N) * p.nmax;
-    for (int N2 = N + warp; N2 < b; N2 += kCmixWarps) {
-        const int col = prow[N2];
-        if (col < 0) continue;  // warp-uniform
-        const double* glN2 = GL + N2 * S;
-        double acc[AT][AT][2];
+    double* Tw = Ts + warp * NZ * AP * TLD;
+    int cnt = 0;
+    for (int Nloc = 0; Nloc < nN; ++Nloc) {
+        const int N = N0 + Nloc;
+        const int npass = (b - N + P - 1) / P;
+        const int* prow = coltab + Nloc * p.nmax;
+        const double* Zn = Zs + (size_t)Nloc * AP * S;
+        const double* Ztn = Zt + (size_t)Nloc * AP * S;
+        for (int pi = (warp - cnt) & (kCmixWarps - 1); pi < npass; pi += kCmixWarps) {
+            const int N2 = N + P * pi;
+            int col[P];
+            bool any = false;
 #pragma unroll
-        for (int i = 0; i < AT; ++i)
+            for (int q = 0; q < P; ++q) {
+                col[q] = (N2 + q < b) ? prow[N2 + q] : -1;
+                any = any || (col[q] >= 0);
+            }
+            if (!any) continue;  // warp-uniform
+            double acc[P][AT][AT][2], acc2[SYM ? 1 : AT][SYM ? 1 : AT][2];
 #pragma unroll
-            for (int j = 0; j < AT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-#pragma unroll 1
-        for (int pass = 0; pass < (SYM ? 1 : 2); ++pass) {
-            const double* Zsrc = pass ? Zt : Zs;
-            for (int k0 = 0; k0 < nrp; k0 += 4) {
-                const double s = glN2[k0 + t];
-                double av[AT], bv[AT];
-#pragma unroll
-                for (int i = 0; i < AT; ++i) av[i] = Zsrc[(i * 8 + g) * S + k0 + t] * s;
-#pragma unroll
-                for (int j = 0; j < AT; ++j) bv[j] = Gl[(j * 8 + g) * S + k0 + t];
+            for (int q = 0; q < P; ++q)
 #pragma unroll
                 for (int i = 0; i < AT; ++i)
 #pragma unroll
-                    for (int j = 0; j < AT; ++j) dmma884(acc[i][j], av[i], bv[j]);
+                    for (int j = 0; j < AT; ++j) acc[q][i][j][0] = acc[q][i][j][1] = 0.0;
+            if (!SYM) {
+#pragma unroll
+                for (int i = 0; i < (SYM ? 1 : AT); ++i)
+#pragma unroll
+                    for (int j = 0; j < (SYM ? 1 : AT); ++j) acc2[i][j][0] = acc2[i][j][1] = 0.0;
             }
-            double* Tp = Tw + pass * AP * (AP + 1);
+            const double* glA = GL + N2 * S;
+            const double* glB = GL + ((N2 + 1 < b) ? N2 + 1 : N2) * S;
+#pragma unroll 2
+            for (int k0 = 0; k0 < nrp; k0 += 4) {
+                double sc[P], zv[AT], gv[AT];
+                sc[0] = glA[k0 + t];
+                if (P > 1) sc[P - 1] = glB[k0 + t];
 #pragma unroll
-            for (int i = 0; i < AT; ++i)
+                for (int i = 0; i < AT; ++i) zv[i] = Zn[(i * 8 + g) * S + k0 + t];
 #pragma unroll
-                for (int j = 0; j < AT; ++j) {
-                    double* q = Tp + (i * 8 + g) * (AP + 1) + j * 8 + 2 * t;
-                    q[0] = acc[i][j][0];
-                    q[1] = acc[i][j][1];
-                    acc[i][j][0] = acc[i][j][1] = 0.0;
+                for (int j = 0; j < AT; ++j) gv[j] = Gl[(j * 8 + g) * S + k0 + t];
+#pragma unroll
+                for (int q = 0; q < P; ++q)
+#pragma unroll
+                    for (int i = 0; i < AT; ++i) {
+                        const double av = zv[i] * sc[q];
+#pragma unroll
+                        for (int j = 0; j < AT; ++j) dmma884(acc[q][i][j], av, gv[j]);
+                    }
+                if (!SYM) {
+#pragma unroll
+                    for (int i = 0; i < (SYM ? 1 : AT); ++i) {
+                        const double av = Ztn[(i * 8 + g) * S + k0 + t] * sc[0];
+#pragma unroll
+                        for (int j = 0; j < (SYM ? 1 : AT); ++j) dmma884(acc2[i][j], av, gv[j]);
+                    }
                 }
-        }
-        __syncwarp();
-        const double* T1 = Tw;
-        const double* T2 = SYM ? Tw : Tw + AP * (AP + 1);
-        double* Mcol = p.M + (size_t)col * p.ldM;
-        const bool offdiag = (N2 != N);
-        for (int idx = lane; idx < nrows; idx += 32) {
-            const int orow = p.row_out[r0 + idx];
-            if (orow < 0) continue;
-            const int n = p.row_n[r0 + idx], n2 = p.row_n2[r0 + idx];
-            double v;
-            if (p.interchange) {
-                v = T2[n2 * (AP + 1) + n];
-            } else {
-                v = T1[n * (AP + 1) + n2];
-                if (offdiag) v += T2[n2 * (AP + 1) + n];
             }
-            Mcol[orow] = scale * v;
+#pragma unroll
+            for (int q = 0; q < P; ++q) {
+                if (col[q] < 0) continue;  // warp-uniform
+#pragma unroll
+                for (int i = 0; i < AT; ++i)
+#pragma unroll
+                    for (int j = 0; j < AT; ++j) {
+                        const int off = (i * 8 + g) * TLD + j * 8 + 2 * t;
+                        *reinterpret_cast<double2*>(Tw + off) = make_double2(acc[q][i][j][0], acc[q][i][j][1]);
+                        if (!SYM)
+                            *reinterpret_cast<double2*>(Tw + AP * TLD + off) =
+                                make_double2(acc2[SYM ? 0 : i][SYM ? 0 : j][0], acc2[SYM ? 0 : i][SYM ? 0 : j][1]);
+                    }
+                __syncwarp();
+                const double* T1 = Tw;
+                const double* T2 = SYM ? Tw : Tw + AP * TLD;
+                double* Mcol = p.M + (size_t)col[q] * p.ldM;
+                const bool offdiag = (N2 + q != N);
+                for (int idx = lane; idx < nrows; idx += 32) {
+                    const int orow = rowtab[idx];
+                    if (orow < 0) continue;
+                    const int code = rowtab[nrows + idx], n = code & 0xffff, n2 = code >> 16;
+                    double v;
+                    if (p.interchange) {
+                        v = T2[n2 * TLD + n];
+                    } else {
+                        v = T1[n * TLD + n2];
+                        if (offdiag) v += T2[n2 * TLD + n];
+                    }
+                    Mcol[orow] = scale * v;
+                }
+                __syncwarp();
+            }
         }
-        __syncwarp();
+        cnt += npass;
     }
 }
 
 template <int AT, bool SYM>
-static int launch_cmix(const CmixArgs& args, int nl, int nells, int nmax, cudaStream_t stream) {
-    const int AP = AT * 8;
-    const size_t smem = sizeof(double) * ((size_t)AP * args.S * (SYM ? 2 : 3) + (size_t)nmax * args.S +
-                                          (size_t)kCmixWarps * (SYM ? 1 : 2) * AP * (AP + 1));
+static size_t cmix_smem_bytes(int S, int nmax, int NC, int max_rows) {
+    const int AP = AT * 8, NZ = SYM ? 1 : 2;
+    return sizeof(double) * ((size_t)AP * S + (size_t)nmax * S + (size_t)NZ * NC * AP * S +
+                             (size_t)kCmixWarps * NZ * AP * cmix_tld(AP)) +
+           sizeof(int) * (2 * (size_t)max_rows + (size_t)NC * nmax);
+}
+
+template <int AT, bool SYM>
+static int launch_cmix(const CmixArgs& args, int nchunks, int nells, int nmax, int max_rows, cudaStream_t stream) {
+    const size_t smem = cmix_smem_bytes<AT, SYM>(args.S, nmax, args.NC, max_rows);
     SFB_REQUIRE(smem <= 227 * 1024, "cmix_block_kernel: shared memory footprint exceeds 227 KB (nr * nmax too large)");
     SFB_CUDA_OK(cudaFuncSetAttribute(cmix_block_kernel<AT, SYM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(nl, nells);
+    dim3 grid(nchunks, nells);
     cmix_block_kernel<AT, SYM><<<grid, kCmixThreads, smem, stream>>>(args);
     SFB_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
 template <bool SYM>
-static int launch_cmix_at(int AT, const CmixArgs& args, int nl, int nells, int nmax, cudaStream_t stream) {
+static int launch_cmix_at(int AT, const CmixArgs& args, int nchunks, int nells, int nmax, int max_rows,
+                          cudaStream_t stream) {
     switch (AT) {
-        case 1: return launch_cmix<1, SYM>(args, nl, nells, nmax, stream);
-        case 2: return launch_cmix<2, SYM>(args, nl, nells, nmax, stream);
-        case 3: return launch_cmix<3, SYM>(args, nl, nells, nmax, stream);
-        case 4: return launch_cmix<4, SYM>(args, nl, nells, nmax, stream);
+        case 1: return launch_cmix<1, SYM>(args, nchunks, nells, nmax, max_rows, stream);
+        case 2: return launch_cmix<2, SYM>(args, nchunks, nells, nmax, max_rows, stream);
+        case 3: return launch_cmix<3, SYM>(args, nchunks, nells, nmax, max_rows, stream);
+        case 4: return launch_cmix<4, SYM>(args, nchunks, nells, nmax, max_rows, stream);
         default: break;
     }
     set_error("cmix: nmax_l > 32 is not supported by this build");
     return 2;
+}
+
+// number of N values whose Z fits next to the fixed buffers in ~200 KB of shared memory
+static int cmix_chunk_size(int AT, bool sym, int S, int nmax, int max_rows) {
+    const size_t budget = 200 * 1024;
+    const int AP = AT * 8, NZ = sym ? 1 : 2;
+    const size_t fixed = sizeof(double) * ((size_t)AP * S + (size_t)nmax * S + (size_t)kCmixWarps * NZ * AP * cmix_tld(AP)) +
+                         sizeof(int) * 2 * (size_t)max_rows;
+    const size_t per = sizeof(double) * (size_t)NZ * AP * S + sizeof(int) * (size_t)nmax;
+    if (fixed + per > budget) return 0;
+    return (int)std::min<size_t>(nmax, (budget - fixed) / per);
 }
 
 // =============================================================================================
@@ -459,8 +595,7 @@ int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp
     args.row_n2 = p->d_row_n2.p;
     args.a_of_ell = p->d_a.p;
     args.pairidx = p->d_pairidx.p;
-    args.nl_L = p->d_nl_L.p;
-    args.nl_N = p->d_nl_N.p;
+    size_t chunk_fill = 0;
     args.M = d_M;
     args.ldM = ldM;
     args.lmax = lmax;
@@ -490,6 +625,7 @@ int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp
         p->launches++;
         SFB_CUDA_OK(cudaEventRecord(e1, stream));
         args.ell0 = ell0;
+        chunk_fill = 0;  // the previous l-chunk's kernels have completed (event sync below)
         for (int AT = p->amax_tiles; AT >= 1; --AT) {
             std::vector<int> ells;
             for (int l = ell0; l < ell1; ++l)
@@ -501,10 +637,36 @@ int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp
             SFB_CUDA_OK(cudaMemcpyAsync(p->d_ell_list.p + off, ells.data(), ells.size() * sizeof(int),
                                         cudaMemcpyHostToDevice, stream));
             args.ell_list = p->d_ell_list.p + off;
+            int max_rows = 0;
+            for (int l : ells) max_rows = std::max(max_rows, p->ell_ptr[l + 1] - p->ell_ptr[l]);
+            // chunk list (L, N0, N1) for this tile class
+            const int NC = cmix_chunk_size(AT, sym, p->S, p->nmax, max_rows);
+            SFB_REQUIRE(NC >= 1, "cmix: nr * nmax too large for the shared-memory tiling of this build");
+            std::vector<int> chL, chN0, chN1;
+            for (int L = 0; L <= lmax; ++L)
+                for (int n0 = 0; n0 < p->a_of_ell[L]; n0 += NC) {
+                    chL.push_back(L);
+                    chN0.push_back(n0);
+                    chN1.push_back(std::min(n0 + NC, p->a_of_ell[L]));
+                }
+            const size_t coff = chunk_fill;
+            chunk_fill += chL.size();
+            SFB_TRY(p->d_chunks.alloc(3 * (size_t)(lmax + 1) * p->nmax * 4));
+            SFB_REQUIRE(3 * chunk_fill <= p->d_chunks.n, "cmix_run: internal chunk list overflow");
+            int* dch = p->d_chunks.p + 3 * coff;
+            SFB_CUDA_OK(cudaMemcpyAsync(dch, chL.data(), chL.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+            SFB_CUDA_OK(cudaMemcpyAsync(dch + chL.size(), chN0.data(), chL.size() * sizeof(int), cudaMemcpyHostToDevice,
+                                        stream));
+            SFB_CUDA_OK(cudaMemcpyAsync(dch + 2 * chL.size(), chN1.data(), chL.size() * sizeof(int),
+                                        cudaMemcpyHostToDevice, stream));
+            args.ch_L = dch;
+            args.ch_N0 = dch + chL.size();
+            args.ch_N1 = dch + 2 * chL.size();
+            args.NC = NC;
             if (sym)
-                SFB_TRY(launch_cmix_at<true>(AT, args, p->nl, (int)ells.size(), p->nmax, stream));
+                SFB_TRY(launch_cmix_at<true>(AT, args, (int)chL.size(), (int)ells.size(), p->nmax, max_rows, stream));
             else
-                SFB_TRY(launch_cmix_at<false>(AT, args, p->nl, (int)ells.size(), p->nmax, stream));
+                SFB_TRY(launch_cmix_at<false>(AT, args, (int)chL.size(), (int)ells.size(), p->nmax, max_rows, stream));
             p->launches++;
             for (int l : ells)
                 for (int L = 0; L <= lmax; ++L) {

@@ -36,6 +36,7 @@ struct CmixPlan {
     DevBuf<double> d_W;               // [LMAX+1][nrp][nrp]
     DevBuf<double> d_What;            // [ell chunk][L][nrp][nrp]
     DevBuf<int> d_ell_list;           // per-launch list of ells
+    DevBuf<int> d_chunks;             // per-launch (L, N0, N1) chunk lists
     size_t what_budget_bytes = size_t(2) << 30;
 
     // last-run stage times (ms): wl, w3j, what, block
