@@ -454,6 +454,201 @@ __global__ void __launch_bounds__(kT) belt_synthesis_fft_kernel(const double* __
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Polar-cap rings (nφ = 4i, shifted: φ_j = (j+½)·2π/nφ) with the four-fold mirror symmetry of the ring folded in:
+// with q < nφ/4 and the four pixels j1=q, j2=nφ-1-q (φ -> 2π-φ), j3=nφ/2-1-q (φ -> π-φ), j4=nφ/2+q (φ -> π+φ),
+//   Re F_m =  Σ_q cos(mφ_q) · (m even ? f1+f2+f3+f4 : f1+f2-f3-f4)
+//   Im F_m = -Σ_q sin(mφ_q) · (m even ? f1-f2-f3+f4 : f1-f2+f3-f4)
+// so the DFT-as-GEMM runs over nφ/4 points per ring (4x fewer DMMA flops than the unfolded form).
+constexpr int kFK = 16;        // folded points (analysis) / m's per parity (synthesis) per smem chunk
+constexpr int kLdF = kFK + 4;  // 20 ≡ 4 (mod 16)
+
+// CTA = (cap ring, 32 consecutive m, 64 shells).  Row groups of 16: [cos, m even][cos, m odd][-sin, m even][-sin, m odd];
+// warp group wm uses its own folded B tile.
+__global__ void __launch_bounds__(kT) cap_analysis_kernel(const double* __restrict__ map, long long ldw, int nr, int nrp,
+                                                          RingTabs rt, const int* __restrict__ ring_list, int nrings,
+                                                          int lmax, double* __restrict__ F) {
+    __shared__ double As[64 * kLdF];
+    __shared__ double Bs[4][kFK * kLdB];
+    const int ring = ring_list[blockIdx.x], m0 = blockIdx.y * 32, sh0 = blockIdx.z * 64;
+    const int nphi = rt.nphi[ring], start = rt.start[ring];
+    const int nq = nphi >> 2;
+    const double2* tw = rt.tw + rt.twoff[ring];
+    const unsigned two_nphi = 2u * nphi;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int wm = warp >> 1, wn = warp & 1;
+    double acc[2][4][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    for (int q0 = 0; q0 < nq; q0 += kFK) {
+        {
+            // A: 32 m x 16 q lookups, each gives a cos row and a sin row
+            const int kk = tid & 15, q = q0 + kk;
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int mm = (tid >> 4) + 16 * r, m = m0 + mm;
+                double c = 0.0, sn = 0.0;
+                if (q < nq && m <= lmax) {
+                    const unsigned tt = ((unsigned)m * (unsigned)(2 * q + 1)) % two_nphi;
+                    const double2 w = tw[tt];
+                    c = w.x;
+                    sn = -w.y;
+                }
+                const int row = (mm & 1) * 16 + (mm >> 1);
+                As[row * kLdF + kk] = c;
+                As[(32 + row) * kLdF + kk] = sn;
+            }
+            // B: 16 q x 64 shells, four folded combinations
+            const int c = tid & 63;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int k2 = (tid >> 6) + 4 * r, qq = q0 + k2;
+                double f1 = 0.0, f2 = 0.0, f3 = 0.0, f4 = 0.0;
+                if (qq < nq && sh0 + c < nr) {
+                    const double* base = map + (size_t)start * ldw + sh0 + c;
+                    f1 = base[(size_t)qq * ldw];
+                    f2 = base[(size_t)(nphi - 1 - qq) * ldw];
+                    f3 = base[(size_t)(nphi / 2 - 1 - qq) * ldw];
+                    f4 = base[(size_t)(nphi / 2 + qq) * ldw];
+                }
+                const double s = f1 + f2, sp = f3 + f4, d = f1 - f2, dp = f3 - f4;
+                Bs[0][k2 * kLdB + c] = s + sp;
+                Bs[1][k2 * kLdB + c] = s - sp;
+                Bs[2][k2 * kLdB + c] = d - dp;
+                Bs[3][k2 * kLdB + c] = d + dp;
+            }
+        }
+        __syncthreads();
+        warp_gemm_ss<2, 4>(acc, As + wm * 16 * kLdF, kLdF, Bs[wm] + wn * 32, kLdB, kFK);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int rg = i * 8 + g;                    // row within the group of 16
+        const int m = m0 + 2 * rg + (wm & 1), comp = wm >> 1;
+        if (m > lmax) continue;
+        double* dst = F + ((size_t)m * nrings + ring) * 2 * nrp + (size_t)comp * nrp + sh0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int col = wn * 32 + j * 8 + 2 * t;
+            if (sh0 + col < nrp) {
+                dst[col] = acc[i][j][0];
+                dst[col + 1] = acc[i][j][1];
+            }
+        }
+    }
+}
+
+// Synthesis with the same folding: for q < nφ/4
+//   Ce = Σ_{m even} c_m ReG_m cos(mφ_q), Co = Σ_{m odd} …, Se = Σ_{m even} c_m ImG_m sin(mφ_q), So = Σ_{m odd} …
+//   f1 = Ce+Co-Se-So, f2 = Ce+Co+Se+So, f3 = Ce-Co+Se-So, f4 = Ce-Co-Se+So;   out = residual ? map - f : f
+// CTA = (tile = (cap ring, 32 folded points), 64 shells); warp group wm computes one of Ce, Co, Se, So.
+__global__ void __launch_bounds__(kT) cap_synthesis_kernel(const double* __restrict__ G, RingTabs rt,
+                                                           const int* __restrict__ tile_ring,
+                                                           const int* __restrict__ tile_q0, int nrings, int lmax, int nr,
+                                                           int nrp, const double* __restrict__ map, long long ldw,
+                                                           int residual, double* __restrict__ out) {
+    extern __shared__ double cs_smem[];
+    double* As = cs_smem;                    // [4][32][kLdF]   cos even, cos odd, sin even, sin odd
+    double* Bs = As + 4 * 32 * kLdF;         // [4][kFK][kLdB]  Re even, Re odd, Im even, Im odd (times c_m)
+    double* Rs = cs_smem;                    // [4][32][kLdB]   results, aliases the tiles after the K loop
+    const int ring = tile_ring[blockIdx.x], q0 = tile_q0[blockIdx.x], sh0 = blockIdx.y * 64;
+    const int nphi = rt.nphi[ring], start = rt.start[ring];
+    const int nq = nphi >> 2;
+    const double2* tw = rt.tw + rt.twoff[ring];
+    const unsigned two_nphi = 2u * nphi;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int wm = warp >> 1, wn = warp & 1;
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    for (int m0 = 0; m0 <= lmax; m0 += 2 * kFK) {
+        {
+            // A: 32 q x 32 m lookups -> cos / sin tiles by parity of m
+            const int row = tid & 31, q = q0 + row;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int mm = (tid >> 5) + 8 * r, m = m0 + mm;
+                double c = 0.0, sn = 0.0;
+                if (q < nq && m <= lmax) {
+                    const unsigned tt = ((unsigned)m * (unsigned)(2 * q + 1)) % two_nphi;
+                    const double2 w = tw[tt];
+                    c = w.x;
+                    sn = w.y;
+                }
+                const int par = mm & 1, kk = mm >> 1;
+                As[(par * 32 + row) * kLdF + kk] = c;
+                As[((2 + par) * 32 + row) * kLdF + kk] = sn;
+            }
+            // B: 32 m x {re, im} x 64 shells
+            const int c = tid & 63;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int mm = (tid >> 6) + 4 * r, m = m0 + mm;
+                double vr = 0.0, vi = 0.0;
+                if (m <= lmax && sh0 + c < nrp) {
+                    const double cm = (m == 0) ? 1.0 : 2.0;
+                    const double* src = G + ((size_t)m * nrings + ring) * 2 * nrp + sh0 + c;
+                    vr = cm * src[0];
+                    vi = cm * src[nrp];
+                }
+                const int par = mm & 1, kk = mm >> 1;
+                Bs[(par * kFK + kk) * kLdB + c] = vr;
+                Bs[((2 + par) * kFK + kk) * kLdB + c] = vi;
+            }
+        }
+        __syncthreads();
+        warp_gemm_ss<4, 4>(acc, As + wm * 32 * kLdF, kLdF, Bs + wm * kFK * kLdB + wn * 32, kLdB, kFK);
+        __syncthreads();
+    }
+    // exchange the four partial results through shared memory
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            double* dst = Rs + ((size_t)wm * 32 + i * 8 + g) * kLdB + wn * 32 + j * 8 + 2 * t;
+            dst[0] = acc[i][j][0];
+            dst[1] = acc[i][j][1];
+        }
+    __syncthreads();
+    const int c = tid & 63;
+    const int sh = sh0 + c;
+    if (sh < nrp) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int row = (tid >> 6) + 4 * r, q = q0 + row;
+            if (q >= nq) continue;
+            const double ce = Rs[(0 * 32 + row) * kLdB + c], co = Rs[(1 * 32 + row) * kLdB + c];
+            const double se = Rs[(2 * 32 + row) * kLdB + c], so = Rs[(3 * 32 + row) * kLdB + c];
+            const size_t p1 = (size_t)start + q, p2 = (size_t)start + nphi - 1 - q;
+            const size_t p3 = (size_t)start + nphi / 2 - 1 - q, p4 = (size_t)start + nphi / 2 + q;
+            double f1 = 0.0, f2 = 0.0, f3 = 0.0, f4 = 0.0;
+            if (sh < nr) {
+                f1 = ce + co - se - so;
+                f2 = ce + co + se + so;
+                f3 = ce - co + se - so;
+                f4 = ce - co - se + so;
+                if (residual) {
+                    f1 = map[p1 * ldw + sh] - f1;
+                    f2 = map[p2 * ldw + sh] - f2;
+                    f3 = map[p3 * ldw + sh] - f3;
+                    f4 = map[p4 * ldw + sh] - f4;
+                }
+            }
+            out[p1 * nrp + sh] = f1;
+            out[p2 * nrp + sh] = f2;
+            out[p3 * nrp + sh] = f3;
+            out[p4 * nrp + sh] = f4;
+        }
+    }
+}
+
 // a_lm[c] (+)= w Σ_k λ_lm(θ_k) (F_N ± F_S)[k][c]   CTA = (m, 64 columns, 64 l's: 32 of each parity)
 __global__ void __launch_bounds__(kT) legendre_analysis_kernel(const double* __restrict__ F,
                                                                const double* __restrict__ lam, int nrings, int nhalf,
@@ -630,7 +825,7 @@ int sht_plan_create(ShtPlan** out, int64_t nside_in, int64_t nside_out, int64_t 
 
     const int ns = p->nside;
     std::vector<int> nphi(p->nrings), start(p->nrings), shift(p->nrings), twoff(p->nrings), tile_ring, tile_j0;
-    std::vector<int> gemm_rings, fft_rings;
+    std::vector<int> gemm_rings, fft_rings, cap_rings, ctile_ring, ctile_q0;
     // belt rings (nφ = 4 nside) go through the shared-memory FFT when nside is a power of two
     p->use_fft = pow2(nside_out) && (4 * nside_out >= 8);
     p->log2n = 0;
@@ -657,13 +852,21 @@ int sht_plan_create(ShtPlan** out, int64_t nside_in, int64_t nside_out, int64_t 
         shift[idx] = sh;
         twoff[idx] = 4 * slot * (slot - 1);
         const bool fft = p->use_fft && north >= ns;
-        (fft ? fft_rings : gemm_rings).push_back(idx);
-        if (!fft)
+        const bool cap = north < ns;  // shifted ring with nφ = 4i: four-fold folded DFT-as-GEMM
+        (fft ? fft_rings : (cap ? cap_rings : gemm_rings)).push_back(idx);
+        if (cap)
+            for (int q0 = 0; q0 < np / 4; q0 += 32) {
+                ctile_ring.push_back(idx);
+                ctile_q0.push_back(q0);
+            }
+        else if (!fft)
             for (int j0 = 0; j0 < np; j0 += 64) {
                 tile_ring.push_back(idx);
                 tile_j0.push_back(j0);
             }
     }
+    p->n_cap_rings = (int)cap_rings.size();
+    p->n_ctiles = (int)ctile_ring.size();
     p->ntiles = (int)tile_ring.size();
     p->n_gemm_rings = (int)gemm_rings.size();
     p->n_fft_rings = (int)fft_rings.size();
@@ -688,6 +891,9 @@ int sht_plan_create(ShtPlan** out, int64_t nside_in, int64_t nside_out, int64_t 
     rc = rc ? rc : up(p->d_tile_ring, tile_ring);
     rc = rc ? rc : up(p->d_gemm_rings, gemm_rings);
     rc = rc ? rc : up(p->d_fft_rings, fft_rings);
+    rc = rc ? rc : up(p->d_cap_rings, cap_rings);
+    rc = rc ? rc : up(p->d_ctile_ring, ctile_ring);
+    rc = rc ? rc : up(p->d_ctile_q0, ctile_q0);
     rc = rc ? rc : up(p->d_tile_j0, tile_j0);
     rc = rc ? rc : p->d_tw.alloc((size_t)4 * ns * (ns + 1));
     rc = rc ? rc : p->d_lam.alloc(p->lmsize * p->nhalf);
@@ -719,6 +925,12 @@ static int run_analysis(ShtPlan* p, const double* map, int64_t ldw, int accumula
     if (p->n_gemm_rings > 0) {
         dim3 g1(p->n_gemm_rings, (unsigned)ceil_div(lmax + 1, 32), (unsigned)ceil_div(nrp, 64));
         ring_analysis_kernel<<<g1, kT, 0, st>>>(map, ldw, p->nr, nrp, rt, p->d_gemm_rings.p, p->nrings, lmax, p->d_FG.p);
+        SFB_CUDA_OK(cudaGetLastError());
+        p->launches++;
+    }
+    if (p->n_cap_rings > 0) {
+        dim3 gc(p->n_cap_rings, (unsigned)ceil_div(lmax + 1, 32), (unsigned)ceil_div(nrp, 64));
+        cap_analysis_kernel<<<gc, kT, 0, st>>>(map, ldw, p->nr, nrp, rt, p->d_cap_rings.p, p->nrings, lmax, p->d_FG.p);
         SFB_CUDA_OK(cudaGetLastError());
         p->launches++;
     }
@@ -772,6 +984,16 @@ int sht_map2alm(ShtPlan* p, const double* d_win, int64_t ldw, int niter, double*
             dim3 gr(p->ntiles, (unsigned)ceil_div(p->nrp, 64));
             ring_synthesis_kernel<<<gr, kT, 0, st>>>(p->d_FG.p, rt, p->d_tile_ring.p, p->d_tile_j0.p, p->nrings,
                                                      p->lmax, p->nr, p->nrp, map, ldm, 1, p->d_resid.p);
+            SFB_CUDA_OK(cudaGetLastError());
+            p->launches++;
+        }
+        if (p->n_ctiles > 0) {
+            constexpr int cs_bytes = 4 * 32 * kLdB * (int)sizeof(double);  // results alias the A/B tiles
+            static_assert(4 * 32 * kLdB >= 4 * 32 * kLdF + 4 * kFK * kLdB, "cap_synthesis smem aliasing");
+            SFB_CUDA_OK(cudaFuncSetAttribute(cap_synthesis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cs_bytes));
+            dim3 gc(p->n_ctiles, (unsigned)ceil_div(p->nrp, 64));
+            cap_synthesis_kernel<<<gc, kT, cs_bytes, st>>>(p->d_FG.p, rt, p->d_ctile_ring.p, p->d_ctile_q0.p, p->nrings,
+                                                           p->lmax, p->nr, p->nrp, map, ldm, 1, p->d_resid.p);
             SFB_CUDA_OK(cudaGetLastError());
             p->launches++;
         }

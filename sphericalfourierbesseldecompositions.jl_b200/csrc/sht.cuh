@@ -21,6 +21,8 @@ struct ShtPlan {
     DevBuf<int> d_nphi, d_start, d_shift, d_twoff;
     DevBuf<int> d_tile_ring, d_tile_j0;
     DevBuf<int> d_gemm_rings, d_fft_rings;  // rings transformed by DFT-as-GEMM (polar caps) / by the smem FFT (belt)
+    DevBuf<int> d_cap_rings, d_ctile_ring, d_ctile_q0;  // polar-cap rings: four-fold folded DFT-as-GEMM
+    int n_cap_rings = 0, n_ctiles = 0;
     bool use_fft = false;
     int n_gemm_rings = 0, n_fft_rings = 0, log2n = 0, fft_sch = 1;
     DevBuf<double2> d_tw;    // (cos, sin)(π t / nφ), t in [0, 2nφ), one block per distinct ring length

@@ -42,7 +42,8 @@ def _random_window(rng, owm, smooth=True):
 
 # --------------------------------------------------------------------------------------------- stage 1
 
-@pytest.mark.parametrize("nside,lmax,nr", [(4, 8, 3), (8, 16, 10), (8, 32, 8), (16, 40, 17), (32, 64, 5)])
+@pytest.mark.parametrize("nside,lmax,nr", [(4, 8, 3), (8, 16, 10), (8, 32, 8), (16, 40, 17), (32, 64, 5), (1, 2, 2),
+                                           (6, 12, 5), (12, 30, 9), (64, 130, 3)])  # 6, 12: not powers of two
 def test_calc_wr_lm_matches_oracle(nside, lmax, nr):
     import sfb_b200 as sfb
     rng = np.random.default_rng(nside + lmax)
