@@ -200,7 +200,7 @@ def run_b200(args):
 
     import sfb_b200 as sfb
     from sfb_b200 import _lib, configs
-    from sfb_b200.device import DevicePipeline, gather_row_slabs, shard_rows
+    from sfb_b200.device import DevicePipeline, PeerMatrix, shard_rows
     from sfb_b200.separable import SeparableArray
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -224,14 +224,16 @@ def run_b200(args):
     d_win = torch.from_numpy(np.ascontiguousarray(win.T)).cuda()
     ranges = shard_rows(pipe.row_costs, pipe.ell_of_row, world)
     lo, hi = ranges[rank]
-    slab = torch.empty((pipe.nout, hi - lo), dtype=torch.float64, device="cuda")
+    # N = 1: the matrix stays in a device buffer; N > 1: every rank holds the full matrix, rows stored into all
+    # copies by the block kernel itself (all-gather fused into the epilogue over NVLink peer memory)
+    slab = torch.empty((pipe.nout, hi - lo), dtype=torch.float64, device="cuda") if world == 1 else None
+    pm = PeerMatrix(pipe.nout) if world > 1 else None
 
     def step():
-        pipe.calc_wr_lm(d_win)
-        pipe.power_win_mix_rows(lo, hi, out=slab)
         if world > 1:
-            return gather_row_slabs(slab, ranges, pipe.nout)
-        return slab
+            return pipe.power_win_mix_fused(d_win, pm, sync=False)[0]
+        pipe.calc_wr_lm_sharded(d_win)
+        return pipe.power_win_mix_rows(lo, hi, out=slab)
 
     def barrier():
         if world > 1:
@@ -257,7 +259,7 @@ def run_b200(args):
         stage_ms["wl"].append(tim["wl_ms"])
         stage_ms["what"].append(tim["what_ms"])
         stage_ms["block"].append(tim["block_ms"])
-        launches_per_step = int(tim["launches"]) + (2 if world > 1 else 0)
+        launches_per_step = int(tim["launches"])
     ev1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -344,12 +346,15 @@ def run_b200(args):
             "data": "synthetic",
             "config": dict(wl.describe(), l2="working set (win 0.4 GB + ring buffers 0.3 GB + M %.1f GB) exceeds the "
                                              "126 MB L2, no explicit flush" % (8e-9 * n * n),
-                           parallelism=f"row-sharded x{world}" + (" + NCCL all-gather" if world > 1 else "")),
+                           parallelism=f"row-sharded x{world}" + (" (stage 1 shell-sharded + NCCL all-gather of W_lm(r); "
+                                                                   "all-gather of M fused into the block kernel via "
+                                                                   "NVLink P2P stores)" if world > 1 else "")),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
         }
         print(json.dumps(line))
     if world > 1:
+        pm.close()
         dist.destroy_process_group()
 
 

@@ -126,6 +126,20 @@ int32_t sfb_cmix_plan_destroy(sfb_cmix_plan* plan);
 int32_t sfb_power_win_mix_dev(sfb_cmix_plan* plan, const double* d_alm1, const double* d_alm2, int32_t div2Lp1,
                               int32_t interchange_NN, int64_t row_lo, int64_t row_hi, double* d_M, int64_t ldM,
                               void* stream);
+/* Fused stage 2+3 + all-gather: rows [row_lo,row_hi) are written into the FULL column-major matrix on this
+ * device (d_M_full, leading dimension ldM >= nout) and, with P2P stores over NVLink, into the full matrices of
+ * up to 7 peers (pointers obtained with sfb_ipc_open).  Callers synchronise the stream and barrier across ranks
+ * before reading.                                                                                   */
+int32_t sfb_power_win_mix_dev_peers(sfb_cmix_plan* plan, const double* d_alm1, const double* d_alm2, int32_t div2Lp1,
+                                    int32_t interchange_NN, int64_t row_lo, int64_t row_hi, double* d_M_full,
+                                    double* const* peer_M_full, int32_t npeers, int64_t ldM, void* stream);
+/* device buffers shareable between the per-GPU processes of one node (cudaIpc*); handle64 is 64 bytes */
+int32_t sfb_ipc_alloc(void** dptr, int64_t bytes, void* handle64);
+int32_t sfb_ipc_open(const void* handle64, void** dptr);
+int32_t sfb_ipc_close(void* dptr);
+int32_t sfb_ipc_free(void* dptr);
+int32_t sfb_memcpy_dev(void* dst, const void* src, int64_t bytes, void* stream);
+
 /* cost model used to balance row shards: cost[i] for each of the nout rows (host array) */
 int32_t sfb_cmix_row_costs(const sfb_cmix_plan* plan, double* cost, int64_t n);
 

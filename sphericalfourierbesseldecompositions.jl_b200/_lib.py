@@ -40,6 +40,12 @@ SIGNATURES = {
     "sfb_cmix_plan_destroy": (_i32, [_vp]),
     "sfb_power_win_mix_dev": (_i32, [_vp, _f64p, _f64p, _i32, _i32, _i64, _i64, _f64p, _i64, _vp]),
     "sfb_cmix_row_costs": (_i32, [_vp, _f64p, _i64]),
+    "sfb_power_win_mix_dev_peers": (_i32, [_vp, _f64p, _f64p, _i32, _i32, _i64, _i64, _f64p, _vp, _i32, _i64, _vp]),
+    "sfb_ipc_alloc": (_i32, [C.POINTER(_vp), _i64, _vp]),
+    "sfb_ipc_open": (_i32, [_vp, C.POINTER(_vp)]),
+    "sfb_ipc_close": (_i32, [_vp]),
+    "sfb_ipc_free": (_i32, [_vp]),
+    "sfb_memcpy_dev": (_i32, [_vp, _vp, _i64, _vp]),
 }
 
 _lib = None

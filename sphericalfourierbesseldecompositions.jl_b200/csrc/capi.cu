@@ -372,6 +372,60 @@ int32_t sfb_power_win_mix_dev(sfb_cmix_plan* plan, const double* d_alm1, const d
     g_times[6] = t0 + p->launches;
     return 0;
 }
+int32_t sfb_power_win_mix_dev_peers(sfb_cmix_plan* plan, const double* d_alm1, const double* d_alm2, int32_t div2Lp1,
+                                    int32_t interchange_NN, int64_t row_lo, int64_t row_hi, double* d_M_full,
+                                    double* const* peer_M_full, int32_t npeers, int64_t ldM, void* stream) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    auto* p = reinterpret_cast<CmixPlan*>(plan);
+    SFB_REQUIRE(p && d_M_full, "null pointer");
+    SFB_REQUIRE(npeers >= 0 && npeers <= 7, "at most 7 peers");
+    SFB_REQUIRE(ldM >= p->nout, "ldM must be the leading dimension of the full matrix");
+    double* peers[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    for (int i = 0; i < npeers; ++i) {
+        SFB_REQUIRE(peer_M_full && peer_M_full[i], "null peer pointer");
+        peers[i] = peer_M_full[i] + row_lo;
+    }
+    const double t0 = g_times[6];
+    SFB_TRY(cmix_run(p, d_alm1, d_alm2, div2Lp1, interchange_NN, row_lo, row_hi, d_M_full + row_lo, ldM,
+                     (cudaStream_t)stream, peers, npeers));
+    record_cmix_times(p);
+    g_times[6] = t0 + p->launches;
+    return 0;
+}
+
+int32_t sfb_ipc_alloc(void** dptr, int64_t bytes, void* handle64) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    SFB_REQUIRE(dptr && handle64 && bytes > 0, "bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    SFB_CUDA_OK(cudaMalloc(dptr, (size_t)bytes));
+    cudaIpcMemHandle_t h;
+    SFB_CUDA_OK(cudaIpcGetMemHandle(&h, *dptr));
+    std::memcpy(handle64, &h, 64);
+    return 0;
+}
+int32_t sfb_ipc_open(const void* handle64, void** dptr) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    SFB_REQUIRE(dptr && handle64, "bad arguments");
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle64, 64);
+    SFB_CUDA_OK(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+int32_t sfb_ipc_close(void* dptr) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    SFB_CUDA_OK(cudaIpcCloseMemHandle(dptr));
+    return 0;
+}
+int32_t sfb_ipc_free(void* dptr) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    SFB_CUDA_OK(cudaFree(dptr));
+    return 0;
+}
+int32_t sfb_memcpy_dev(void* dst, const void* src, int64_t bytes, void* stream) {
+    SFB_CUDA_OK(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return 0;
+}
+
 int32_t sfb_cmix_row_costs(const sfb_cmix_plan* plan, double* cost, int64_t n) {
     const auto* p = reinterpret_cast<const CmixPlan*>(plan);
     SFB_REQUIRE(p && cost && n == p->nout, "sfb_cmix_row_costs: bad arguments");

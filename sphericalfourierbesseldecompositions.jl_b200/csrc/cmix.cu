@@ -76,9 +76,10 @@ __global__ void wl_build_kernel(const double* __restrict__ alm1, const double* _
 // the per-element work (the quadratic form is linear in W).  One CTA = one ℓ and four L of equal parity, so
 // every W_{L1} element loaded from L2 feeds four accumulators.
 __global__ void __launch_bounds__(256) what_build_kernel(const double* __restrict__ W, const double* __restrict__ w2,
-                                                         double* __restrict__ What, int ell0, int lmax, int nrp) {
+                                                         double* __restrict__ What, const int* __restrict__ ells,
+                                                         int ell0, int lmax, int nrp) {
     extern __shared__ double wsm[];  // [4][lmax+1]
-    const int ell = ell0 + blockIdx.y;
+    const int ell = ells[blockIdx.y];
     const int gi = blockIdx.x, p = gi & 1, base = (gi >> 1) * 8 + p;
     const int par = (ell + p) & 1;
     const int KW = lmax + 1;
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(256) what_build_kernel(const double* __restric
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int L = base + 2 * q;
-            if (L <= lmax) What[((size_t)blockIdx.y * (lmax + 1) + L) * n2 + e] = acc[q];
+            if (L <= lmax) What[((size_t)(ell - ell0) * (lmax + 1) + L) * n2 + e] = acc[q];
         }
     }
 }
@@ -133,7 +134,8 @@ struct CmixArgs {
     const int* ch_L;        // blockIdx.x -> (L, N0, N1)
     const int* ch_N0;
     const int* ch_N1;
-    double* M;
+    double* M[8];           // output matrix on this device ([0]) and, for the fused all-gather, on every peer
+    int npeers;
     long long ldM;
     int ell0, lmax, nmax, nrp, S, NC;
     int div2Lp1, interchange;
@@ -359,7 +361,7 @@ __global__ void __launch_bounds__(kCmixThreads, 1) cmix_block_kernel(CmixArgs p)
                 __syncwarp();
                 const double* T1 = Tw;
                 const double* T2 = SYM ? Tw : Tw + AP * TLD;
-                double* Mcol = p.M + (size_t)col[q] * p.ldM;
+                const size_t coff = (size_t)col[q] * p.ldM;
                 const bool offdiag = (N2 + q != N);
                 for (int idx = lane; idx < nrows; idx += 32) {
                     const int orow = rowtab[idx];
@@ -372,7 +374,12 @@ __global__ void __launch_bounds__(kCmixThreads, 1) cmix_block_kernel(CmixArgs p)
                         v = T1[n * TLD + n2];
                         if (offdiag) v += T2[n2 * TLD + n];
                     }
-                    Mcol[orow] = scale * v;
+                    v *= scale;
+                    // own copy first, then the same element straight into every peer's matrix over NVLink
+                    // (P2P stores): the all-gather of the row shards is fused into the epilogue
+#pragma unroll
+                    for (int d = 0; d < 8; ++d)
+                        if (d < p.npeers) p.M[d][coff + orow] = v;
                 }
                 __syncwarp();
             }
@@ -549,8 +556,9 @@ int cmix_plan_create(CmixPlan** out, const int64_t* lnn, int64_t lnnsize, int64_
 void cmix_plan_destroy(CmixPlan* p) { delete p; }
 
 int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp1, int interchange, int64_t row_lo,
-             int64_t row_hi, double* d_M, int64_t ldM, cudaStream_t stream) {
+             int64_t row_hi, double* d_M, int64_t ldM, cudaStream_t stream, double* const* peers, int npeers) {
     SFB_REQUIRE(p && d_alm1 && d_alm2 && d_M, "cmix_run: null pointer");
+    SFB_REQUIRE(npeers >= 0 && npeers <= 7, "cmix_run: at most 7 peers");
     SFB_REQUIRE(0 <= row_lo && row_lo <= row_hi && row_hi <= p->nout, "cmix_run: bad row range");
     SFB_REQUIRE(ldM >= row_hi - row_lo, "cmix_run: ldM smaller than the row shard");
     if (row_hi == row_lo) return 0;
@@ -596,7 +604,9 @@ int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp
     args.a_of_ell = p->d_a.p;
     args.pairidx = p->d_pairidx.p;
     size_t chunk_fill = 0;
-    args.M = d_M;
+    args.M[0] = d_M;
+    for (int d = 0; d < 7; ++d) args.M[d + 1] = (d < npeers) ? peers[d] : nullptr;
+    args.npeers = npeers + 1;
     args.ldM = ldM;
     args.lmax = lmax;
     args.nmax = p->nmax;
@@ -619,8 +629,15 @@ int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp
         SFB_CUDA_OK(cudaEventCreate(&e1));
         SFB_CUDA_OK(cudaEventCreate(&e2));
         SFB_CUDA_OK(cudaEventRecord(e0, stream));
-        what_build_kernel<<<dim3(ngroups, ell1 - ell0), 256, 4 * (lmax + 1) * sizeof(double), stream>>>(
-            p->d_W.p, p->d_w2.p, p->d_What.p, ell0, lmax, nrp);
+        // only the l-blocks this row shard touches
+        std::vector<int> wells;
+        for (int l = ell0; l < ell1; ++l)
+            if (ell_used[l] && p->a_of_ell[l] > 0) wells.push_back(l);
+        SFB_TRY(p->d_what_ells.alloc(lmax + 1));
+        SFB_CUDA_OK(cudaMemcpyAsync(p->d_what_ells.p, wells.data(), wells.size() * sizeof(int), cudaMemcpyHostToDevice,
+                                    stream));
+        what_build_kernel<<<dim3(ngroups, (unsigned)wells.size()), 256, 4 * (lmax + 1) * sizeof(double), stream>>>(
+            p->d_W.p, p->d_w2.p, p->d_What.p, p->d_what_ells.p, ell0, lmax, nrp);
         SFB_CUDA_OK(cudaGetLastError());
         p->launches++;
         SFB_CUDA_OK(cudaEventRecord(e1, stream));

@@ -37,6 +37,7 @@ struct CmixPlan {
     DevBuf<double> d_What;            // [ell chunk][L][nrp][nrp]
     DevBuf<int> d_ell_list;           // per-launch list of ells
     DevBuf<int> d_chunks;             // per-launch (L, N0, N1) chunk lists
+    DevBuf<int> d_what_ells;          // l-blocks whose Ŵ is built for the current row shard
     size_t what_budget_bytes = size_t(2) << 30;
 
     // last-run stage times (ms): wl, w3j, what, block
@@ -55,8 +56,11 @@ void cmix_plan_destroy(CmixPlan* p);
 // alm layout (device): planar [lm (m-major, lmax2 = 2*lmax)][comp (re,im)][nrp], padded shells zero.
 // Writes rows [row_lo,row_hi) (0-based, of the nout x nout matrix) into d_M (column-major, leading dim ldM,
 // row row_lo at offset 0).
+// `peers` (optional): up to 7 more device pointers (peer-mapped, same offset/ldM semantics as d_M); every element
+// is also stored there, which fuses the all-gather of row shards into the kernel epilogue.
 int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp1, int interchange,
-             int64_t row_lo, int64_t row_hi, double* d_M, int64_t ldM, cudaStream_t stream);
+             int64_t row_lo, int64_t row_hi, double* d_M, int64_t ldM, cudaStream_t stream,
+             double* const* peers = nullptr, int npeers = 0);
 
 // Host complex (nr x lmsize, column-major, interleaved) -> device planar alm; layout 0 = m-major, 1 = m-fast.
 int alm_from_host(const double* h_wrlm, int64_t nr, int lmax2, int layout, DevBuf<double>& d_alm, int nrp,

@@ -463,25 +463,35 @@ __global__ void __launch_bounds__(kT) belt_synthesis_fft_kernel(const double* __
 constexpr int kFK = 16;        // folded points (analysis) / m's per parity (synthesis) per smem chunk
 constexpr int kLdF = kFK + 4;  // 20 ≡ 4 (mod 16)
 
-// CTA = (cap ring, 32 consecutive m, 64 shells).  Row groups of 16: [cos, m even][cos, m odd][-sin, m even][-sin, m odd];
+// The GEMM kernels below are templated on NI = 8-wide column tiles per warp: the CTA covers BW = 16·NI columns
+// (64 for a full shell batch; 32 / 16 when the shells are sharded over GPUs and each rank holds only a few).
+template <int NI>
+struct ColTile {
+    static constexpr int BW = 16 * NI;   // columns per CTA
+    static constexpr int LD = BW + 4;    // ≡ 4 (mod 16)
+};
+
+// CTA = (cap ring, 32 consecutive m, BW shells).  Row groups of 16: [cos, m even][cos, m odd][-sin, m even][-sin, m odd];
 // warp group wm uses its own folded B tile.
+template <int NI>
 __global__ void __launch_bounds__(kT) cap_analysis_kernel(const double* __restrict__ map, long long ldw, int nr, int nrp,
                                                           RingTabs rt, const int* __restrict__ ring_list, int nrings,
                                                           int lmax, double* __restrict__ F) {
+    constexpr int BW = ColTile<NI>::BW, LD = ColTile<NI>::LD;
     __shared__ double As[64 * kLdF];
-    __shared__ double Bs[4][kFK * kLdB];
-    const int ring = ring_list[blockIdx.x], m0 = blockIdx.y * 32, sh0 = blockIdx.z * 64;
+    __shared__ double Bs[4][kFK * LD];
+    const int ring = ring_list[blockIdx.x], m0 = blockIdx.y * 32, sh0 = blockIdx.z * BW;
     const int nphi = rt.nphi[ring], start = rt.start[ring];
     const int nq = nphi >> 2;
     const double2* tw = rt.tw + rt.twoff[ring];
     const unsigned two_nphi = 2u * nphi;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int wm = warp >> 1, wn = warp & 1;
-    double acc[2][4][2];
+    double acc[2][NI][2];
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     for (int q0 = 0; q0 < nq; q0 += kFK) {
         {
@@ -501,11 +511,9 @@ __global__ void __launch_bounds__(kT) cap_analysis_kernel(const double* __restri
                 As[row * kLdF + kk] = c;
                 As[(32 + row) * kLdF + kk] = sn;
             }
-            // B: 16 q x 64 shells, four folded combinations
-            const int c = tid & 63;
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int k2 = (tid >> 6) + 4 * r, qq = q0 + k2;
+            // B: 16 q x BW shells, four folded combinations
+            for (int x = tid; x < kFK * BW; x += kT) {
+                const int k2 = x / BW, c = x % BW, qq = q0 + k2;
                 double f1 = 0.0, f2 = 0.0, f3 = 0.0, f4 = 0.0;
                 if (qq < nq && sh0 + c < nr) {
                     const double* base = map + (size_t)start * ldw + sh0 + c;
@@ -515,14 +523,14 @@ __global__ void __launch_bounds__(kT) cap_analysis_kernel(const double* __restri
                     f4 = base[(size_t)(nphi / 2 + qq) * ldw];
                 }
                 const double s = f1 + f2, sp = f3 + f4, d = f1 - f2, dp = f3 - f4;
-                Bs[0][k2 * kLdB + c] = s + sp;
-                Bs[1][k2 * kLdB + c] = s - sp;
-                Bs[2][k2 * kLdB + c] = d - dp;
-                Bs[3][k2 * kLdB + c] = d + dp;
+                Bs[0][k2 * LD + c] = s + sp;
+                Bs[1][k2 * LD + c] = s - sp;
+                Bs[2][k2 * LD + c] = d - dp;
+                Bs[3][k2 * LD + c] = d + dp;
             }
         }
         __syncthreads();
-        warp_gemm_ss<2, 4>(acc, As + wm * 16 * kLdF, kLdF, Bs[wm] + wn * 32, kLdB, kFK);
+        warp_gemm_ss<2, NI>(acc, As + wm * 16 * kLdF, kLdF, Bs[wm] + wn * 8 * NI, LD, kFK);
         __syncthreads();
     }
 #pragma unroll
@@ -532,8 +540,8 @@ __global__ void __launch_bounds__(kT) cap_analysis_kernel(const double* __restri
         if (m > lmax) continue;
         double* dst = F + ((size_t)m * nrings + ring) * 2 * nrp + (size_t)comp * nrp + sh0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int col = wn * 32 + j * 8 + 2 * t;
+        for (int j = 0; j < NI; ++j) {
+            const int col = wn * 8 * NI + j * 8 + 2 * t;
             if (sh0 + col < nrp) {
                 dst[col] = acc[i][j][0];
                 dst[col + 1] = acc[i][j][1];
@@ -545,28 +553,30 @@ __global__ void __launch_bounds__(kT) cap_analysis_kernel(const double* __restri
 // Synthesis with the same folding: for q < nφ/4
 //   Ce = Σ_{m even} c_m ReG_m cos(mφ_q), Co = Σ_{m odd} …, Se = Σ_{m even} c_m ImG_m sin(mφ_q), So = Σ_{m odd} …
 //   f1 = Ce+Co-Se-So, f2 = Ce+Co+Se+So, f3 = Ce-Co+Se-So, f4 = Ce-Co-Se+So;   out = residual ? map - f : f
-// CTA = (tile = (cap ring, 32 folded points), 64 shells); warp group wm computes one of Ce, Co, Se, So.
+// CTA = (tile = (cap ring, 32 folded points), BW shells); warp group wm computes one of Ce, Co, Se, So.
+template <int NI>
 __global__ void __launch_bounds__(kT) cap_synthesis_kernel(const double* __restrict__ G, RingTabs rt,
                                                            const int* __restrict__ tile_ring,
                                                            const int* __restrict__ tile_q0, int nrings, int lmax, int nr,
                                                            int nrp, const double* __restrict__ map, long long ldw,
                                                            int residual, double* __restrict__ out) {
+    constexpr int BW = ColTile<NI>::BW, LD = ColTile<NI>::LD;
     extern __shared__ double cs_smem[];
     double* As = cs_smem;                    // [4][32][kLdF]   cos even, cos odd, sin even, sin odd
-    double* Bs = As + 4 * 32 * kLdF;         // [4][kFK][kLdB]  Re even, Re odd, Im even, Im odd (times c_m)
-    double* Rs = cs_smem;                    // [4][32][kLdB]   results, aliases the tiles after the K loop
-    const int ring = tile_ring[blockIdx.x], q0 = tile_q0[blockIdx.x], sh0 = blockIdx.y * 64;
+    double* Bs = As + 4 * 32 * kLdF;         // [4][kFK][LD]    Re even, Re odd, Im even, Im odd (times c_m)
+    double* Rs = cs_smem;                    // [4][32][LD]     results, aliases the tiles after the K loop
+    const int ring = tile_ring[blockIdx.x], q0 = tile_q0[blockIdx.x], sh0 = blockIdx.y * BW;
     const int nphi = rt.nphi[ring], start = rt.start[ring];
     const int nq = nphi >> 2;
     const double2* tw = rt.tw + rt.twoff[ring];
     const unsigned two_nphi = 2u * nphi;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int wm = warp >> 1, wn = warp & 1;
-    double acc[4][4][2];
+    double acc[4][NI][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     for (int m0 = 0; m0 <= lmax; m0 += 2 * kFK) {
         {
@@ -586,11 +596,9 @@ __global__ void __launch_bounds__(kT) cap_synthesis_kernel(const double* __restr
                 As[(par * 32 + row) * kLdF + kk] = c;
                 As[((2 + par) * 32 + row) * kLdF + kk] = sn;
             }
-            // B: 32 m x {re, im} x 64 shells
-            const int c = tid & 63;
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                const int mm = (tid >> 6) + 4 * r, m = m0 + mm;
+            // B: 32 m x {re, im} x BW shells
+            for (int x = tid; x < 2 * kFK * BW; x += kT) {
+                const int mm = x / BW, c = x % BW, m = m0 + mm;
                 double vr = 0.0, vi = 0.0;
                 if (m <= lmax && sh0 + c < nrp) {
                     const double cm = (m == 0) ? 1.0 : 2.0;
@@ -599,76 +607,79 @@ __global__ void __launch_bounds__(kT) cap_synthesis_kernel(const double* __restr
                     vi = cm * src[nrp];
                 }
                 const int par = mm & 1, kk = mm >> 1;
-                Bs[(par * kFK + kk) * kLdB + c] = vr;
-                Bs[((2 + par) * kFK + kk) * kLdB + c] = vi;
+                Bs[(par * kFK + kk) * LD + c] = vr;
+                Bs[((2 + par) * kFK + kk) * LD + c] = vi;
             }
         }
         __syncthreads();
-        warp_gemm_ss<4, 4>(acc, As + wm * 32 * kLdF, kLdF, Bs + wm * kFK * kLdB + wn * 32, kLdB, kFK);
+        warp_gemm_ss<4, NI>(acc, As + wm * 32 * kLdF, kLdF, Bs + wm * kFK * LD + wn * 8 * NI, LD, kFK);
         __syncthreads();
     }
     // exchange the four partial results through shared memory
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            double* dst = Rs + ((size_t)wm * 32 + i * 8 + g) * kLdB + wn * 32 + j * 8 + 2 * t;
+        for (int j = 0; j < NI; ++j) {
+            double* dst = Rs + ((size_t)wm * 32 + i * 8 + g) * LD + wn * 8 * NI + j * 8 + 2 * t;
             dst[0] = acc[i][j][0];
             dst[1] = acc[i][j][1];
         }
     __syncthreads();
-    const int c = tid & 63;
-    const int sh = sh0 + c;
-    if (sh < nrp) {
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            const int row = (tid >> 6) + 4 * r, q = q0 + row;
-            if (q >= nq) continue;
-            const double ce = Rs[(0 * 32 + row) * kLdB + c], co = Rs[(1 * 32 + row) * kLdB + c];
-            const double se = Rs[(2 * 32 + row) * kLdB + c], so = Rs[(3 * 32 + row) * kLdB + c];
-            const size_t p1 = (size_t)start + q, p2 = (size_t)start + nphi - 1 - q;
-            const size_t p3 = (size_t)start + nphi / 2 - 1 - q, p4 = (size_t)start + nphi / 2 + q;
-            double f1 = 0.0, f2 = 0.0, f3 = 0.0, f4 = 0.0;
-            if (sh < nr) {
-                f1 = ce + co - se - so;
-                f2 = ce + co + se + so;
-                f3 = ce - co + se - so;
-                f4 = ce - co - se + so;
-                if (residual) {
-                    f1 = map[p1 * ldw + sh] - f1;
-                    f2 = map[p2 * ldw + sh] - f2;
-                    f3 = map[p3 * ldw + sh] - f3;
-                    f4 = map[p4 * ldw + sh] - f4;
-                }
+    for (int x = tid; x < 32 * BW; x += kT) {
+        const int row = x / BW, c = x % BW, q = q0 + row, sh = sh0 + c;
+        if (q >= nq || sh >= nrp) continue;
+        const double ce = Rs[(0 * 32 + row) * LD + c], co = Rs[(1 * 32 + row) * LD + c];
+        const double se = Rs[(2 * 32 + row) * LD + c], so = Rs[(3 * 32 + row) * LD + c];
+        const size_t p1 = (size_t)start + q, p2 = (size_t)start + nphi - 1 - q;
+        const size_t p3 = (size_t)start + nphi / 2 - 1 - q, p4 = (size_t)start + nphi / 2 + q;
+        double f1 = 0.0, f2 = 0.0, f3 = 0.0, f4 = 0.0;
+        if (sh < nr) {
+            f1 = ce + co - se - so;
+            f2 = ce + co + se + so;
+            f3 = ce - co + se - so;
+            f4 = ce - co - se + so;
+            if (residual) {
+                f1 = map[p1 * ldw + sh] - f1;
+                f2 = map[p2 * ldw + sh] - f2;
+                f3 = map[p3 * ldw + sh] - f3;
+                f4 = map[p4 * ldw + sh] - f4;
             }
-            out[p1 * nrp + sh] = f1;
-            out[p2 * nrp + sh] = f2;
-            out[p3 * nrp + sh] = f3;
-            out[p4 * nrp + sh] = f4;
         }
+        out[p1 * nrp + sh] = f1;
+        out[p2 * nrp + sh] = f2;
+        out[p3 * nrp + sh] = f3;
+        out[p4 * nrp + sh] = f4;
     }
 }
 
-// a_lm[c] (+)= w Σ_k λ_lm(θ_k) (F_N ± F_S)[k][c]   CTA = (m, 64 columns, 64 l's: 32 of each parity)
+template <int NI>
+static constexpr int cap_synthesis_smem_bytes() {
+    constexpr int tiles = 4 * 32 * kLdF + 4 * kFK * ColTile<NI>::LD, res = 4 * 32 * ColTile<NI>::LD;
+    return (tiles > res ? tiles : res) * (int)sizeof(double);
+}
+
+// a_lm[c] (+)= w Σ_k λ_lm(θ_k) (F_N ± F_S)[k][c]   CTA = (m, BW columns, 64 l's: 32 of each parity)
+template <int NI>
 __global__ void __launch_bounds__(kT) legendre_analysis_kernel(const double* __restrict__ F,
                                                                const double* __restrict__ lam, int nrings, int nhalf,
                                                                int lmax, int nrp, double w, int accumulate,
                                                                double* __restrict__ alm) {
+    constexpr int BW = ColTile<NI>::BW, LD = ColTile<NI>::LD;
     extern __shared__ double la_smem[];
     double* As = la_smem;              // [64][kLdA]
-    double* Bp = As + 64 * kLdA;       // [32][kLdB]  F_N + F_S
-    double* Bm = Bp + 32 * kLdB;       // [32][kLdB]  F_N - F_S
-    const int m = blockIdx.x, c0 = blockIdx.y * 64, l0 = m + blockIdx.z * 64;
+    double* Bp = As + 64 * kLdA;       // [32][LD]  F_N + F_S
+    double* Bm = Bp + 32 * LD;         // [32][LD]  F_N - F_S
+    const int m = blockIdx.x, c0 = blockIdx.y * BW, l0 = m + blockIdx.z * 64;
     if (l0 > lmax) return;
     const int ncol = 2 * nrp;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int wm = warp >> 1, wn = warp & 1;
     const double* Bsel = (wm >> 1) ? Bm : Bp;
-    double acc[2][4][2];
+    double acc[2][NI][2];
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
     const double* Fm = F + (size_t)m * nrings * ncol;
 
     for (int k0 = 0; k0 < nhalf; k0 += 32) {
@@ -682,21 +693,19 @@ __global__ void __launch_bounds__(kT) legendre_analysis_kernel(const double* __r
                 if (l <= lmax && k0 + kk < nhalf) v = lam[lm_mmajor(lmax, l, m) * nhalf + k0 + kk];
                 As[row * kLdA + kk] = v;
             }
-            const int c = tid & 63;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int k2 = (tid >> 6) + 4 * q, k = k0 + k2;
+            for (int x = tid; x < 32 * BW; x += kT) {
+                const int k2 = x / BW, c = x % BW, k = k0 + k2;
                 double fn = 0.0, fs = 0.0;
                 if (k < nhalf && c0 + c < ncol) {
                     fn = Fm[(size_t)k * ncol + c0 + c];
                     if (k != nhalf - 1) fs = Fm[(size_t)(nrings - 1 - k) * ncol + c0 + c];
                 }
-                Bp[k2 * kLdB + c] = fn + fs;
-                Bm[k2 * kLdB + c] = fn - fs;
+                Bp[k2 * LD + c] = fn + fs;
+                Bm[k2 * LD + c] = fn - fs;
             }
         }
         __syncthreads();
-        warp_gemm_ss<2, 4>(acc, As + wm * 16 * kLdA, kLdA, Bsel + wn * 32, kLdB, 32);
+        warp_gemm_ss<2, NI>(acc, As + wm * 16 * kLdA, kLdA, Bsel + wn * 8 * NI, LD, 32);
         __syncthreads();
     }
 #pragma unroll
@@ -706,8 +715,8 @@ __global__ void __launch_bounds__(kT) legendre_analysis_kernel(const double* __r
         if (l > lmax) continue;
         double* dst = alm + lm_mmajor(lmax, l, m) * ncol + c0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int col = wn * 32 + j * 8 + 2 * t;
+        for (int j = 0; j < NI; ++j) {
+            const int col = wn * 8 * NI + j * 8 + 2 * t;
             if (c0 + col < ncol) {
                 if (accumulate) {
                     dst[col] += w * acc[i][j][0];
@@ -721,21 +730,23 @@ __global__ void __launch_bounds__(kT) legendre_analysis_kernel(const double* __r
     }
 }
 
-// G_m(ring)[c] = Σ_l λ_lm(θ) a_lm[c]: north = E + O, south = E - O    CTA = (m, 64 north rings, 64 columns)
+// G_m(ring)[c] = Σ_l λ_lm(θ) a_lm[c]: north = E + O, south = E - O    CTA = (m, 64 north rings, BW columns)
+template <int NI>
 __global__ void __launch_bounds__(kT) legendre_synthesis_kernel(const double* __restrict__ alm,
                                                                 const double* __restrict__ lam, int nrings, int nhalf,
                                                                 int lmax, int nrp, double* __restrict__ G) {
+    constexpr int BW = ColTile<NI>::BW, LD = ColTile<NI>::LD;
     __shared__ double Ls[32 * kLdB];  // [l (16 even-parity, 16 odd-parity)][ring]
-    __shared__ double Bs[32 * kLdB];
-    const int m = blockIdx.x, k0 = blockIdx.y * 64, c0 = blockIdx.z * 64;
+    __shared__ double Bs[32 * LD];
+    const int m = blockIdx.x, k0 = blockIdx.y * 64, c0 = blockIdx.z * BW;
     const int ncol = 2 * nrp;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int wm = warp >> 1, wn = warp & 1;
-    double accE[2][4][2], accO[2][4][2];
+    double accE[2][NI][2], accO[2][NI][2];
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) accE[i][j][0] = accE[i][j][1] = accO[i][j][0] = accO[i][j][1] = 0.0;
+        for (int j = 0; j < NI; ++j) accE[i][j][0] = accE[i][j][1] = accO[i][j][0] = accO[i][j][1] = 0.0;
 
     for (int l0 = m; l0 <= lmax; l0 += 32) {
         {
@@ -744,19 +755,21 @@ __global__ void __launch_bounds__(kT) legendre_synthesis_kernel(const double* __
             for (int q = 0; q < 8; ++q) {
                 const int k2 = (tid >> 6) + 4 * q;
                 const int l = l0 + ((k2 < 16) ? 2 * k2 : 2 * (k2 - 16) + 1);
-                double lv = 0.0, av = 0.0;
-                if (l <= lmax) {
-                    const size_t lm = lm_mmajor(lmax, l, m);
-                    if (k0 + x < nhalf) lv = lam[lm * nhalf + k0 + x];
-                    if (c0 + x < ncol) av = alm[lm * ncol + c0 + x];
-                }
+                double lv = 0.0;
+                if (l <= lmax && k0 + x < nhalf) lv = lam[lm_mmajor(lmax, l, m) * nhalf + k0 + x];
                 Ls[k2 * kLdB + x] = lv;
-                Bs[k2 * kLdB + x] = av;
+            }
+            for (int y = tid; y < 32 * BW; y += kT) {
+                const int k2 = y / BW, c = y % BW;
+                const int l = l0 + ((k2 < 16) ? 2 * k2 : 2 * (k2 - 16) + 1);
+                double av = 0.0;
+                if (l <= lmax && c0 + c < ncol) av = alm[lm_mmajor(lmax, l, m) * ncol + c0 + c];
+                Bs[k2 * LD + c] = av;
             }
         }
         __syncthreads();
-        warp_gemm_ts<2, 4>(accE, Ls + wm * 16, kLdB, Bs + wn * 32, kLdB, 16);
-        warp_gemm_ts<2, 4>(accO, Ls + 16 * kLdB + wm * 16, kLdB, Bs + 16 * kLdB + wn * 32, kLdB, 16);
+        warp_gemm_ts<2, NI>(accE, Ls + wm * 16, kLdB, Bs + wn * 8 * NI, LD, 16);
+        warp_gemm_ts<2, NI>(accO, Ls + 16 * kLdB + wm * 16, kLdB, Bs + 16 * LD + wn * 8 * NI, LD, 16);
         __syncthreads();
     }
     double* Gm = G + (size_t)m * nrings * ncol;
@@ -767,8 +780,8 @@ __global__ void __launch_bounds__(kT) legendre_synthesis_kernel(const double* __
         double* dn = Gm + (size_t)k * ncol + c0;
         double* ds = Gm + (size_t)(nrings - 1 - k) * ncol + c0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int col = wn * 32 + j * 8 + 2 * t;
+        for (int j = 0; j < NI; ++j) {
+            const int col = wn * 8 * NI + j * 8 + 2 * t;
             if (c0 + col < ncol) {
                 dn[col] = accE[i][j][0] + accO[i][j][0];
                 dn[col + 1] = accE[i][j][1] + accO[i][j][1];
@@ -780,6 +793,9 @@ __global__ void __launch_bounds__(kT) legendre_synthesis_kernel(const double* __
         }
     }
 }
+
+// column-tile width class for `cols` live columns
+static inline int pick_ni(int cols) { return cols > 32 ? 4 : (cols > 16 ? 2 : 1); }
 
 // planar [lm m-major][comp][nrp] -> interleaved complex, column-major nr x lmsize, requested column order
 __global__ void alm_to_complex_kernel(const double* __restrict__ alm, int lmax, int nr, int nrp, int layout,
@@ -929,8 +945,14 @@ static int run_analysis(ShtPlan* p, const double* map, int64_t ldw, int accumula
         p->launches++;
     }
     if (p->n_cap_rings > 0) {
-        dim3 gc(p->n_cap_rings, (unsigned)ceil_div(lmax + 1, 32), (unsigned)ceil_div(nrp, 64));
-        cap_analysis_kernel<<<gc, kT, 0, st>>>(map, ldw, p->nr, nrp, rt, p->d_cap_rings.p, p->nrings, lmax, p->d_FG.p);
+        const int ni = pick_ni(nrp);
+        dim3 gc(p->n_cap_rings, (unsigned)ceil_div(lmax + 1, 32), (unsigned)ceil_div(nrp, 16 * ni));
+        if (ni == 4)
+            cap_analysis_kernel<4><<<gc, kT, 0, st>>>(map, ldw, p->nr, nrp, rt, p->d_cap_rings.p, p->nrings, lmax, p->d_FG.p);
+        else if (ni == 2)
+            cap_analysis_kernel<2><<<gc, kT, 0, st>>>(map, ldw, p->nr, nrp, rt, p->d_cap_rings.p, p->nrings, lmax, p->d_FG.p);
+        else
+            cap_analysis_kernel<1><<<gc, kT, 0, st>>>(map, ldw, p->nr, nrp, rt, p->d_cap_rings.p, p->nrings, lmax, p->d_FG.p);
         SFB_CUDA_OK(cudaGetLastError());
         p->launches++;
     }
@@ -944,12 +966,24 @@ static int run_analysis(ShtPlan* p, const double* map, int64_t ldw, int accumula
         SFB_CUDA_OK(cudaGetLastError());
         p->launches++;
     }
-    dim3 g2(lmax + 1, (unsigned)ceil_div(2 * nrp, 64), (unsigned)ceil_div(lmax + 1, 64));
+    const int nil = pick_ni(2 * nrp);
+    dim3 g2(lmax + 1, (unsigned)ceil_div(2 * nrp, 16 * nil), (unsigned)ceil_div(lmax + 1, 64));
     const double w = 4.0 * 3.14159265358979323846 / (double)p->npix;
-    constexpr int la_smem_bytes = (64 * kLdA + 2 * 32 * kLdB) * (int)sizeof(double);
-    SFB_CUDA_OK(cudaFuncSetAttribute(legendre_analysis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, la_smem_bytes));
-    legendre_analysis_kernel<<<g2, kT, la_smem_bytes, st>>>(p->d_FG.p, p->d_lam.p, p->nrings, p->nhalf, lmax, nrp, w, accumulate,
-                                                d_alm);
+    const int la_smem_bytes = (64 * kLdA + 2 * 32 * (16 * nil + 4)) * (int)sizeof(double);
+#define SFB_LAUNCH_LA(NI_)                                                                                            \
+    do {                                                                                                              \
+        SFB_CUDA_OK(cudaFuncSetAttribute(legendre_analysis_kernel<NI_>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                         la_smem_bytes));                                                             \
+        legendre_analysis_kernel<NI_><<<g2, kT, la_smem_bytes, st>>>(p->d_FG.p, p->d_lam.p, p->nrings, p->nhalf, lmax, \
+                                                                     nrp, w, accumulate, d_alm);                      \
+    } while (0)
+    if (nil == 4)
+        SFB_LAUNCH_LA(4);
+    else if (nil == 2)
+        SFB_LAUNCH_LA(2);
+    else
+        SFB_LAUNCH_LA(1);
+#undef SFB_LAUNCH_LA
     SFB_CUDA_OK(cudaGetLastError());
     p->launches += 1;
     return 0;
@@ -976,8 +1010,14 @@ int sht_map2alm(ShtPlan* p, const double* d_win, int64_t ldw, int niter, double*
     RingTabs rt{p->d_nphi.p, p->d_start.p, p->d_shift.p, p->d_twoff.p, p->d_tw.p};
     SFB_TRY(run_analysis(p, map, ldm, 0, d_alm, st));
     for (int it = 0; it < niter; ++it) {
-        dim3 gs(p->lmax + 1, (unsigned)ceil_div(p->nhalf, 64), (unsigned)ceil_div(2 * p->nrp, 64));
-        legendre_synthesis_kernel<<<gs, kT, 0, st>>>(d_alm, p->d_lam.p, p->nrings, p->nhalf, p->lmax, p->nrp, p->d_FG.p);
+        const int nil = pick_ni(2 * p->nrp);
+        dim3 gs(p->lmax + 1, (unsigned)ceil_div(p->nhalf, 64), (unsigned)ceil_div(2 * p->nrp, 16 * nil));
+        if (nil == 4)
+            legendre_synthesis_kernel<4><<<gs, kT, 0, st>>>(d_alm, p->d_lam.p, p->nrings, p->nhalf, p->lmax, p->nrp, p->d_FG.p);
+        else if (nil == 2)
+            legendre_synthesis_kernel<2><<<gs, kT, 0, st>>>(d_alm, p->d_lam.p, p->nrings, p->nhalf, p->lmax, p->nrp, p->d_FG.p);
+        else
+            legendre_synthesis_kernel<1><<<gs, kT, 0, st>>>(d_alm, p->d_lam.p, p->nrings, p->nhalf, p->lmax, p->nrp, p->d_FG.p);
         SFB_CUDA_OK(cudaGetLastError());
         p->launches += 1;
         if (p->ntiles > 0) {
@@ -988,12 +1028,24 @@ int sht_map2alm(ShtPlan* p, const double* d_win, int64_t ldw, int niter, double*
             p->launches++;
         }
         if (p->n_ctiles > 0) {
-            constexpr int cs_bytes = 4 * 32 * kLdB * (int)sizeof(double);  // results alias the A/B tiles
-            static_assert(4 * 32 * kLdB >= 4 * 32 * kLdF + 4 * kFK * kLdB, "cap_synthesis smem aliasing");
-            SFB_CUDA_OK(cudaFuncSetAttribute(cap_synthesis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cs_bytes));
-            dim3 gc(p->n_ctiles, (unsigned)ceil_div(p->nrp, 64));
-            cap_synthesis_kernel<<<gc, kT, cs_bytes, st>>>(p->d_FG.p, rt, p->d_ctile_ring.p, p->d_ctile_q0.p, p->nrings,
-                                                           p->lmax, p->nr, p->nrp, map, ldm, 1, p->d_resid.p);
+            const int ni = pick_ni(p->nrp);
+            dim3 gc(p->n_ctiles, (unsigned)ceil_div(p->nrp, 16 * ni));
+#define SFB_LAUNCH_CS(NI_)                                                                                             \
+    do {                                                                                                               \
+        constexpr int cs_bytes = cap_synthesis_smem_bytes<NI_>();                                                      \
+        SFB_CUDA_OK(cudaFuncSetAttribute(cap_synthesis_kernel<NI_>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                         cs_bytes));                                                                   \
+        cap_synthesis_kernel<NI_><<<gc, kT, cs_bytes, st>>>(p->d_FG.p, rt, p->d_ctile_ring.p, p->d_ctile_q0.p,         \
+                                                            p->nrings, p->lmax, p->nr, p->nrp, map, ldm, 1,            \
+                                                            p->d_resid.p);                                             \
+    } while (0)
+            if (ni == 4)
+                SFB_LAUNCH_CS(4);
+            else if (ni == 2)
+                SFB_LAUNCH_CS(2);
+            else
+                SFB_LAUNCH_CS(1);
+#undef SFB_LAUNCH_CS
             SFB_CUDA_OK(cudaGetLastError());
             p->launches++;
         }

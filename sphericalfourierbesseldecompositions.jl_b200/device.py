@@ -22,6 +22,12 @@ def _torch():
     return torch
 
 
+def shard_shells(nr, world):
+    """Contiguous shell ranges [lo, hi) per rank for stage 1 (shells are independent, src/windows.jl:531-535)."""
+    base = -(-nr // world)
+    return [(min(g * base, nr), min((g + 1) * base, nr)) for g in range(world)]
+
+
 def shard_rows(costs, ell_of_row, world):
     """Contiguous row ranges [lo, hi) per rank, cut only where `ell_of_row` changes, balancing `costs`.
     Returns a list of `world` (lo, hi) tuples covering [0, n)."""
@@ -77,6 +83,9 @@ class DevicePipeline:
         if self._cmix:
             self.lib.sfb_cmix_plan_destroy(self._cmix)
             self._cmix = C.c_void_p()
+        if getattr(self, "_sht_shard", None):
+            self.lib.sfb_sht_plan_destroy(self._sht_shard)
+            self._sht_shard = None
 
     def __del__(self):
         try:
@@ -104,6 +113,42 @@ class DevicePipeline:
                                                    self._stream()))
         return out  # out.T is the Julia (nr, lmsize) matrix
 
+    def calc_wr_lm_sharded(self, d_win, group=None, niter=3):
+        """Stage 1 with the shells partitioned over the ranks of `group`, then an all-gather of the planar
+        W_lm(r) shards (cfg5: 74 MB in total) so that every rank can build all W_{L1}."""
+        torch = _torch()
+        import torch.distributed as dist
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if world == 1:
+            return self.calc_wr_lm(d_win, niter)
+        rank = dist.get_rank(group)
+        ranges = shard_shells(self.nr, world)
+        lo, hi = ranges[rank]
+        cnt = hi - lo
+        nrp_g = 8 * (-(-max(h - l for l, h in ranges) // 8))
+        nrp_mine = 8 * (-(-max(cnt, 1) // 8))
+        if getattr(self, "_sht_shard", None) is None:
+            self._sht_shard = C.c_void_p()
+            _lib.check(self.lib.sfb_sht_plan_create(C.byref(self._sht_shard), self.nside_in, self.amodes.nside,
+                                                    self.LMAX, max(cnt, 1)))
+            self._alm_shard = torch.zeros(self.lmsize * 2 * nrp_mine, dtype=torch.float64, device=self.device)
+            self._alm_recv = torch.empty(world * self.lmsize * 2 * nrp_g, dtype=torch.float64, device=self.device)
+        if cnt > 0:
+            _lib.check(self.lib.sfb_calc_wr_lm_dev(self._sht_shard, d_win.data_ptr() + 8 * lo, self.nr, niter,
+                                                   self._alm_shard.data_ptr(), self._stream()))
+        send = self._alm_shard
+        if nrp_mine != nrp_g:
+            send = torch.nn.functional.pad(send.view(self.lmsize, 2, nrp_mine), (0, nrp_g - nrp_mine)).contiguous().view(-1)
+        dist.all_gather_into_tensor(self._alm_recv, send, group=group)
+        nrp = self.alm.numel() // (self.lmsize * 2)
+        full = self.alm.view(self.lmsize, 2, nrp)
+        full.zero_()
+        recv = self._alm_recv.view(world, self.lmsize, 2, nrp_g)
+        for g, (l, h) in enumerate(ranges):
+            if h > l:
+                full[:, :, l:h] = recv[g, :, :, :h - l]
+        return self.alm
+
     # ---- stage 2+3 -----------------------------------------------------------------------------
     def power_win_mix_rows(self, lo, hi, out=None, alm2=None, div2Lp1=False, interchange_NN=False):
         """Rows [lo, hi) of M as a torch tensor of shape (nout, hi-lo) (memory = column-major (hi-lo) x nout)."""
@@ -121,6 +166,24 @@ class DevicePipeline:
         return self.power_win_mix_rows(0, self.nout, **kw)
 
     # ---- multi-GPU -----------------------------------------------------------------------------
+    def power_win_mix_fused(self, d_win, peer_matrix, div2Lp1=False, interchange_NN=False, sync=True):
+        """Row-sharded coupling matrix whose all-gather is fused into the block kernel: this rank's rows are stored
+        into `peer_matrix` on every GPU over NVLink.  Returns (tensor view of the local full matrix, ranges); the
+        tensor holds Mᵀ in C order (= M in Julia's column-major order)."""
+        torch = _torch()
+        import torch.distributed as dist
+        pm = peer_matrix
+        self.calc_wr_lm_sharded(d_win, pm.group)
+        ranges = shard_rows(self.row_costs, self.ell_of_row, pm.world)
+        lo, hi = ranges[pm.rank]
+        _lib.check(self.lib.sfb_power_win_mix_dev_peers(self._cmix, self.alm.data_ptr(), self.alm.data_ptr(),
+                                                        int(div2Lp1), int(interchange_NN), lo, hi, pm.ptr,
+                                                        pm.peer_array, len(pm.peer_ptrs), self.nout, self._stream()))
+        if sync:
+            torch.cuda.synchronize()
+            dist.barrier(pm.group)   # every rank's stores have landed in every copy
+        return pm.tensor, ranges
+
     def power_win_mix_sharded(self, d_win, group=None, gather=True, **kw):
         """Row-sharded coupling matrix over the ranks of `group`; with gather=True every rank returns the
         full matrix as a (nout, nout) tensor holding Mᵀ in C order (= M in Julia's column-major order)."""
@@ -128,13 +191,62 @@ class DevicePipeline:
         import torch.distributed as dist
         world = dist.get_world_size(group) if dist.is_initialized() else 1
         rank = dist.get_rank(group) if dist.is_initialized() else 0
-        self.calc_wr_lm(d_win)
+        self.calc_wr_lm_sharded(d_win, group)
         ranges = shard_rows(self.row_costs, self.ell_of_row, world)
         lo, hi = ranges[rank]
         slab = self.power_win_mix_rows(lo, hi, **kw)  # (nout, hi-lo)
         if world == 1 or not gather:
             return slab, ranges
         return gather_row_slabs(slab, ranges, self.nout, group), ranges
+
+
+class _DevArray:
+    """__cuda_array_interface__ holder so torch can view a library-owned device buffer without a copy."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+
+class PeerMatrix:
+    """Full nout x nout matrix on every rank, IPC-mapped into all peers of the node, so that the block kernel can
+    store each element it produces directly into every GPU's copy over NVLink (fused all-gather)."""
+
+    def __init__(self, nout, group=None):
+        torch = _torch()
+        import torch.distributed as dist
+        self.lib = _lib.load()
+        self.nout = nout
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        if self.world > 8:
+            raise ValueError("PeerMatrix supports at most 8 GPUs of one node")
+        self.ptr = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        _lib.check(self.lib.sfb_ipc_alloc(C.byref(self.ptr), 8 * nout * nout, handle))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle.raw), group=group)
+        self.peer_ptrs = []
+        for g, h in enumerate(handles):
+            if g == self.rank:
+                continue
+            q = C.c_void_p()
+            _lib.check(self.lib.sfb_ipc_open(C.create_string_buffer(h, 64), C.byref(q)))
+            self.peer_ptrs.append(q)
+        self.peer_array = (C.c_void_p * max(1, len(self.peer_ptrs)))(*[q.value for q in self.peer_ptrs])
+        self.tensor = torch.as_tensor(_DevArray(self.ptr.value, (nout, nout)), device=torch.device("cuda", torch.cuda.current_device()))
+
+    def close(self):
+        import torch.distributed as dist
+        if self.ptr:
+            _torch().cuda.synchronize()
+            dist.barrier(self.group)
+            for q in self.peer_ptrs:
+                self.lib.sfb_ipc_close(q)
+            dist.barrier(self.group)
+            self.lib.sfb_ipc_free(self.ptr)
+            self.ptr = C.c_void_p()
+            self.peer_ptrs = []
 
 
 def gather_row_slabs(slab, ranges, nout, group=None):
