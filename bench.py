@@ -229,11 +229,32 @@ def run_b200(args):
     slab = torch.empty((pipe.nout, hi - lo), dtype=torch.float64, device="cuda") if world == 1 else None
     pm = PeerMatrix(pipe.nout) if world > 1 else None
 
+    xmode = os.environ.get("SFB_BENCH_EXCHANGE", "dma")   # dma | stores | nccl
+    fused = xmode in ("dma", "stores")
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    if world > 1 and not fused:
+        from sfb_b200.device import gather_row_slabs
+        slab = torch.empty((pipe.nout, hi - lo), dtype=torch.float64, device="cuda")
+
     def step():
-        if world > 1:
-            return pipe.power_win_mix_fused(d_win, pm, sync=False)[0]
+        evs[0].record()
         pipe.calc_wr_lm_sharded(d_win)
-        return pipe.power_win_mix_rows(lo, hi, out=slab)
+        evs[1].record()
+        if world > 1 and fused:
+            _lib.check(lib.sfb_power_win_mix_dev_peers(pipe._cmix, pipe.alm.data_ptr(), pipe.alm.data_ptr(), 0, 0, lo, hi,
+                                                       pm.ptr, pm.peer_array,
+                                                       len(pm.peer_ptrs) if xmode == "stores" else 0, pipe.nout,
+                                                       pipe._stream()))
+            if xmode == "dma":
+                _lib.check(lib.sfb_push_rows_to_peers(pm.ptr, pm.peer_array, len(pm.peer_ptrs), lo, hi, pipe.nout,
+                                                      pipe.nout, pipe._stream()))
+            out = pm.tensor
+        else:
+            out = pipe.power_win_mix_rows(lo, hi, out=slab)
+            if world > 1:
+                out = gather_row_slabs(slab, ranges, pipe.nout)
+        evs[2].record()
+        return out
 
     def barrier():
         if world > 1:
@@ -244,7 +265,7 @@ def run_b200(args):
         full = step()
     barrier()
     tim = _lib.timings()
-    stage_ms = {"stage1": [], "wl": [], "what": [], "block": []}
+    stage_ms = {"stage1": [], "wl": [], "what": [], "block": [], "stage1_incl_gather": [], "stage23_incl_exchange": []}
     launches_per_step = 0
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -259,6 +280,9 @@ def run_b200(args):
         stage_ms["wl"].append(tim["wl_ms"])
         stage_ms["what"].append(tim["what_ms"])
         stage_ms["block"].append(tim["block_ms"])
+        torch.cuda.synchronize()
+        stage_ms["stage1_incl_gather"].append(evs[0].elapsed_time(evs[1]))
+        stage_ms["stage23_incl_exchange"].append(evs[1].elapsed_time(evs[2]))
         launches_per_step = int(tim["launches"])
     ev1.record()
     barrier()
@@ -269,6 +293,11 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     value = n * n / (ms * 1e-3)
+    per_rank = None
+    if world > 1:
+        mine = {"rank": rank, "rows": [int(lo), int(hi)], **{k: round(statistics.mean(v), 3) for k, v in stage_ms.items()}}
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
 
     # ---- roofline of the dominant kernel (measured live: CUDA events on the launching stream, inside the lib) ----
     block_ms = statistics.mean(stage_ms["block"])
@@ -347,9 +376,10 @@ def run_b200(args):
             "config": dict(wl.describe(), l2="working set (win 0.4 GB + ring buffers 0.3 GB + M %.1f GB) exceeds the "
                                              "126 MB L2, no explicit flush" % (8e-9 * n * n),
                            parallelism=f"row-sharded x{world}" + (" (stage 1 shell-sharded + NCCL all-gather of W_lm(r); "
-                                                                   "all-gather of M fused into the block kernel via "
-                                                                   "NVLink P2P stores)" if world > 1 else "")),
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+                                                                   "rows of M pushed into every GPU's full "
+                                                                   "matrix by pitched P2P copies over NVLink)"
+                                                                   if world > 1 else "")),
+            "roofline": roofline, "per_rank": per_rank, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
         }
         print(json.dumps(line))

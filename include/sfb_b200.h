@@ -133,6 +133,10 @@ int32_t sfb_power_win_mix_dev(sfb_cmix_plan* plan, const double* d_alm1, const d
 int32_t sfb_power_win_mix_dev_peers(sfb_cmix_plan* plan, const double* d_alm1, const double* d_alm2, int32_t div2Lp1,
                                     int32_t interchange_NN, int64_t row_lo, int64_t row_hi, double* d_M_full,
                                     double* const* peer_M_full, int32_t npeers, int64_t ldM, void* stream);
+/* copy-engine variant of the exchange: rows [row_lo,row_hi) of this device's full matrix -> the same rows of each
+ * peer's full matrix (one pitched P2P copy per peer, concurrent, ordered after and joined back into `stream`) */
+int32_t sfb_push_rows_to_peers(const double* d_M_full, double* const* peer_M_full, int32_t npeers, int64_t row_lo,
+                               int64_t row_hi, int64_t ncols, int64_t ldM, void* stream);
 /* device buffers shareable between the per-GPU processes of one node (cudaIpc*); handle64 is 64 bytes */
 int32_t sfb_ipc_alloc(void** dptr, int64_t bytes, void* handle64);
 int32_t sfb_ipc_open(const void* handle64, void** dptr);

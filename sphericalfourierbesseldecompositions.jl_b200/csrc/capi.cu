@@ -393,6 +393,41 @@ int32_t sfb_power_win_mix_dev_peers(sfb_cmix_plan* plan, const double* d_alm1, c
     return 0;
 }
 
+// Push rows [row_lo,row_hi) of this device's full matrix into the same rows of every peer's full matrix with one
+// pitched peer-to-peer copy per peer (copy engines over NVLink), each on its own stream, ordered after `stream`.
+int32_t sfb_push_rows_to_peers(const double* d_M_full, double* const* peer_M_full, int32_t npeers, int64_t row_lo,
+                               int64_t row_hi, int64_t ncols, int64_t ldM, void* stream) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    SFB_REQUIRE(d_M_full && npeers >= 0 && npeers <= 7, "bad arguments");
+    SFB_REQUIRE(0 <= row_lo && row_lo <= row_hi && row_hi <= ldM, "bad row range");
+    if (row_hi == row_lo || npeers == 0) return 0;
+    static cudaStream_t ps[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    static cudaEvent_t ready = nullptr, done[7];
+    static int ps_dev = -1;
+    int dev = 0;
+    SFB_CUDA_OK(cudaGetDevice(&dev));
+    if (!ready || ps_dev != dev) {
+        SFB_CUDA_OK(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+        for (int i = 0; i < 7; ++i) {
+            SFB_CUDA_OK(cudaStreamCreateWithFlags(&ps[i], cudaStreamNonBlocking));
+            SFB_CUDA_OK(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+        }
+        ps_dev = dev;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    SFB_CUDA_OK(cudaEventRecord(ready, st));
+    const size_t pitch = (size_t)ldM * sizeof(double), width = (size_t)(row_hi - row_lo) * sizeof(double);
+    for (int i = 0; i < npeers; ++i) {
+        SFB_REQUIRE(peer_M_full && peer_M_full[i], "null peer pointer");
+        SFB_CUDA_OK(cudaStreamWaitEvent(ps[i], ready, 0));
+        SFB_CUDA_OK(cudaMemcpy2DAsync(peer_M_full[i] + row_lo, pitch, d_M_full + row_lo, pitch, width, (size_t)ncols,
+                                      cudaMemcpyDeviceToDevice, ps[i]));
+        SFB_CUDA_OK(cudaEventRecord(done[i], ps[i]));
+        SFB_CUDA_OK(cudaStreamWaitEvent(st, done[i], 0));
+    }
+    return 0;
+}
+
 int32_t sfb_ipc_alloc(void** dptr, int64_t bytes, void* handle64) {
     std::lock_guard<std::mutex> lk(g_mutex);
     SFB_REQUIRE(dptr && handle64 && bytes > 0, "bad arguments");

@@ -166,19 +166,25 @@ class DevicePipeline:
         return self.power_win_mix_rows(0, self.nout, **kw)
 
     # ---- multi-GPU -----------------------------------------------------------------------------
-    def power_win_mix_fused(self, d_win, peer_matrix, div2Lp1=False, interchange_NN=False, sync=True):
-        """Row-sharded coupling matrix whose all-gather is fused into the block kernel: this rank's rows are stored
-        into `peer_matrix` on every GPU over NVLink.  Returns (tensor view of the local full matrix, ranges); the
-        tensor holds Mᵀ in C order (= M in Julia's column-major order)."""
+    def power_win_mix_fused(self, d_win, peer_matrix, div2Lp1=False, interchange_NN=False, sync=True, mode="dma"):
+        """Row-sharded coupling matrix assembled in `peer_matrix` on every GPU without NCCL or a placement pass.
+        mode="dma": the block kernel writes this rank's rows into its own full matrix and the copy engines push
+        them to every peer (pitched P2P copies, one stream per peer); mode="stores": the block kernel itself
+        stores every element into all copies over NVLink.  Returns (tensor view of the local full matrix,
+        ranges); the tensor holds Mᵀ in C order (= M in Julia's column-major order)."""
         torch = _torch()
         import torch.distributed as dist
         pm = peer_matrix
         self.calc_wr_lm_sharded(d_win, pm.group)
         ranges = shard_rows(self.row_costs, self.ell_of_row, pm.world)
         lo, hi = ranges[pm.rank]
+        nstore = len(pm.peer_ptrs) if mode == "stores" else 0
         _lib.check(self.lib.sfb_power_win_mix_dev_peers(self._cmix, self.alm.data_ptr(), self.alm.data_ptr(),
                                                         int(div2Lp1), int(interchange_NN), lo, hi, pm.ptr,
-                                                        pm.peer_array, len(pm.peer_ptrs), self.nout, self._stream()))
+                                                        pm.peer_array, nstore, self.nout, self._stream()))
+        if mode != "stores":
+            _lib.check(self.lib.sfb_push_rows_to_peers(pm.ptr, pm.peer_array, len(pm.peer_ptrs), lo, hi, self.nout,
+                                                       self.nout, self._stream()))
         if sync:
             torch.cuda.synchronize()
             dist.barrier(pm.group)   # every rank's stores have landed in every copy

@@ -39,8 +39,12 @@ def _worker(rank, world, port, ret):
     ok = rel(pipe.alm, alm_single) < 1e-13 and rel(full, single) < 1e-13
     from sfb_b200.device import PeerMatrix
     pm = PeerMatrix(pipe.nout)
-    fused, _ = pipe.power_win_mix_fused(d_win, pm)
-    ok = ok and rel(fused, single) < 1e-13
+    for mode in ("dma", "stores"):
+        pm.tensor.zero_()
+        torch.cuda.synchronize()
+        dist.barrier()
+        fused, _ = pipe.power_win_mix_fused(d_win, pm, mode=mode)
+        ok = ok and rel(fused, single) < 1e-13
     pm.close()
     flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
