@@ -222,15 +222,15 @@ def run_b200(args):
     pipe = DevicePipeline(wl.wmodes, wl.cmodes, wl.G)
     # window resident in HBM in Julia memory order: (npix, nr) C-contiguous == (nr, npix) column-major
     d_win = torch.from_numpy(np.ascontiguousarray(win.T)).cuda()
-    ranges = shard_rows(pipe.row_costs, pipe.ell_of_row, world)
+    xmode = os.environ.get("SFB_BENCH_EXCHANGE", "cols")   # cols | dma | stores | nccl
+    ranges = shard_rows(pipe.col_costs if xmode == "cols" else pipe.row_costs, pipe.ell_of_row, world)
     lo, hi = ranges[rank]
     # N = 1: the matrix stays in a device buffer; N > 1: every rank holds the full matrix, rows stored into all
     # copies by the block kernel itself (all-gather fused into the epilogue over NVLink peer memory)
     slab = torch.empty((pipe.nout, hi - lo), dtype=torch.float64, device="cuda") if world == 1 else None
     pm = PeerMatrix(pipe.nout) if world > 1 else None
 
-    xmode = os.environ.get("SFB_BENCH_EXCHANGE", "dma")   # dma | stores | nccl
-    fused = xmode in ("dma", "stores")
+    fused = xmode in ("cols", "dma", "stores")
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     if world > 1 and not fused:
         from sfb_b200.device import gather_row_slabs
@@ -240,7 +240,14 @@ def run_b200(args):
         evs[0].record()
         pipe.calc_wr_lm_sharded(d_win)
         evs[1].record()
-        if world > 1 and fused:
+        if world > 1 and xmode == "cols":
+            _lib.check(lib.sfb_power_win_mix_block_dev(pipe._cmix, pipe.alm.data_ptr(), pipe.alm.data_ptr(), 0, 0, 0,
+                                                       pipe.nout, lo, hi, pm.ptr.value + 8 * lo * pipe.nout, pipe.nout,
+                                                       pipe._stream()))
+            _lib.check(lib.sfb_push_cols_to_peers(pm.ptr, pm.peer_array, len(pm.peer_ptrs), lo, hi, pipe.nout,
+                                                  pipe._stream()))
+            out = pm.tensor
+        elif world > 1 and fused:
             _lib.check(lib.sfb_power_win_mix_dev_peers(pipe._cmix, pipe.alm.data_ptr(), pipe.alm.data_ptr(), 0, 0, lo, hi,
                                                        pm.ptr, pm.peer_array,
                                                        len(pm.peer_ptrs) if xmode == "stores" else 0, pipe.nout,
@@ -311,7 +318,7 @@ def run_b200(args):
         pass
     # algorithmic flops of the block kernel's share of F_alg: the two GEMM terms, for this rank's rows
     nl = np.asarray(wl.amodes.nmax_l, dtype=np.float64)
-    ells_mine = np.unique(wl.cmodes.lnn[0, lo:hi])
+    ells_mine = np.unique(wl.cmodes.lnn[0, lo:hi])      # l-blocks (row shard) or L-blocks (column shard): same model
     nn = nl[ells_mine][:, None] * nl[None, :]
     f_alg_block = float(np.sum(2 * nn * wl.nr ** 2 + 2 * nn * nn * wl.nr))
     roofline = {
@@ -375,9 +382,10 @@ def run_b200(args):
             "data": "synthetic",
             "config": dict(wl.describe(), l2="working set (win 0.4 GB + ring buffers 0.3 GB + M %.1f GB) exceeds the "
                                              "126 MB L2, no explicit flush" % (8e-9 * n * n),
-                           parallelism=f"row-sharded x{world}" + (" (stage 1 shell-sharded + NCCL all-gather of W_lm(r); "
-                                                                   "rows of M pushed into every GPU's full "
-                                                                   "matrix by pitched P2P copies over NVLink)"
+                           parallelism=f"sharded x{world}" + (" (stage 1 shell-sharded + NCCL all-gather of W_lm(r); "
+                                                                   "M sharded by columns (L,N,N') = contiguous "
+                                                                   "slabs, pushed into every GPU's full matrix by "
+                                                                   "P2P copies over NVLink)"
                                                                    if world > 1 else "")),
             "roofline": roofline, "per_rank": per_rank, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,

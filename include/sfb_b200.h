@@ -137,6 +137,9 @@ int32_t sfb_power_win_mix_dev_peers(sfb_cmix_plan* plan, const double* d_alm1, c
  * peer's full matrix (one pitched P2P copy per peer, concurrent, ordered after and joined back into `stream`) */
 int32_t sfb_push_rows_to_peers(const double* d_M_full, double* const* peer_M_full, int32_t npeers, int64_t row_lo,
                                int64_t row_hi, int64_t ncols, int64_t ldM, void* stream);
+/* columns [col_lo,col_hi) (a contiguous slab) -> the same columns of each peer's full matrix */
+int32_t sfb_push_cols_to_peers(const double* d_M_full, double* const* peer_M_full, int32_t npeers, int64_t col_lo,
+                               int64_t col_hi, int64_t ldM, void* stream);
 /* device buffers shareable between the per-GPU processes of one node (cudaIpc*); handle64 is 64 bytes */
 int32_t sfb_ipc_alloc(void** dptr, int64_t bytes, void* handle64);
 int32_t sfb_ipc_open(const void* handle64, void** dptr);
@@ -144,8 +147,14 @@ int32_t sfb_ipc_close(void* dptr);
 int32_t sfb_ipc_free(void* dptr);
 int32_t sfb_memcpy_dev(void* dst, const void* src, int64_t bytes, void* stream);
 
-/* cost model used to balance row shards: cost[i] for each of the nout rows (host array) */
+/* general block: rows [row_lo,row_hi) x columns [col_lo,col_hi), element (row_lo, col_lo) at d_M[0].  A column
+ * shard (all rows, a range of (L,N,N')) is a contiguous slab of the column-major matrix.              */
+int32_t sfb_power_win_mix_block_dev(sfb_cmix_plan* plan, const double* d_alm1, const double* d_alm2, int32_t div2Lp1,
+                                    int32_t interchange_NN, int64_t row_lo, int64_t row_hi, int64_t col_lo,
+                                    int64_t col_hi, double* d_M, int64_t ldM, void* stream);
+/* cost models used to balance shards: cost[i] for each of the nout rows / columns (host array) */
 int32_t sfb_cmix_row_costs(const sfb_cmix_plan* plan, double* cost, int64_t n);
+int32_t sfb_cmix_col_costs(const sfb_cmix_plan* plan, double* cost, int64_t n);
 
 #ifdef __cplusplus
 }

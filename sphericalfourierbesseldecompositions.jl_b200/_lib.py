@@ -40,6 +40,9 @@ SIGNATURES = {
     "sfb_cmix_plan_destroy": (_i32, [_vp]),
     "sfb_power_win_mix_dev": (_i32, [_vp, _f64p, _f64p, _i32, _i32, _i64, _i64, _f64p, _i64, _vp]),
     "sfb_cmix_row_costs": (_i32, [_vp, _f64p, _i64]),
+    "sfb_cmix_col_costs": (_i32, [_vp, _f64p, _i64]),
+    "sfb_power_win_mix_block_dev": (_i32, [_vp, _f64p, _f64p, _i32, _i32, _i64, _i64, _i64, _i64, _f64p, _i64, _vp]),
+    "sfb_push_cols_to_peers": (_i32, [_f64p, _vp, _i32, _i64, _i64, _i64, _vp]),
     "sfb_power_win_mix_dev_peers": (_i32, [_vp, _f64p, _f64p, _i32, _i32, _i64, _i64, _f64p, _vp, _i32, _i64, _vp]),
     "sfb_push_rows_to_peers": (_i32, [_f64p, _vp, _i32, _i64, _i64, _i64, _i64, _vp]),
     "sfb_ipc_alloc": (_i32, [C.POINTER(_vp), _i64, _vp]),

@@ -207,7 +207,7 @@ int32_t sfb_power_win_mix_from_wrlm(const double* w1r_lm, const double* w2r_lm, 
     SFB_TRY(dM.alloc((size_t)n * n));
     g_times[0] = 0;
     g_times[6] = 0;
-    SFB_TRY(cmix_run(pg.p, a1.p, same ? a1.p : a2.p, div2Lp1, interchange_NN, 0, n, dM.p, n, 0));
+    SFB_TRY(cmix_run(pg.p, a1.p, same ? a1.p : a2.p, div2Lp1, interchange_NN, 0, n, 0, n, dM.p, n, 0));
     record_cmix_times(pg.p);
     SFB_TRY(check_finite(dM.p, (size_t)n * n, "mix"));
     SFB_CUDA_OK(cudaMemcpy(M_out, dM.p, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost));
@@ -227,7 +227,7 @@ int32_t sfb_power_win_mix(const double* win1, const double* win2, int64_t nr, in
     SFB_TRY(windows_to_alm(win1, win2, nr, npix_in, ld_win, nside, 2 * lmax, a1, a2, &same));
     const int64_t n = pg.p->nout;
     SFB_TRY(dM.alloc((size_t)n * n));
-    SFB_TRY(cmix_run(pg.p, a1.p, same ? a1.p : a2.p, div2Lp1, interchange_NN, 0, n, dM.p, n, 0));
+    SFB_TRY(cmix_run(pg.p, a1.p, same ? a1.p : a2.p, div2Lp1, interchange_NN, 0, n, 0, n, dM.p, n, 0));
     record_cmix_times(pg.p);
     SFB_TRY(check_finite(dM.p, (size_t)n * n, "mix"));
     SFB_CUDA_OK(cudaMemcpy(M_out, dM.p, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost));
@@ -250,7 +250,7 @@ int32_t sfb_power_win_mix_binned(const double* win1, int64_t nr, int64_t npix_in
     SFB_TRY(windows_to_alm(win1, nullptr, nr, npix_in, ld_win, nside, 2 * lmax, a1, a2, &same));
     const int64_t n = pg.p->nout;
     SFB_TRY(dM.alloc((size_t)n * n));
-    SFB_TRY(cmix_run(pg.p, a1.p, a1.p, div2Lp1, interchange_NN, 0, n, dM.p, n, 0));
+    SFB_TRY(cmix_run(pg.p, a1.p, a1.p, div2Lp1, interchange_NN, 0, n, 0, n, dM.p, n, 0));
     record_cmix_times(pg.p);
     float t_bin = 0;
     SFB_TRY(binned_product_to_host(dM.p, n, wt_colptr, wt_rowval, wt_nzval, LNN1, v_colptr, v_rowval, v_nzval, LNN2,
@@ -367,7 +367,20 @@ int32_t sfb_power_win_mix_dev(sfb_cmix_plan* plan, const double* d_alm1, const d
     std::lock_guard<std::mutex> lk(g_mutex);
     auto* p = reinterpret_cast<CmixPlan*>(plan);
     const double t0 = g_times[6];
-    SFB_TRY(cmix_run(p, d_alm1, d_alm2, div2Lp1, interchange_NN, row_lo, row_hi, d_M, ldM, (cudaStream_t)stream));
+    SFB_TRY(cmix_run(p, d_alm1, d_alm2, div2Lp1, interchange_NN, row_lo, row_hi, 0, p->nout, d_M, ldM,
+                     (cudaStream_t)stream));
+    record_cmix_times(p);
+    g_times[6] = t0 + p->launches;
+    return 0;
+}
+int32_t sfb_power_win_mix_block_dev(sfb_cmix_plan* plan, const double* d_alm1, const double* d_alm2, int32_t div2Lp1,
+                                    int32_t interchange_NN, int64_t row_lo, int64_t row_hi, int64_t col_lo,
+                                    int64_t col_hi, double* d_M, int64_t ldM, void* stream) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    auto* p = reinterpret_cast<CmixPlan*>(plan);
+    const double t0 = g_times[6];
+    SFB_TRY(cmix_run(p, d_alm1, d_alm2, div2Lp1, interchange_NN, row_lo, row_hi, col_lo, col_hi, d_M, ldM,
+                     (cudaStream_t)stream));
     record_cmix_times(p);
     g_times[6] = t0 + p->launches;
     return 0;
@@ -386,7 +399,7 @@ int32_t sfb_power_win_mix_dev_peers(sfb_cmix_plan* plan, const double* d_alm1, c
         peers[i] = peer_M_full[i] + row_lo;
     }
     const double t0 = g_times[6];
-    SFB_TRY(cmix_run(p, d_alm1, d_alm2, div2Lp1, interchange_NN, row_lo, row_hi, d_M_full + row_lo, ldM,
+    SFB_TRY(cmix_run(p, d_alm1, d_alm2, div2Lp1, interchange_NN, row_lo, row_hi, 0, p->nout, d_M_full + row_lo, ldM,
                      (cudaStream_t)stream, peers, npeers));
     record_cmix_times(p);
     g_times[6] = t0 + p->launches;
@@ -428,6 +441,21 @@ int32_t sfb_push_rows_to_peers(const double* d_M_full, double* const* peer_M_ful
     return 0;
 }
 
+// Column slabs are contiguous in a column-major matrix: one plain peer copy per peer.
+int32_t sfb_push_cols_to_peers(const double* d_M_full, double* const* peer_M_full, int32_t npeers, int64_t col_lo,
+                               int64_t col_hi, int64_t ldM, void* stream) {
+    SFB_REQUIRE(d_M_full && npeers >= 0 && npeers <= 7 && col_lo >= 0 && col_lo <= col_hi, "bad arguments");
+    if (col_hi == col_lo || npeers == 0) return 0;
+    double* shifted[7];
+    for (int i = 0; i < npeers; ++i) {
+        SFB_REQUIRE(peer_M_full && peer_M_full[i], "null peer pointer");
+        shifted[i] = peer_M_full[i] + col_lo * ldM;
+    }
+    // the slab is one contiguous run of (col_hi-col_lo)*ldM doubles == a single "row" of a pitched copy
+    const int64_t run = (col_hi - col_lo) * ldM;
+    return sfb_push_rows_to_peers(d_M_full + col_lo * ldM, shifted, npeers, 0, run, 1, run, stream);
+}
+
 int32_t sfb_ipc_alloc(void** dptr, int64_t bytes, void* handle64) {
     std::lock_guard<std::mutex> lk(g_mutex);
     SFB_REQUIRE(dptr && handle64 && bytes > 0, "bad arguments");
@@ -458,6 +486,27 @@ int32_t sfb_ipc_free(void* dptr) {
 }
 int32_t sfb_memcpy_dev(void* dst, const void* src, int64_t bytes, void* stream) {
     SFB_CUDA_OK(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return 0;
+}
+
+// cost of each output COLUMN (L,N,N'): the block (l,L) costs the same whichever way it is assigned, so the
+// column cost is the transpose of the row model
+int32_t sfb_cmix_col_costs(const sfb_cmix_plan* plan, double* cost, int64_t n) {
+    const auto* p = reinterpret_cast<const CmixPlan*>(plan);
+    SFB_REQUIRE(p && cost && n == p->nout, "sfb_cmix_col_costs: bad arguments");
+    for (int L = 0; L <= p->lmax; ++L) {
+        const int cols = p->ell_ptr[L + 1] - p->ell_ptr[L];
+        if (!cols) continue;
+        const double b = p->a_of_ell[L];
+        double c = 0;
+        for (int l = 0; l <= p->lmax; ++l) {
+            if (p->ell_ptr[l + 1] == p->ell_ptr[l]) continue;
+            const double ap = 8.0 * ((p->a_of_ell[l] + 7) / 8);
+            c += 2.0 * ap * p->nrp * p->nrp * b + 2.0 * ap * ap * p->nrp * b * (b + 1) / 2 +
+                 2.0 * p->nrp * p->nrp * (std::min(l, L) + 1);
+        }
+        for (int s = p->ell_ptr[L]; s < p->ell_ptr[L + 1]; ++s) cost[p->h_row_out[s]] = c / cols;
+    }
     return 0;
 }
 

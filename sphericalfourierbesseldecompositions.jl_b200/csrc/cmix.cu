@@ -77,10 +77,11 @@ __global__ void wl_build_kernel(const double* __restrict__ alm1, const double* _
 // every W_{L1} element loaded from L2 feeds four accumulators.
 __global__ void __launch_bounds__(256) what_build_kernel(const double* __restrict__ W, const double* __restrict__ w2,
                                                          double* __restrict__ What, const int* __restrict__ ells,
-                                                         int ell0, int lmax, int nrp) {
+                                                         int ell0, int lmax, int nrp, int Llo, int Lhi) {
     extern __shared__ double wsm[];  // [4][lmax+1]
     const int ell = ells[blockIdx.y];
     const int gi = blockIdx.x, p = gi & 1, base = (gi >> 1) * 8 + p;
+    if (base > Lhi || base + 6 < Llo) return;  // no L of this group is needed by the column shard
     const int par = (ell + p) & 1;
     const int KW = lmax + 1;
     for (int x = threadIdx.x; x < 4 * KW; x += blockDim.x) wsm[x] = 0.0;
@@ -138,6 +139,7 @@ struct CmixArgs {
     int npeers;
     long long ldM;
     int ell0, lmax, nmax, nrp, S, NC;
+    int col_lo, col_hi;     // output columns [col_lo, col_hi) are written, relative to col_lo
     int div2Lp1, interchange;
 };
 
@@ -184,7 +186,8 @@ __global__ void __launch_bounds__(kCmixThreads, 1) cmix_block_kernel(CmixArgs p)
     }
     for (int x = tid; x < nN * p.nmax; x += kCmixThreads) {
         const int Nloc = x / p.nmax, N2 = x - Nloc * p.nmax;
-        coltab[x] = (N2 < b) ? p.pairidx[((size_t)L * p.nmax + N0 + Nloc) * p.nmax + N2] : -1;
+        int c = (N2 < b) ? p.pairidx[((size_t)L * p.nmax + N0 + Nloc) * p.nmax + N2] : -1;
+        coltab[x] = (c >= p.col_lo && c < p.col_hi) ? c - p.col_lo : -1;
     }
     __syncthreads();
 
@@ -556,12 +559,17 @@ int cmix_plan_create(CmixPlan** out, const int64_t* lnn, int64_t lnnsize, int64_
 void cmix_plan_destroy(CmixPlan* p) { delete p; }
 
 int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp1, int interchange, int64_t row_lo,
-             int64_t row_hi, double* d_M, int64_t ldM, cudaStream_t stream, double* const* peers, int npeers) {
+             int64_t row_hi, int64_t col_lo, int64_t col_hi, double* d_M, int64_t ldM, cudaStream_t stream,
+             double* const* peers, int npeers) {
     SFB_REQUIRE(p && d_alm1 && d_alm2 && d_M, "cmix_run: null pointer");
     SFB_REQUIRE(npeers >= 0 && npeers <= 7, "cmix_run: at most 7 peers");
     SFB_REQUIRE(0 <= row_lo && row_lo <= row_hi && row_hi <= p->nout, "cmix_run: bad row range");
+    SFB_REQUIRE(0 <= col_lo && col_lo <= col_hi && col_hi <= p->nout, "cmix_run: bad column range");
     SFB_REQUIRE(ldM >= row_hi - row_lo, "cmix_run: ldM smaller than the row shard");
-    if (row_hi == row_lo) return 0;
+    p->t_wl = p->t_what = p->t_block = 0;
+    p->flops_executed = 0;
+    p->launches = 0;
+    if (row_hi == row_lo || col_hi == col_lo) return 0;
     const bool sym = (d_alm1 == d_alm2);
     const int lmax = p->lmax, nrp = p->nrp;
     cudaEvent_t ev[4];
@@ -579,6 +587,19 @@ int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp
         }
     SFB_CUDA_OK(cudaMemcpyAsync(p->d_row_out.p, row_out.data(), row_out.size() * sizeof(int), cudaMemcpyHostToDevice,
                                 stream));
+    // L-blocks with at least one column in [col_lo, col_hi) (rows and columns share the same index set)
+    std::vector<char> L_used(lmax + 1, 0);
+    int Llo = lmax + 1, Lhi = -1;
+    for (int L = 0; L <= lmax; ++L)
+        for (int s = p->ell_ptr[L]; s < p->ell_ptr[L + 1]; ++s) {
+            const int o = p->h_row_out[s];
+            if (o >= col_lo && o < col_hi) {
+                L_used[L] = 1;
+                Llo = std::min(Llo, L);
+                Lhi = std::max(Lhi, L);
+            }
+        }
+    if (Lhi < 0) return 0;
 
     // ---- W_{L1} ----
     SFB_CUDA_OK(cudaEventRecord(ev[0], stream));
@@ -614,6 +635,8 @@ int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp
     args.S = p->S;
     args.div2Lp1 = div2Lp1;
     args.interchange = interchange;
+    args.col_lo = (int)col_lo;
+    args.col_hi = (int)col_hi;
 
     float t_what = 0.f, t_block = 0.f;
     double flops = 0.0;
@@ -637,7 +660,7 @@ int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp
         SFB_CUDA_OK(cudaMemcpyAsync(p->d_what_ells.p, wells.data(), wells.size() * sizeof(int), cudaMemcpyHostToDevice,
                                     stream));
         what_build_kernel<<<dim3(ngroups, (unsigned)wells.size()), 256, 4 * (lmax + 1) * sizeof(double), stream>>>(
-            p->d_W.p, p->d_w2.p, p->d_What.p, p->d_what_ells.p, ell0, lmax, nrp);
+            p->d_W.p, p->d_w2.p, p->d_What.p, p->d_what_ells.p, ell0, lmax, nrp, Llo, Lhi);
         SFB_CUDA_OK(cudaGetLastError());
         p->launches++;
         SFB_CUDA_OK(cudaEventRecord(e1, stream));
@@ -661,7 +684,7 @@ int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp
             SFB_REQUIRE(NC >= 1, "cmix: nr * nmax too large for the shared-memory tiling of this build");
             std::vector<int> chL, chN0, chN1;
             for (int L = 0; L <= lmax; ++L)
-                for (int n0 = 0; n0 < p->a_of_ell[L]; n0 += NC) {
+                for (int n0 = 0; L_used[L] && n0 < p->a_of_ell[L]; n0 += NC) {
                     chL.push_back(L);
                     chN0.push_back(n0);
                     chN1.push_back(std::min(n0 + NC, p->a_of_ell[L]));
@@ -687,6 +710,7 @@ int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp
             p->launches++;
             for (int l : ells)
                 for (int L = 0; L <= lmax; ++L) {
+                    if (!L_used[L]) continue;
                     const double b = p->a_of_ell[L], ap = AT * 8.0;
                     flops += (sym ? 1.0 : 2.0) * (2.0 * ap * nrp * nrp * b + 2.0 * ap * ap * nrp * b * (b + 1) / 2);
                 }

@@ -54,13 +54,13 @@ int cmix_plan_create(CmixPlan** out, const int64_t* lnn, int64_t lnnsize, int64_
 void cmix_plan_destroy(CmixPlan* p);
 
 // alm layout (device): planar [lm (m-major, lmax2 = 2*lmax)][comp (re,im)][nrp], padded shells zero.
-// Writes rows [row_lo,row_hi) (0-based, of the nout x nout matrix) into d_M (column-major, leading dim ldM,
-// row row_lo at offset 0).
+// Writes the block rows [row_lo,row_hi) x columns [col_lo,col_hi) (0-based, of the nout x nout matrix) into d_M
+// (column-major, leading dim ldM, element (row_lo, col_lo) at offset 0).
 // `peers` (optional): up to 7 more device pointers (peer-mapped, same offset/ldM semantics as d_M); every element
 // is also stored there, which fuses the all-gather of row shards into the kernel epilogue.
 int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp1, int interchange,
-             int64_t row_lo, int64_t row_hi, double* d_M, int64_t ldM, cudaStream_t stream,
-             double* const* peers = nullptr, int npeers = 0);
+             int64_t row_lo, int64_t row_hi, int64_t col_lo, int64_t col_hi, double* d_M, int64_t ldM,
+             cudaStream_t stream, double* const* peers = nullptr, int npeers = 0);
 
 // Host complex (nr x lmsize, column-major, interleaved) -> device planar alm; layout 0 = m-major, 1 = m-fast.
 int alm_from_host(const double* h_wrlm, int64_t nr, int lmax2, int layout, DevBuf<double>& d_alm, int nrp,

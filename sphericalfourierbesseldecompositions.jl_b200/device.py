@@ -74,6 +74,9 @@ class DevicePipeline:
         costs = np.zeros(self.nout)
         _lib.check(self.lib.sfb_cmix_row_costs(self._cmix, _lib.ptr(costs), self.nout))
         self.row_costs = costs
+        ccosts = np.zeros(self.nout)
+        _lib.check(self.lib.sfb_cmix_col_costs(self._cmix, _lib.ptr(ccosts), self.nout))
+        self.col_costs = ccosts
         self.ell_of_row = self.lnn[0, lnn_min - 1:]
 
     def close(self):
@@ -161,30 +164,54 @@ class DevicePipeline:
                                                   self._stream()))
         return out
 
+    def power_win_mix_cols(self, lo, hi, out=None, alm2=None, div2Lp1=False, interchange_NN=False):
+        """Columns [lo, hi) of M (all rows): a contiguous slab of the column-major matrix, returned as a torch
+        tensor of shape (hi-lo, nout)."""
+        torch = _torch()
+        if out is None:
+            out = torch.empty((hi - lo, self.nout), dtype=torch.float64, device=self.device)
+        a2 = self.alm if alm2 is None else alm2
+        _lib.check(self.lib.sfb_power_win_mix_block_dev(self._cmix, self.alm.data_ptr(), a2.data_ptr(), int(div2Lp1),
+                                                        int(interchange_NN), 0, self.nout, lo, hi, out.data_ptr(),
+                                                        self.nout, self._stream()))
+        return out
+
     def power_win_mix(self, d_win, **kw):
         self.calc_wr_lm(d_win)
         return self.power_win_mix_rows(0, self.nout, **kw)
 
     # ---- multi-GPU -----------------------------------------------------------------------------
-    def power_win_mix_fused(self, d_win, peer_matrix, div2Lp1=False, interchange_NN=False, sync=True, mode="dma"):
-        """Row-sharded coupling matrix assembled in `peer_matrix` on every GPU without NCCL or a placement pass.
-        mode="dma": the block kernel writes this rank's rows into its own full matrix and the copy engines push
-        them to every peer (pitched P2P copies, one stream per peer); mode="stores": the block kernel itself
-        stores every element into all copies over NVLink.  Returns (tensor view of the local full matrix,
-        ranges); the tensor holds Mᵀ in C order (= M in Julia's column-major order)."""
+    def power_win_mix_fused(self, d_win, peer_matrix, div2Lp1=False, interchange_NN=False, sync=True, mode="cols"):
+        """Sharded coupling matrix assembled in `peer_matrix` on every GPU without NCCL or a placement pass.
+        mode="cols" (default): shard the COLUMN index (L,N,N') — a column range is a contiguous slab of the
+          column-major matrix, so each rank pushes its slab to every peer with one plain P2P copy per peer;
+        mode="dma": shard rows (l,n,n'), pushed with pitched P2P copies (strided, slower);
+        mode="stores": shard rows, the block kernel itself stores every element into all copies over NVLink.
+        Returns (tensor view of the local full matrix, ranges); the tensor holds Mᵀ in C order (= M in Julia's
+        column-major order)."""
         torch = _torch()
         import torch.distributed as dist
         pm = peer_matrix
         self.calc_wr_lm_sharded(d_win, pm.group)
-        ranges = shard_rows(self.row_costs, self.ell_of_row, pm.world)
-        lo, hi = ranges[pm.rank]
-        nstore = len(pm.peer_ptrs) if mode == "stores" else 0
-        _lib.check(self.lib.sfb_power_win_mix_dev_peers(self._cmix, self.alm.data_ptr(), self.alm.data_ptr(),
-                                                        int(div2Lp1), int(interchange_NN), lo, hi, pm.ptr,
-                                                        pm.peer_array, nstore, self.nout, self._stream()))
-        if mode != "stores":
-            _lib.check(self.lib.sfb_push_rows_to_peers(pm.ptr, pm.peer_array, len(pm.peer_ptrs), lo, hi, self.nout,
-                                                       self.nout, self._stream()))
+        if mode == "cols":
+            ranges = shard_rows(self.col_costs, self.ell_of_row, pm.world)
+            lo, hi = ranges[pm.rank]
+            _lib.check(self.lib.sfb_power_win_mix_block_dev(self._cmix, self.alm.data_ptr(), self.alm.data_ptr(),
+                                                            int(div2Lp1), int(interchange_NN), 0, self.nout, lo, hi,
+                                                            pm.ptr.value + 8 * lo * self.nout, self.nout,
+                                                            self._stream()))
+            _lib.check(self.lib.sfb_push_cols_to_peers(pm.ptr, pm.peer_array, len(pm.peer_ptrs), lo, hi, self.nout,
+                                                       self._stream()))
+        else:
+            ranges = shard_rows(self.row_costs, self.ell_of_row, pm.world)
+            lo, hi = ranges[pm.rank]
+            nstore = len(pm.peer_ptrs) if mode == "stores" else 0
+            _lib.check(self.lib.sfb_power_win_mix_dev_peers(self._cmix, self.alm.data_ptr(), self.alm.data_ptr(),
+                                                            int(div2Lp1), int(interchange_NN), lo, hi, pm.ptr,
+                                                            pm.peer_array, nstore, self.nout, self._stream()))
+            if mode != "stores":
+                _lib.check(self.lib.sfb_push_rows_to_peers(pm.ptr, pm.peer_array, len(pm.peer_ptrs), lo, hi,
+                                                           self.nout, self.nout, self._stream()))
         if sync:
             torch.cuda.synchronize()
             dist.barrier(pm.group)   # every rank's stores have landed in every copy

@@ -39,7 +39,7 @@ def _worker(rank, world, port, ret):
     ok = rel(pipe.alm, alm_single) < 1e-13 and rel(full, single) < 1e-13
     from sfb_b200.device import PeerMatrix
     pm = PeerMatrix(pipe.nout)
-    for mode in ("dma", "stores"):
+    for mode in ("cols", "dma", "stores"):
         pm.tensor.zero_()
         torch.cuda.synchronize()
         dist.barrier()
