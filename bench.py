@@ -222,15 +222,20 @@ def run_b200(args):
     pipe = DevicePipeline(wl.wmodes, wl.cmodes, wl.G)
     # window resident in HBM in Julia memory order: (npix, nr) C-contiguous == (nr, npix) column-major
     d_win = torch.from_numpy(np.ascontiguousarray(win.T)).cuda()
-    xmode = os.environ.get("SFB_BENCH_EXCHANGE", "cols")   # cols | dma | stores | nccl
-    ranges = shard_rows(pipe.col_costs if xmode == "cols" else pipe.row_costs, pipe.ell_of_row, world)
+    # exchange variants (default first): cols = column slabs + in-place NCCL send/recv; cols_dma = column slabs +
+    # IPC copy-engine pushes; dma / stores = row shards via pitched P2P copies / in-kernel P2P stores;
+    # nccl = row slabs + padded all_gather + placement
+    xmode = os.environ.get("SFB_BENCH_EXCHANGE", "cols")
+    ranges = shard_rows(pipe.col_costs if xmode.startswith("cols") else pipe.row_costs, pipe.ell_of_row, world)
     lo, hi = ranges[rank]
     # N = 1: the matrix stays in a device buffer; N > 1: every rank holds the full matrix, rows stored into all
     # copies by the block kernel itself (all-gather fused into the epilogue over NVLink peer memory)
     slab = torch.empty((pipe.nout, hi - lo), dtype=torch.float64, device="cuda") if world == 1 else None
-    pm = PeerMatrix(pipe.nout) if world > 1 else None
+    pm = PeerMatrix(pipe.nout) if (world > 1 and xmode in ("cols_dma", "dma", "stores")) else None
+    full_t = torch.empty((pipe.nout, pipe.nout), dtype=torch.float64, device="cuda") if (world > 1 and xmode == "cols") else None
 
-    fused = xmode in ("cols", "dma", "stores")
+    fused = xmode in ("dma", "stores")
+    from sfb_b200.device import allgather_col_slabs
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     if world > 1 and not fused:
         from sfb_b200.device import gather_row_slabs
@@ -241,6 +246,11 @@ def run_b200(args):
         pipe.calc_wr_lm_sharded(d_win)
         evs[1].record()
         if world > 1 and xmode == "cols":
+            if hi > lo:
+                pipe.power_win_mix_cols(lo, hi, out=full_t[lo:hi])
+            allgather_col_slabs(full_t, ranges)
+            out = full_t
+        elif world > 1 and xmode == "cols_dma":
             _lib.check(lib.sfb_power_win_mix_block_dev(pipe._cmix, pipe.alm.data_ptr(), pipe.alm.data_ptr(), 0, 0, 0,
                                                        pipe.nout, lo, hi, pm.ptr.value + 8 * lo * pipe.nout, pipe.nout,
                                                        pipe._stream()))
@@ -384,15 +394,17 @@ def run_b200(args):
                                              "126 MB L2, no explicit flush" % (8e-9 * n * n),
                            parallelism=f"sharded x{world}" + (" (stage 1 shell-sharded + NCCL all-gather of W_lm(r); "
                                                                    "M sharded by columns (L,N,N') = contiguous "
-                                                                   "slabs, pushed into every GPU's full matrix by "
-                                                                   "P2P copies over NVLink)"
+                                                                   "slabs written in place, then an uneven in-place "
+                                                                   "NCCL all-gather (grouped send/recv) over NVLink; "
+                                                                   f"exchange={xmode})"
                                                                    if world > 1 else "")),
             "roofline": roofline, "per_rank": per_rank, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
         }
         print(json.dumps(line))
     if world > 1:
-        pm.close()
+        if pm is not None:
+            pm.close()
         dist.destroy_process_group()
 
 

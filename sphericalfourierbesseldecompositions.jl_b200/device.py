@@ -217,6 +217,26 @@ class DevicePipeline:
             dist.barrier(pm.group)   # every rank's stores have landed in every copy
         return pm.tensor, ranges
 
+    def power_win_mix_allgather(self, d_win, full=None, group=None, div2Lp1=False, interchange_NN=False):
+        """The multi-GPU path: stage 1 shell-sharded, stage 2+3 sharded over the COLUMN index (L,N,N') with a cost
+        prefix sum, each rank writing its contiguous column slab straight into its copy of the full matrix, then
+        an in-place uneven NCCL all-gather (grouped send/recv over NVLink; no padding, no placement pass).
+        Returns (full, ranges): `full` has shape (nout, nout) and holds Mᵀ in C order, i.e. Julia's column-major M."""
+        torch = _torch()
+        import torch.distributed as dist
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if full is None:
+            full = torch.empty((self.nout, self.nout), dtype=torch.float64, device=self.device)
+        self.calc_wr_lm_sharded(d_win, group)
+        ranges = shard_rows(self.col_costs, self.ell_of_row, world)
+        lo, hi = ranges[rank]
+        if hi > lo:
+            self.power_win_mix_cols(lo, hi, out=full[lo:hi], div2Lp1=div2Lp1, interchange_NN=interchange_NN)
+        if world > 1:
+            allgather_col_slabs(full, ranges, group)
+        return full, ranges
+
     def power_win_mix_sharded(self, d_win, group=None, gather=True, **kw):
         """Row-sharded coupling matrix over the ranks of `group`; with gather=True every rank returns the
         full matrix as a (nout, nout) tensor holding Mᵀ in C order (= M in Julia's column-major order)."""
@@ -231,6 +251,25 @@ class DevicePipeline:
         if world == 1 or not gather:
             return slab, ranges
         return gather_row_slabs(slab, ranges, self.nout, group), ranges
+
+
+def allgather_col_slabs(full, ranges, group=None):
+    """In-place uneven all-gather of contiguous column slabs: rank g owns full[lo_g:hi_g] (rows of the C-ordered
+    tensor = columns of Julia's matrix); grouped NCCL send/recv fills every other slab."""
+    import torch.distributed as dist
+    rank = dist.get_rank(group)
+    lo, hi = ranges[rank]
+    ops = []
+    for g, (l, h) in enumerate(ranges):
+        if g == rank or h <= l:
+            continue
+        if hi > lo:
+            ops.append(dist.P2POp(dist.isend, full[lo:hi], g, group))
+        ops.append(dist.P2POp(dist.irecv, full[l:h], g, group))
+    if not ops:
+        return
+    for w in dist.batch_isend_irecv(ops):
+        w.wait()
 
 
 class _DevArray:

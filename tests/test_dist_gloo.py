@@ -26,6 +26,14 @@ def _worker(rank, world, port, ret):
     slab = torch.from_numpy(np.ascontiguousarray(M[lo:hi, :].T))   # (nout, rows) like DevicePipeline
     full = gather_row_slabs(slab, ranges, n)
     ok = np.array_equal(full.numpy().T, M)
+    # column slabs: in-place uneven all-gather
+    from sfb_b200.device import allgather_col_slabs
+    cr = shard_rows(cost, ell, world)
+    fullc = torch.zeros((n, n), dtype=torch.float64)
+    clo, chi = cr[rank]
+    fullc[clo:chi] = torch.from_numpy(np.ascontiguousarray(M.T[clo:chi]))
+    allgather_col_slabs(fullc, cr)
+    ok = ok and np.array_equal(fullc.numpy().T, M)
     out = torch.tensor([1.0 if ok else 0.0])
     dist.all_reduce(out, op=dist.ReduceOp.MIN)
     if rank == 0:

@@ -37,6 +37,8 @@ def _worker(rank, world, port, ret):
     full, ranges = pipe.power_win_mix_sharded(d_win)
     rel = lambda x, y: float((x - y).norm() / y.norm())
     ok = rel(pipe.alm, alm_single) < 1e-13 and rel(full, single) < 1e-13
+    ag, _ = pipe.power_win_mix_allgather(d_win)
+    ok = ok and rel(ag, single) < 1e-13
     from sfb_b200.device import PeerMatrix
     pm = PeerMatrix(pipe.nout)
     for mode in ("cols", "dma", "stores"):
