@@ -101,6 +101,75 @@ static void record_cmix_times(const CmixPlan* p) {
     g_times[6] += p->launches;
 }
 
+// Device workspace reused across host-pointer calls (cudaMalloc / cudaFree of multi-GB buffers is slow).
+struct Workspace {
+    DevBuf<double> win, alm1, alm2, slab[2];
+    DevBuf<int> flag;
+    cudaStream_t copy = nullptr;
+    cudaEvent_t computed[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
+    int dev = -1;
+    int init() {
+        int d = 0;
+        SFB_CUDA_OK(cudaGetDevice(&d));
+        if (copy && d == dev) return 0;
+        SFB_CUDA_OK(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            SFB_CUDA_OK(cudaEventCreateWithFlags(&computed[i], cudaEventDisableTiming));
+            SFB_CUDA_OK(cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming));
+        }
+        dev = d;
+        return 0;
+    }
+};
+static Workspace g_ws;
+
+// Stage 2+3 for all columns, pipelined with the device->host copy: the matrix is produced in column slabs
+// (contiguous in column-major order); while slab k is copied to the caller's buffer, slab k+1 is computed.
+static int cmix_to_host_pipelined(CmixPlan* p, const double* a1, const double* a2, int div2Lp1, int interchange,
+                                  double* M_out) {
+    SFB_TRY(g_ws.init());
+    const int64_t n = p->nout;
+    const auto chunks = cmix_col_chunks(p, 8);
+    int64_t maxc = 0;
+    for (auto& c : chunks) maxc = std::max(maxc, c.second - c.first);
+    for (int i = 0; i < 2 && i < (int)chunks.size(); ++i) SFB_TRY(g_ws.slab[i].alloc((size_t)maxc * n));
+    SFB_TRY(g_ws.flag.alloc(1));
+    SFB_CUDA_OK(cudaMemsetAsync(g_ws.flag.p, 0, sizeof(int), 0));
+    float t_wl = 0, t_what = 0, t_block = 0;
+    double flops = 0;
+    int launches = 0;
+    for (size_t k = 0; k < chunks.size(); ++k) {
+        const int b = (int)(k & 1);
+        const int64_t c0 = chunks[k].first, c1 = chunks[k].second;
+        if (k >= 2) SFB_CUDA_OK(cudaEventSynchronize(g_ws.copied[b]));  // slab free again
+        SFB_TRY(cmix_run(p, a1, a2, div2Lp1, interchange, 0, n, c0, c1, g_ws.slab[b].p, n, 0, nullptr, 0, k > 0));
+        t_wl += p->t_wl;
+        t_what += p->t_what;
+        t_block += p->t_block;
+        flops += p->flops_executed;
+        launches += p->launches;
+        finite_check_kernel<<<512, 256, 0, 0>>>(g_ws.slab[b].p, (size_t)(c1 - c0) * n, g_ws.flag.p);
+        SFB_CUDA_OK(cudaEventRecord(g_ws.computed[b], 0));
+        SFB_CUDA_OK(cudaStreamWaitEvent(g_ws.copy, g_ws.computed[b], 0));
+        SFB_CUDA_OK(cudaMemcpyAsync(M_out + c0 * n, g_ws.slab[b].p, (size_t)(c1 - c0) * n * sizeof(double),
+                                    cudaMemcpyDeviceToHost, g_ws.copy));
+        SFB_CUDA_OK(cudaEventRecord(g_ws.copied[b], g_ws.copy));
+    }
+    SFB_CUDA_OK(cudaStreamSynchronize(g_ws.copy));
+    p->t_wl = t_wl;
+    p->t_what = t_what;
+    p->t_block = t_block;
+    p->flops_executed = flops;
+    p->launches = launches + (int)chunks.size();
+    int h = 0;
+    SFB_CUDA_OK(cudaMemcpy(&h, g_ws.flag.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (h) {  // @assert all(isfinite.(mix))  src/windows.jl:803
+        set_error("AssertionError: all(isfinite.(mix))");
+        return 4;
+    }
+    return 0;
+}
+
 struct PlanGuard {
     CmixPlan* p = nullptr;
     ~PlanGuard() {
@@ -116,7 +185,7 @@ static int windows_to_alm(const double* win1, const double* win2, int64_t nr, in
     ShtPlan* sp = nullptr;
     SFB_TRY(get_sht_plan(&sp, nside_in, nside, LMAX, nr));
     const size_t nalm = sp->lmsize * 2 * sp->nrp;
-    DevBuf<double> d_win;
+    DevBuf<double>& d_win = g_ws.win;
     SFB_TRY(upload_win(win1, nr, npix_in, ld_win, d_win));
     SFB_TRY(alm1.alloc(nalm));
     SFB_TRY(sht_map2alm(sp, d_win.p, nr, 3, alm1.p, 0));
@@ -222,15 +291,11 @@ int32_t sfb_power_win_mix(const double* win1, const double* win2, int64_t nr, in
     SFB_REQUIRE(win1 && M_out, "null pointer");
     PlanGuard pg;
     SFB_TRY(cmix_plan_create(&pg.p, lnn, lnnsize, lnn_min, G, nr, nmax, lmax));
-    DevBuf<double> a1, a2, dM;
+    DevBuf<double>&a1 = g_ws.alm1, &a2 = g_ws.alm2;
     bool same = true;
     SFB_TRY(windows_to_alm(win1, win2, nr, npix_in, ld_win, nside, 2 * lmax, a1, a2, &same));
-    const int64_t n = pg.p->nout;
-    SFB_TRY(dM.alloc((size_t)n * n));
-    SFB_TRY(cmix_run(pg.p, a1.p, same ? a1.p : a2.p, div2Lp1, interchange_NN, 0, n, 0, n, dM.p, n, 0));
+    SFB_TRY(cmix_to_host_pipelined(pg.p, a1.p, same ? a1.p : a2.p, div2Lp1, interchange_NN, M_out));
     record_cmix_times(pg.p);
-    SFB_TRY(check_finite(dM.p, (size_t)n * n, "mix"));
-    SFB_CUDA_OK(cudaMemcpy(M_out, dM.p, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost));
     return 0;
 }
 

@@ -560,7 +560,7 @@ void cmix_plan_destroy(CmixPlan* p) { delete p; }
 
 int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp1, int interchange, int64_t row_lo,
              int64_t row_hi, int64_t col_lo, int64_t col_hi, double* d_M, int64_t ldM, cudaStream_t stream,
-             double* const* peers, int npeers) {
+             double* const* peers, int npeers, bool reuse_wl) {
     SFB_REQUIRE(p && d_alm1 && d_alm2 && d_M, "cmix_run: null pointer");
     SFB_REQUIRE(npeers >= 0 && npeers <= 7, "cmix_run: at most 7 peers");
     SFB_REQUIRE(0 <= row_lo && row_lo <= row_hi && row_hi <= p->nout, "cmix_run: bad row range");
@@ -603,10 +603,12 @@ int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp
 
     // ---- W_{L1} ----
     SFB_CUDA_OK(cudaEventRecord(ev[0], stream));
-    wl_build_kernel<<<p->LMAX + 1, 256, 0, stream>>>(d_alm1, d_alm2, p->d_W.p, p->LMAX, nrp);
-    SFB_CUDA_OK(cudaGetLastError());
+    if (!reuse_wl) {
+        wl_build_kernel<<<p->LMAX + 1, 256, 0, stream>>>(d_alm1, d_alm2, p->d_W.p, p->LMAX, nrp);
+        SFB_CUDA_OK(cudaGetLastError());
+        p->launches = 1;
+    }
     SFB_CUDA_OK(cudaEventRecord(ev[1], stream));
-    p->launches = 1;
 
     // ---- ℓ chunks: Ŵ then blocks ----
     const size_t per_ell = (size_t)(lmax + 1) * nrp * nrp * sizeof(double);
@@ -733,6 +735,48 @@ int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp
     p->flops_executed = flops;
     for (auto& e : ev) cudaEventDestroy(e);
     return 0;
+}
+
+// Split the columns into at most `k` contiguous ranges of roughly equal cost, cut on L-block boundaries.
+// Falls back to a single range when the caller's table does not keep each L-block contiguous.
+std::vector<std::pair<int64_t, int64_t>> cmix_col_chunks(const CmixPlan* p, int k) {
+    std::vector<std::pair<int64_t, int64_t>> out;
+    const int lmax = p->lmax;
+    std::vector<int64_t> first(lmax + 2, -1);
+    std::vector<double> cost(lmax + 1, 0.0);
+    bool contiguous = true;
+    int64_t expect = 0;
+    for (int L = 0; L <= lmax; ++L) {
+        const int c0 = p->ell_ptr[L], c1 = p->ell_ptr[L + 1];
+        first[L] = expect;
+        for (int s = c0; s < c1; ++s)
+            if (p->h_row_out[s] != expect++) contiguous = false;
+        const double b = p->a_of_ell[L];
+        for (int l = 0; l <= lmax && c1 > c0; ++l) {
+            const double ap = 8.0 * ((p->a_of_ell[l] + 7) / 8);
+            cost[L] += 2.0 * ap * p->nrp * p->nrp * b + 2.0 * ap * ap * p->nrp * b * (b + 1) / 2;
+        }
+    }
+    first[lmax + 1] = expect;
+    if (!contiguous || k <= 1) {
+        out.emplace_back(0, p->nout);
+        return out;
+    }
+    double total = 0;
+    for (double c : cost) total += c;
+    double acc = 0;
+    int64_t start = 0;
+    int made = 0;
+    for (int L = 0; L <= lmax; ++L) {
+        acc += cost[L];
+        if (acc >= total * (made + 1) / k && first[L + 1] > start && made < k - 1) {
+            out.emplace_back(start, first[L + 1]);
+            start = first[L + 1];
+            ++made;
+        }
+    }
+    if (start < p->nout) out.emplace_back(start, p->nout);
+    return out;
 }
 
 // =============================================================================================

@@ -8,6 +8,7 @@
 //   _power_win_mix      src/windows.jl:825-862   -> csr/csc products in binned.cu
 #pragma once
 #include "common.cuh"
+#include <utility>
 #include <vector>
 
 namespace sfb {
@@ -60,7 +61,9 @@ void cmix_plan_destroy(CmixPlan* p);
 // is also stored there, which fuses the all-gather of row shards into the kernel epilogue.
 int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp1, int interchange,
              int64_t row_lo, int64_t row_hi, int64_t col_lo, int64_t col_hi, double* d_M, int64_t ldM,
-             cudaStream_t stream, double* const* peers = nullptr, int npeers = 0);
+             cudaStream_t stream, double* const* peers = nullptr, int npeers = 0, bool reuse_wl = false);
+// column ranges of roughly equal cost (L-block aligned) for pipelining compute with the D2H of finished slabs
+std::vector<std::pair<int64_t, int64_t>> cmix_col_chunks(const CmixPlan* p, int k);
 
 // Host complex (nr x lmsize, column-major, interleaved) -> device planar alm; layout 0 = m-major, 1 = m-fast.
 int alm_from_host(const double* h_wrlm, int64_t nr, int lmax2, int layout, DevBuf<double>& d_alm, int nrp,

@@ -112,19 +112,35 @@ def check_nsamp(amodes, nr):
 
 def precompute_gnlr(amodes, wmodes):
     """gnlr[:, n-1, l] = g_nl(r); NaN where n > nmax_l[l]   (src/windows.jl:548-559).  Fortran order."""
+    from scipy import special
     r = wmodes.r
+    g = amodes.basisfunctions
     gnlr = np.full((r.size, amodes.nmax, amodes.lmax + 1), np.nan, order="F")
     for l in range(amodes.lmax + 1):
-        for n in range(1, int(amodes.nmax_l[l]) + 1):
-            gnlr[:, n - 1, l] = amodes.basisfunctions(n, l, r)
+        nl = int(amodes.nmax_l[l])
+        q = r[:, None] * g.knl[None, :nl, l]                      # all n of this l at once
+        val = g.cnl[None, :nl, l] * special.spherical_jn(l, q)
+        d = g.dnl[:nl, l]
+        if np.any(d != 0):
+            val = val + d[None, :] * special.spherical_yn(l, np.where(q == 0, 1.0, q)) * (d != 0)[None, :]
+        gnlr[:, :nl, l] = val
     check_nsamp(amodes, wmodes.nr)
     return gnlr
 
 
 def rsdrgnlr(amodes, wmodes):
-    """r .* √Δr .* precompute_gnlr(amodes, wmodes)   (src/windows.jl:799,1009)"""
+    """r .* √Δr .* precompute_gnlr(amodes, wmodes)   (src/windows.jl:799,1009).
+    The table only depends on (amodes, rmin, rmax, nr); it is memoised on the amodes object, playing the role of
+    the reference's g_nl cache (AnlmModes(...; cache=true), src/SphericalBesselGNLs.jl:558-579)."""
     r, dr = window_r(wmodes)
-    return np.asfortranarray(r[:, None, None] * math.sqrt(dr) * precompute_gnlr(amodes, wmodes))
+    key = (wmodes.rmin, wmodes.rmax, wmodes.nr)
+    cache = amodes.__dict__.setdefault("_rsdrgnlr_cache", {})
+    if key not in cache:
+        cache.clear()
+        cache[key] = np.asfortranarray(r[:, None, None] * math.sqrt(dr) * precompute_gnlr(amodes, wmodes))
+    else:
+        check_nsamp(amodes, wmodes.nr)
+    return cache[key]
 
 
 # --------------------------------------------------------------------------- power_win_mix
