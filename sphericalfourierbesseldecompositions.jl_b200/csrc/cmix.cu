@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace sfb {
@@ -53,21 +54,40 @@ __global__ void w3j000sq_table_kernel(double* __restrict__ w2, int lmax) {
 
 // =============================================================================================
 // W[L1][i][j] = Σ_{M>=0} (2-δ_M0) Re(W1[i,L1M] conj W2[j,L1M])      (src/windows.jl:682-696)
-__global__ void wl_build_kernel(const double* __restrict__ alm1, const double* __restrict__ alm2,
-                                double* __restrict__ W, int LMAX, int nrp) {
+__global__ void __launch_bounds__(256) wl_build_kernel(const double* __restrict__ alm1, const double* __restrict__ alm2,
+                                                       double* __restrict__ W, int LMAX, int nrp) {
+    // each thread owns a 4 x 4 block of (i, j): 16 loads feed 32 FMAs per M
     const int L1 = blockIdx.x;
-    const int n2 = nrp * nrp;
-    for (int e = threadIdx.x; e < n2; e += blockDim.x) {
-        const int i = e / nrp, j = e - i * nrp;
-        double s = 0.0;
+    const int nb = nrp / 4;  // nrp is a multiple of 8
+    for (int blk = threadIdx.x; blk < nb * nb; blk += blockDim.x) {
+        const int i0 = (blk / nb) * 4, j0 = (blk % nb) * 4;
+        double s[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) s[a][b] = 0.0;
         for (int M = 0; M <= L1; ++M) {
             const size_t lm = (size_t)L1 + ((size_t)M * (2 * LMAX + 1 - M)) / 2;
             const double* a1 = alm1 + lm * 2 * nrp;
             const double* a2 = alm2 + lm * 2 * nrp;
-            const double v = a1[i] * a2[j] + a1[nrp + i] * a2[nrp + j];
-            s += (M == 0) ? v : 2.0 * v;
+            const double c = (M == 0) ? 1.0 : 2.0;
+            double r1[4], m1[4], r2[4], m2[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                r1[a] = c * a1[i0 + a];
+                m1[a] = c * a1[nrp + i0 + a];
+                r2[a] = a2[j0 + a];
+                m2[a] = a2[nrp + j0 + a];
+            }
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) s[a][b] = fma(r1[a], r2[b], fma(m1[a], m2[b], s[a][b]));
         }
-        W[(size_t)L1 * n2 + e] = s;
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) W[(size_t)L1 * nrp * nrp + (size_t)(i0 + a) * nrp + j0 + b] = s[a][b];
     }
 }
 
@@ -75,19 +95,21 @@ __global__ void wl_build_kernel(const double* __restrict__ alm1, const double* _
 // Ŵ_{ℓL}[r][r'] = Σ_{L1} (ℓ L L1;000)² W_{L1}[r][r']   — the L1 loop of src/windows.jl:619-622 hoisted out of
 // the per-element work (the quadratic form is linear in W).  One CTA = one ℓ and four L of equal parity, so
 // every W_{L1} element loaded from L2 feeds four accumulators.
+constexpr int kWhatGroup = 8;  // L values (same parity) per CTA: every W_{L1} element loaded from L2 feeds 8 accumulators
+
 __global__ void __launch_bounds__(256) what_build_kernel(const double* __restrict__ W, const double* __restrict__ w2,
                                                          double* __restrict__ What, const int* __restrict__ ells,
                                                          int ell0, int lmax, int nrp, int Llo, int Lhi) {
-    extern __shared__ double wsm[];  // [4][lmax+1]
+    extern __shared__ double wsm[];  // [kWhatGroup][lmax+1]
     const int ell = ells[blockIdx.y];
-    const int gi = blockIdx.x, p = gi & 1, base = (gi >> 1) * 8 + p;
-    if (base > Lhi || base + 6 < Llo) return;  // no L of this group is needed by the column shard
+    const int gi = blockIdx.x, p = gi & 1, base = (gi >> 1) * (2 * kWhatGroup) + p;
+    if (base > Lhi || base + 2 * (kWhatGroup - 1) < Llo) return;  // no L of this group is needed by the column shard
     const int par = (ell + p) & 1;
     const int KW = lmax + 1;
-    for (int x = threadIdx.x; x < 4 * KW; x += blockDim.x) wsm[x] = 0.0;
+    for (int x = threadIdx.x; x < kWhatGroup * KW; x += blockDim.x) wsm[x] = 0.0;
     __syncthreads();
     int L1lo = 1 << 30, L1hi = -1;
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < kWhatGroup; ++q) {
         const int L = base + 2 * q;
         if (L > lmax) break;
         const int lo = min(ell, L), d = abs(ell - L);
@@ -100,15 +122,18 @@ __global__ void __launch_bounds__(256) what_build_kernel(const double* __restric
     if (L1hi < 0) return;
     const int n2 = nrp * nrp;
     for (int e = threadIdx.x; e < n2; e += blockDim.x) {
-        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        double acc[kWhatGroup];
+#pragma unroll
+        for (int q = 0; q < kWhatGroup; ++q) acc[q] = 0.0;
+#pragma unroll 2
         for (int L1 = L1lo; L1 <= L1hi; L1 += 2) {
             const double x = __ldg(W + (size_t)L1 * n2 + e);
             const int h = (L1 - par) >> 1;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) acc[q] = fma(wsm[q * KW + h], x, acc[q]);
+            for (int q = 0; q < kWhatGroup; ++q) acc[q] = fma(wsm[q * KW + h], x, acc[q]);
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < kWhatGroup; ++q) {
             const int L = base + 2 * q;
             if (L <= lmax) What[((size_t)(ell - ell0) * (lmax + 1) + L) * n2 + e] = acc[q];
         }
@@ -141,15 +166,16 @@ struct CmixArgs {
     int ell0, lmax, nmax, nrp, S, NC;
     int col_lo, col_hi;     // output columns [col_lo, col_hi) are written, relative to col_lo
     int div2Lp1, interchange;
+    int dbg;                // profiling aid (SFB_CMIX_DBG): 1 skip epilogue stores, 2 skip Z phase, 4 skip T-phase DMMA
 };
 
-constexpr int kCmixThreads = 256;
+constexpr int kCmixThreads = 128;   // 4 warps; two CTAs per SM so that one CTA's prologue/tail overlaps the other's DMMA phase
 constexpr int kCmixWarps = kCmixThreads / 32;
 
 __host__ __device__ constexpr int cmix_tld(int AP) { return (AP % 16 == 8) ? AP : AP + 8; }  // ≡ 8 (mod 16)
 
 template <int AT, bool SYM>
-__global__ void __launch_bounds__(kCmixThreads, 1) cmix_block_kernel(CmixArgs p) {
+__global__ void __launch_bounds__(kCmixThreads, 2) cmix_block_kernel(CmixArgs p) {
     extern __shared__ double sm[];
     const int ell = p.ell_list[blockIdx.y];
     const int L = p.ch_L[blockIdx.x], N0 = p.ch_N0[blockIdx.x], N1 = p.ch_N1[blockIdx.x];
@@ -196,7 +222,7 @@ __global__ void __launch_bounds__(kCmixThreads, 1) cmix_block_kernel(CmixArgs p)
     const int ntile = nrp / 8, njp = (ntile + 1) / 2;
     const int wgrp = min(njp, kCmixWarps), nlane = kCmixWarps / wgrp;
     const int wj = warp % wgrp, wn = warp / wgrp;
-    if (wn < nlane) {
+    if (wn < nlane && !(p.dbg & 2)) {
         for (int jtp = wj; jtp < njp; jtp += wgrp) {
             const int jt = 2 * jtp;
             const bool two = (jt + 1 < ntile);
@@ -323,7 +349,7 @@ __global__ void __launch_bounds__(kCmixThreads, 1) cmix_block_kernel(CmixArgs p)
             const double* glA = GL + N2 * S;
             const double* glB = GL + ((N2 + 1 < b) ? N2 + 1 : N2) * S;
 #pragma unroll 2
-            for (int k0 = 0; k0 < nrp; k0 += 4) {
+            for (int k0 = 0; k0 < ((p.dbg & 4) ? 4 : nrp); k0 += 4) {
                 double sc[P], zv[AT], gv[AT];
                 sc[0] = glA[k0 + t];
                 if (P > 1) sc[P - 1] = glB[k0 + t];
@@ -350,7 +376,7 @@ __global__ void __launch_bounds__(kCmixThreads, 1) cmix_block_kernel(CmixArgs p)
             }
 #pragma unroll
             for (int q = 0; q < P; ++q) {
-                if (col[q] < 0) continue;  // warp-uniform
+                if (col[q] < 0 || (p.dbg & 1)) continue;  // warp-uniform
 #pragma unroll
                 for (int i = 0; i < AT; ++i)
 #pragma unroll
@@ -366,23 +392,39 @@ __global__ void __launch_bounds__(kCmixThreads, 1) cmix_block_kernel(CmixArgs p)
                 const double* T2 = SYM ? Tw : Tw + AP * TLD;
                 const size_t coff = (size_t)col[q] * p.ldM;
                 const bool offdiag = (N2 + q != N);
-                for (int idx = lane; idx < nrows; idx += 32) {
-                    const int orow = rowtab[idx];
-                    if (orow < 0) continue;
-                    const int code = rowtab[nrows + idx], n = code & 0xffff, n2 = code >> 16;
-                    double v;
-                    if (p.interchange) {
-                        v = T2[n2 * TLD + n];
-                    } else {
-                        v = T1[n * TLD + n2];
-                        if (offdiag) v += T2[n2 * TLD + n];
-                    }
-                    v *= scale;
-                    // own copy first, then the same element straight into every peer's matrix over NVLink
-                    // (P2P stores): the all-gather of the row shards is fused into the epilogue
+                // four rows per lane per iteration: independent load chains hide the shared-memory latency
+                for (int idx0 = lane; idx0 < nrows; idx0 += 128) {
+                    int orow[4], code[4];
+                    double v[4];
 #pragma unroll
-                    for (int d = 0; d < 8; ++d)
-                        if (d < p.npeers) p.M[d][coff + orow] = v;
+                    for (int u = 0; u < 4; ++u) {
+                        const int idx = idx0 + 32 * u;
+                        orow[u] = (idx < nrows) ? rowtab[idx] : -1;
+                        code[u] = (idx < nrows) ? rowtab[nrows + idx] : 0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int n = code[u] & 0xffff, n2 = code[u] >> 16;
+                        if (p.interchange) {
+                            v[u] = T2[n2 * TLD + n];
+                        } else {
+                            v[u] = T1[n * TLD + n2];
+                            if (offdiag) v[u] += T2[n2 * TLD + n];
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (orow[u] < 0) continue;
+                        const double val = v[u] * scale;
+                        // own copy first, then (optional, row-sharded "stores" mode) the same element straight into
+                        // every peer's matrix over NVLink
+                        p.M[0][coff + orow[u]] = val;
+                        if (p.npeers > 1) {
+#pragma unroll
+                            for (int d = 1; d < 8; ++d)
+                                if (d < p.npeers) p.M[d][coff + orow[u]] = val;
+                        }
+                    }
                 }
                 __syncwarp();
             }
@@ -424,15 +466,19 @@ static int launch_cmix_at(int AT, const CmixArgs& args, int nchunks, int nells, 
     return 2;
 }
 
-// number of N values whose Z fits next to the fixed buffers in ~200 KB of shared memory
-static int cmix_chunk_size(int AT, bool sym, int S, int nmax, int max_rows) {
-    const size_t budget = 200 * 1024;
+// number of N values whose Z fits next to the fixed buffers in ~110 KB of shared memory (two CTAs per SM)
+static int cmix_chunk_size_for(size_t budget, int AT, bool sym, int S, int nmax, int max_rows) {
     const int AP = AT * 8, NZ = sym ? 1 : 2;
     const size_t fixed = sizeof(double) * ((size_t)AP * S + (size_t)nmax * S + (size_t)kCmixWarps * NZ * AP * cmix_tld(AP)) +
                          sizeof(int) * 2 * (size_t)max_rows;
     const size_t per = sizeof(double) * (size_t)NZ * AP * S + sizeof(int) * (size_t)nmax;
     if (fixed + per > budget) return 0;
     return (int)std::min<size_t>(nmax, (budget - fixed) / per);
+}
+static int cmix_chunk_size(int AT, bool sym, int S, int nmax, int max_rows) {
+    // prefer two CTAs per SM (~110 KB each); long radial grids need the whole 220 KB for one CTA
+    const int nc = cmix_chunk_size_for(110 * 1024, AT, sym, S, nmax, max_rows);
+    return nc >= 1 ? nc : cmix_chunk_size_for(220 * 1024, AT, sym, S, nmax, max_rows);
 }
 
 // =============================================================================================
@@ -639,10 +685,11 @@ int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp
     args.interchange = interchange;
     args.col_lo = (int)col_lo;
     args.col_hi = (int)col_hi;
+    args.dbg = getenv("SFB_CMIX_DBG") ? atoi(getenv("SFB_CMIX_DBG")) : 0;
 
     float t_what = 0.f, t_block = 0.f;
     double flops = 0.0;
-    const int ngroups = 2 * (int)ceil_div(lmax + 1, 8);
+    const int ngroups = 2 * (int)ceil_div(lmax + 1, 2 * kWhatGroup);
     std::vector<int> ell_list_all;  // device ell_list is filled per launch at distinct offsets
     for (int ell0 = 0; ell0 <= lmax; ell0 += chunk) {
         const int ell1 = std::min(lmax + 1, ell0 + chunk);
@@ -661,7 +708,7 @@ int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp
         SFB_TRY(p->d_what_ells.alloc(lmax + 1));
         SFB_CUDA_OK(cudaMemcpyAsync(p->d_what_ells.p, wells.data(), wells.size() * sizeof(int), cudaMemcpyHostToDevice,
                                     stream));
-        what_build_kernel<<<dim3(ngroups, (unsigned)wells.size()), 256, 4 * (lmax + 1) * sizeof(double), stream>>>(
+        what_build_kernel<<<dim3(ngroups, (unsigned)wells.size()), 256, kWhatGroup * (lmax + 1) * sizeof(double), stream>>>(
             p->d_W.p, p->d_w2.p, p->d_What.p, p->d_what_ells.p, ell0, lmax, nrp, Llo, Lhi);
         SFB_CUDA_OK(cudaGetLastError());
         p->launches++;

@@ -512,6 +512,7 @@ __global__ void __launch_bounds__(kT) cap_analysis_kernel(const double* __restri
                 As[(32 + row) * kLdF + kk] = sn;
             }
             // B: 16 q x BW shells, four folded combinations
+#pragma unroll
             for (int x = tid; x < kFK * BW; x += kT) {
                 const int k2 = x / BW, c = x % BW, qq = q0 + k2;
                 double f1 = 0.0, f2 = 0.0, f3 = 0.0, f4 = 0.0;
@@ -597,6 +598,7 @@ __global__ void __launch_bounds__(kT) cap_synthesis_kernel(const double* __restr
                 As[((2 + par) * 32 + row) * kLdF + kk] = sn;
             }
             // B: 32 m x {re, im} x BW shells
+#pragma unroll
             for (int x = tid; x < 2 * kFK * BW; x += kT) {
                 const int mm = x / BW, c = x % BW, m = m0 + mm;
                 double vr = 0.0, vi = 0.0;
@@ -693,6 +695,7 @@ __global__ void __launch_bounds__(kT) legendre_analysis_kernel(const double* __r
                 if (l <= lmax && k0 + kk < nhalf) v = lam[lm_mmajor(lmax, l, m) * nhalf + k0 + kk];
                 As[row * kLdA + kk] = v;
             }
+#pragma unroll
             for (int x = tid; x < 32 * BW; x += kT) {
                 const int k2 = x / BW, c = x % BW, k = k0 + k2;
                 double fn = 0.0, fs = 0.0;
@@ -759,6 +762,7 @@ __global__ void __launch_bounds__(kT) legendre_synthesis_kernel(const double* __
                 if (l <= lmax && k0 + x < nhalf) lv = lam[lm_mmajor(lmax, l, m) * nhalf + k0 + x];
                 Ls[k2 * kLdB + x] = lv;
             }
+#pragma unroll
             for (int y = tid; y < 32 * BW; y += kT) {
                 const int k2 = y / BW, c = y % BW;
                 const int l = l0 + ((k2 < 16) ? 2 * k2 : 2 * (k2 - 16) + 1);
