@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 namespace sfb {
 
@@ -671,7 +672,8 @@ __global__ void __launch_bounds__(kT) legendre_analysis_kernel(const double* __r
     double* As = la_smem;              // [64][kLdA]
     double* Bp = As + 64 * kLdA;       // [32][LD]  F_N + F_S
     double* Bm = Bp + 32 * LD;         // [32][LD]  F_N - F_S
-    const int m = blockIdx.x, c0 = blockIdx.y * BW, l0 = m + blockIdx.z * 64;
+    // l-chunk index fastest: the CTAs that re-read the same F_m slab are co-scheduled and share it through L2
+    const int m = blockIdx.z, c0 = blockIdx.y * BW, l0 = m + blockIdx.x * 64;
     if (l0 > lmax) return;
     const int ncol = 2 * nrp;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
@@ -892,7 +894,8 @@ int sht_plan_create(ShtPlan** out, int64_t nside_in, int64_t nside_out, int64_t 
     p->n_fft_rings = (int)fft_rings.size();
     {
         // complex lanes per CTA: n * sch * 16 B <= 64 KB, a power of two dividing nrp/2
-        int bound = std::max(1, 4096 / (4 * p->nside));
+        const int fft_budget = getenv("SFB_FFT_ELEMS") ? atoi(getenv("SFB_FFT_ELEMS")) : 4096;  // complex values per CTA
+        int bound = std::max(1, fft_budget / (4 * p->nside));
         bound = std::min(bound, 16);
         int sch = 1;
         while (sch * 2 <= bound && (p->nrp / 2) % (sch * 2) == 0) sch *= 2;
@@ -971,7 +974,7 @@ static int run_analysis(ShtPlan* p, const double* map, int64_t ldw, int accumula
         p->launches++;
     }
     const int nil = pick_ni(2 * nrp);
-    dim3 g2(lmax + 1, (unsigned)ceil_div(2 * nrp, 16 * nil), (unsigned)ceil_div(lmax + 1, 64));
+    dim3 g2((unsigned)ceil_div(lmax + 1, 64), (unsigned)ceil_div(2 * nrp, 16 * nil), lmax + 1);
     const double w = 4.0 * 3.14159265358979323846 / (double)p->npix;
     const int la_smem_bytes = (64 * kLdA + 2 * 32 * (16 * nil + 4)) * (int)sizeof(double);
 #define SFB_LAUNCH_LA(NI_)                                                                                            \
