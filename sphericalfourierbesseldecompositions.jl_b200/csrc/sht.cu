@@ -343,24 +343,104 @@ __global__ void __launch_bounds__(kT) ring_synthesis_kernel(const double* __rest
 // ---------------------------------------------------------------------------------------------
 // Equatorial-belt rings (nφ = 4 nside, a power of two): shared-memory radix-2 FFT, two real shells packed into
 // one complex sequence.  Z holds n x SCH complex values; input in bit-reversed order, output in natural order.
+// R-point DFT of a register array (decimation in frequency, then the bit-reversal is undone by register renaming).
+__device__ __constant__ double c_cos16[8] = {1.0, 0.92387953251128674, 0.70710678118654752, 0.38268343236508977,
+                                            0.0, -0.38268343236508977, -0.70710678118654752, -0.92387953251128674};
+__device__ __constant__ double c_sin16[8] = {0.0, 0.38268343236508977, 0.70710678118654752, 0.92387953251128674,
+                                            1.0, 0.92387953251128674, 0.70710678118654752, 0.38268343236508977};
+
+template <int R, int DIR>
+__device__ __forceinline__ void dft_reg(double2 (&x)[R]) {
+#pragma unroll
+    for (int h = R / 2; h >= 1; h >>= 1) {
+#pragma unroll
+        for (int blk = 0; blk < R; blk += 2 * h) {
+#pragma unroll
+            for (int k = 0; k < h; ++k) {
+                const double2 u = x[blk + k], v = x[blk + k + h];
+                x[blk + k] = make_double2(u.x + v.x, u.y + v.y);
+                const double dx = u.x - v.x, dy = u.y - v.y;
+                const int ti = k * (8 / h);  // W_{2h}^k = W_16^{k * 8/h}
+                if (ti == 0) {
+                    x[blk + k + h] = make_double2(dx, dy);
+                } else if (ti == 4) {       // multiply by (0, DIR) i.e. ±i ... W = e^{DIR iπ/2}
+                    x[blk + k + h] = make_double2(-DIR * dy, DIR * dx);
+                } else {
+                    const double wr = c_cos16[ti], wi = DIR * c_sin16[ti];
+                    x[blk + k + h] = make_double2(dx * wr - dy * wi, dx * wi + dy * wr);
+                }
+            }
+        }
+    }
+    // undo the bit reversal (compile-time permutation)
+    double2 y[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+        int r = 0;
+#pragma unroll
+        for (int b = 1, c = R >> 1; b < R; b <<= 1, c >>= 1)
+            if (i & b) r |= c;
+        y[r] = x[i];
+    }
+#pragma unroll
+    for (int i = 0; i < R; ++i) x[i] = y[i];
+}
+
+// One Stockham (autosort) radix-R pass over Z[n][sch] in shared memory, in place: every thread reads the inputs of
+// its butterflies into registers, barrier, writes the outputs, barrier.  Ns = product of the previous radices.
+// tw[idx] = (cos, sin)(π idx / n), idx in [0, 2n).  At most 16 complex values per thread (n * sch <= 4096).
+template <int R, int DIR>
+__device__ __forceinline__ void stockham_pass(double2* Z, int n, int sch, int Ns, const double2* __restrict__ tw) {
+    constexpr int MAXU = 16 / R;
+    const int nb = n / R, nbf = nb * sch;
+    const int tstep = (2 * n) / (Ns * R);
+    double2 x[MAXU][R];
+    int j0s[MAXU];
+#pragma unroll
+    for (int u = 0; u < MAXU; ++u) {
+        const int b = threadIdx.x + u * kT;
+        if (b < nbf) {
+            const int lane = b % sch, j = b / sch, k = j & (Ns - 1);
+#pragma unroll
+            for (int t = 0; t < R; ++t) x[u][t] = Z[(j + t * nb) * sch + lane];
+#pragma unroll
+            for (int t = 1; t < R; ++t) {
+                const double2 w = tw[k * t * tstep];
+                const double wr = w.x, wi = DIR * w.y;
+                const double2 v = x[u][t];
+                x[u][t] = make_double2(v.x * wr - v.y * wi, v.x * wi + v.y * wr);
+            }
+            dft_reg<R, DIR>(x[u]);
+            j0s[u] = ((j - k) * R + k) * sch + lane;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < MAXU; ++u) {
+        const int b = threadIdx.x + u * kT;
+        if (b < nbf) {
+#pragma unroll
+            for (int t = 0; t < R; ++t) Z[j0s[u] + t * Ns * sch] = x[u][t];
+        }
+    }
+    __syncthreads();
+}
+
+// n-point FFT (n = 2^log2n) of the sch interleaved sequences in Z, natural order in and out.
 template <int DIR>  // -1: forward e^{-iθ}, +1: backward e^{+iθ}
 __device__ __forceinline__ void fft_smem(double2* Z, int n, int log2n, int sch, const double2* __restrict__ tw) {
-    const int nbf = (n >> 1) * sch;
-    for (int s = 0; s < log2n; ++s) {
-        const int half = 1 << s;
-        for (int x = threadIdx.x; x < nbf; x += blockDim.x) {
-            const int lane = x % sch, b = x / sch;
-            const int k = b & (half - 1);
-            const int i0 = ((b >> s) << (s + 1)) + k, i1 = i0 + half;
-            const double2 w = tw[k * (n >> s)];  // (cos, sin)(π k / half)
-            const double wr = w.x, wi = DIR * w.y;
-            const double2 u = Z[i0 * sch + lane], v = Z[i1 * sch + lane];
-            const double2 vw = make_double2(v.x * wr - v.y * wi, v.x * wi + v.y * wr);
-            Z[i0 * sch + lane] = make_double2(u.x + vw.x, u.y + vw.y);
-            Z[i1 * sch + lane] = make_double2(u.x - vw.x, u.y - vw.y);
-        }
-        __syncthreads();
+    int Ns = 1, rem = log2n;
+    while (rem >= 4) {
+        stockham_pass<16, DIR>(Z, n, sch, Ns, tw);
+        Ns *= 16;
+        rem -= 4;
     }
+    if (rem == 3)
+        stockham_pass<8, DIR>(Z, n, sch, Ns, tw);
+    else if (rem == 2)
+        stockham_pass<4, DIR>(Z, n, sch, Ns, tw);
+    else if (rem == 1)
+        stockham_pass<2, DIR>(Z, n, sch, Ns, tw);
 }
 
 // F_m = e^{-imφ0} X[m mod n] for one belt ring and 2*sch shells     CTA = (belt ring, shell chunk)
@@ -378,7 +458,7 @@ __global__ void __launch_bounds__(kT) belt_analysis_fft_kernel(const double* __r
         const int sa = sh0 + 2 * lane;
         const double* src = map + (size_t)(start + j) * ldw + sa;
         const double a = (sa < nr) ? src[0] : 0.0, b = (sa + 1 < nr) ? src[1] : 0.0;
-        Zs[(__brev((unsigned)j) >> (32 - log2n)) * sch + lane] = make_double2(a, b);
+        Zs[j * sch + lane] = make_double2(a, b);
     }
     __syncthreads();
     fft_smem<-1>(Zs, n, log2n, sch, tw);
@@ -437,7 +517,7 @@ __global__ void __launch_bounds__(kT) belt_synthesis_fft_kernel(const double* __
                 }
             }
         }
-        Zs[(__brev((unsigned)k) >> (32 - log2n)) * sch + lane] = make_double2(hr, hi);
+        Zs[k * sch + lane] = make_double2(hr, hi);
     }
     __syncthreads();
     fft_smem<+1>(Zs, n, log2n, sch, tw);
@@ -849,7 +929,7 @@ int sht_plan_create(ShtPlan** out, int64_t nside_in, int64_t nside_out, int64_t 
     std::vector<int> nphi(p->nrings), start(p->nrings), shift(p->nrings), twoff(p->nrings), tile_ring, tile_j0;
     std::vector<int> gemm_rings, fft_rings, cap_rings, ctile_ring, ctile_q0;
     // belt rings (nφ = 4 nside) go through the shared-memory FFT when nside is a power of two
-    p->use_fft = pow2(nside_out) && (4 * nside_out >= 8);
+    p->use_fft = pow2(nside_out) && (4 * nside_out >= 8) && (4 * nside_out <= 4096);  // <= 16 values per thread
     p->log2n = 0;
     while ((1 << p->log2n) < 4 * p->nside) p->log2n++;
     const int64_t ncap = 2LL * ns * (ns - 1);
