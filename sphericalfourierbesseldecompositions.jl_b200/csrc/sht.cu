@@ -561,7 +561,8 @@ __global__ void __launch_bounds__(kT) cap_analysis_kernel(const double* __restri
     constexpr int BW = ColTile<NI>::BW, LD = ColTile<NI>::LD;
     __shared__ double As[64 * kLdF];
     __shared__ double Bs[4][kFK * LD];
-    const int ring = ring_list[blockIdx.x], m0 = blockIdx.y * 32, sh0 = blockIdx.z * BW;
+    // m-chunk index fastest: the CTAs that re-read the same ring of the map are co-scheduled (L2 reuse)
+    const int ring = ring_list[blockIdx.y], m0 = blockIdx.x * 32, sh0 = blockIdx.z * BW;
     const int nphi = rt.nphi[ring], start = rt.start[ring];
     const int nq = nphi >> 2;
     const double2* tw = rt.tw + rt.twoff[ring];
@@ -574,37 +575,47 @@ __global__ void __launch_bounds__(kT) cap_analysis_kernel(const double* __restri
 #pragma unroll
         for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
+    // software pipeline: twiddle lookups and map loads of chunk q+1 are in flight during the DMMAs of chunk q
+    constexpr int NB = (kFK * BW) / kT;
+    double2 rw[2];
+    double rf[NB][4];
+    auto prefetch = [&](int q0) {
+        const int kk = tid & 15, q = q0 + kk;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int m = m0 + (tid >> 4) + 16 * r;
+            rw[r] = make_double2(0.0, 0.0);
+            if (q < nq && m <= lmax) rw[r] = tw[((unsigned)m * (unsigned)(2 * q + 1)) % two_nphi];
+        }
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+            const int x = tid + u * kT, k2 = x / BW, c = x % BW, qq = q0 + k2;
+            rf[u][0] = rf[u][1] = rf[u][2] = rf[u][3] = 0.0;
+            if (qq < nq && sh0 + c < nr) {
+                const double* base = map + (size_t)start * ldw + sh0 + c;
+                rf[u][0] = base[(size_t)qq * ldw];
+                rf[u][1] = base[(size_t)(nphi - 1 - qq) * ldw];
+                rf[u][2] = base[(size_t)(nphi / 2 - 1 - qq) * ldw];
+                rf[u][3] = base[(size_t)(nphi / 2 + qq) * ldw];
+            }
+        }
+    };
+    prefetch(0);
     for (int q0 = 0; q0 < nq; q0 += kFK) {
         {
-            // A: 32 m x 16 q lookups, each gives a cos row and a sin row
-            const int kk = tid & 15, q = q0 + kk;
+            const int kk = tid & 15;
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
-                const int mm = (tid >> 4) + 16 * r, m = m0 + mm;
-                double c = 0.0, sn = 0.0;
-                if (q < nq && m <= lmax) {
-                    const unsigned tt = ((unsigned)m * (unsigned)(2 * q + 1)) % two_nphi;
-                    const double2 w = tw[tt];
-                    c = w.x;
-                    sn = -w.y;
-                }
+                const int mm = (tid >> 4) + 16 * r;
                 const int row = (mm & 1) * 16 + (mm >> 1);
-                As[row * kLdF + kk] = c;
-                As[(32 + row) * kLdF + kk] = sn;
+                As[row * kLdF + kk] = rw[r].x;
+                As[(32 + row) * kLdF + kk] = -rw[r].y;
             }
-            // B: 16 q x BW shells, four folded combinations
 #pragma unroll
-            for (int x = tid; x < kFK * BW; x += kT) {
-                const int k2 = x / BW, c = x % BW, qq = q0 + k2;
-                double f1 = 0.0, f2 = 0.0, f3 = 0.0, f4 = 0.0;
-                if (qq < nq && sh0 + c < nr) {
-                    const double* base = map + (size_t)start * ldw + sh0 + c;
-                    f1 = base[(size_t)qq * ldw];
-                    f2 = base[(size_t)(nphi - 1 - qq) * ldw];
-                    f3 = base[(size_t)(nphi / 2 - 1 - qq) * ldw];
-                    f4 = base[(size_t)(nphi / 2 + qq) * ldw];
-                }
-                const double s = f1 + f2, sp = f3 + f4, d = f1 - f2, dp = f3 - f4;
+            for (int u = 0; u < NB; ++u) {
+                const int x = tid + u * kT, k2 = x / BW, c = x % BW;
+                const double s = rf[u][0] + rf[u][1], sp = rf[u][2] + rf[u][3];
+                const double d = rf[u][0] - rf[u][1], dp = rf[u][2] - rf[u][3];
                 Bs[0][k2 * LD + c] = s + sp;
                 Bs[1][k2 * LD + c] = s - sp;
                 Bs[2][k2 * LD + c] = d - dp;
@@ -612,6 +623,7 @@ __global__ void __launch_bounds__(kT) cap_analysis_kernel(const double* __restri
             }
         }
         __syncthreads();
+        if (q0 + kFK < nq) prefetch(q0 + kFK);
         warp_gemm_ss<2, NI>(acc, As + wm * 16 * kLdF, kLdF, Bs[wm] + wn * 8 * NI, LD, kFK);
         __syncthreads();
     }
@@ -637,7 +649,7 @@ __global__ void __launch_bounds__(kT) cap_analysis_kernel(const double* __restri
 //   f1 = Ce+Co-Se-So, f2 = Ce+Co+Se+So, f3 = Ce-Co+Se-So, f4 = Ce-Co-Se+So;   out = residual ? map - f : f
 // CTA = (tile = (cap ring, 32 folded points), BW shells); warp group wm computes one of Ce, Co, Se, So.
 template <int NI>
-__global__ void __launch_bounds__(kT) cap_synthesis_kernel(const double* __restrict__ G, RingTabs rt,
+__global__ void __launch_bounds__(kT, 2) cap_synthesis_kernel(const double* __restrict__ G, RingTabs rt,
                                                            const int* __restrict__ tile_ring,
                                                            const int* __restrict__ tile_q0, int nrings, int lmax, int nr,
                                                            int nrp, const double* __restrict__ map, long long ldw,
@@ -660,41 +672,51 @@ __global__ void __launch_bounds__(kT) cap_synthesis_kernel(const double* __restr
 #pragma unroll
         for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
+    // software pipeline: twiddle lookups and G loads of the next 32 m's are in flight during the DMMAs
+    constexpr int NB = (2 * kFK * BW) / kT;
+    double2 rw[4];
+    double rr[NB], ri[NB];
+    auto prefetch = [&](int m0) {
+        const int row = tid & 31, q = q0 + row;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int m = m0 + (tid >> 5) + 8 * r;
+            rw[r] = make_double2(0.0, 0.0);
+            if (q < nq && m <= lmax) rw[r] = tw[((unsigned)m * (unsigned)(2 * q + 1)) % two_nphi];
+        }
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+            const int x = tid + u * kT, mm = x / BW, c = x % BW, m = m0 + mm;
+            rr[u] = ri[u] = 0.0;
+            if (m <= lmax && sh0 + c < nrp) {
+                const double cm = (m == 0) ? 1.0 : 2.0;
+                const double* src = G + ((size_t)m * nrings + ring) * 2 * nrp + sh0 + c;
+                rr[u] = cm * src[0];
+                ri[u] = cm * src[nrp];
+            }
+        }
+    };
+    prefetch(0);
     for (int m0 = 0; m0 <= lmax; m0 += 2 * kFK) {
         {
-            // A: 32 q x 32 m lookups -> cos / sin tiles by parity of m
-            const int row = tid & 31, q = q0 + row;
+            const int row = tid & 31;
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
-                const int mm = (tid >> 5) + 8 * r, m = m0 + mm;
-                double c = 0.0, sn = 0.0;
-                if (q < nq && m <= lmax) {
-                    const unsigned tt = ((unsigned)m * (unsigned)(2 * q + 1)) % two_nphi;
-                    const double2 w = tw[tt];
-                    c = w.x;
-                    sn = w.y;
-                }
+                const int mm = (tid >> 5) + 8 * r;
                 const int par = mm & 1, kk = mm >> 1;
-                As[(par * 32 + row) * kLdF + kk] = c;
-                As[((2 + par) * 32 + row) * kLdF + kk] = sn;
+                As[(par * 32 + row) * kLdF + kk] = rw[r].x;
+                As[((2 + par) * 32 + row) * kLdF + kk] = rw[r].y;
             }
-            // B: 32 m x {re, im} x BW shells
 #pragma unroll
-            for (int x = tid; x < 2 * kFK * BW; x += kT) {
-                const int mm = x / BW, c = x % BW, m = m0 + mm;
-                double vr = 0.0, vi = 0.0;
-                if (m <= lmax && sh0 + c < nrp) {
-                    const double cm = (m == 0) ? 1.0 : 2.0;
-                    const double* src = G + ((size_t)m * nrings + ring) * 2 * nrp + sh0 + c;
-                    vr = cm * src[0];
-                    vi = cm * src[nrp];
-                }
+            for (int u = 0; u < NB; ++u) {
+                const int x = tid + u * kT, mm = x / BW, c = x % BW;
                 const int par = mm & 1, kk = mm >> 1;
-                Bs[(par * kFK + kk) * LD + c] = vr;
-                Bs[((2 + par) * kFK + kk) * LD + c] = vi;
+                Bs[(par * kFK + kk) * LD + c] = rr[u];
+                Bs[((2 + par) * kFK + kk) * LD + c] = ri[u];
             }
         }
         __syncthreads();
+        if (m0 + 2 * kFK <= lmax) prefetch(m0 + 2 * kFK);
         warp_gemm_ss<4, NI>(acc, As + wm * 32 * kLdF, kLdF, Bs + wm * kFK * LD + wn * 8 * NI, LD, kFK);
         __syncthreads();
     }
@@ -766,30 +788,46 @@ __global__ void __launch_bounds__(kT) legendre_analysis_kernel(const double* __r
         for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
     const double* Fm = F + (size_t)m * nrings * ncol;
 
+    // software pipeline: the global loads of chunk k+1 are in flight while the DMMAs of chunk k run
+    constexpr int NB = (32 * BW) / kT;  // B elements per thread per chunk
+    double ra[8], rn[NB], rs[NB];
+    size_t arow[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int row = (tid >> 5) + 8 * q;
+        const int l = l0 + ((row < 32) ? 2 * row : 2 * (row - 32) + 1);
+        arow[q] = (l <= lmax) ? lm_mmajor(lmax, l, m) * nhalf : (size_t)-1;
+    }
+    auto prefetch = [&](int k0) {
+        const int kk = tid & 31;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            ra[q] = (arow[q] != (size_t)-1 && k0 + kk < nhalf) ? lam[arow[q] + k0 + kk] : 0.0;
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+            const int x = tid + u * kT, k2 = x / BW, c = x % BW, k = k0 + k2;
+            rn[u] = rs[u] = 0.0;
+            if (k < nhalf && c0 + c < ncol) {
+                rn[u] = Fm[(size_t)k * ncol + c0 + c];
+                if (k != nhalf - 1) rs[u] = Fm[(size_t)(nrings - 1 - k) * ncol + c0 + c];
+            }
+        }
+    };
+    prefetch(0);
     for (int k0 = 0; k0 < nhalf; k0 += 32) {
         {
             const int kk = tid & 31;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int row = (tid >> 5) + 8 * q;
-                const int l = l0 + ((row < 32) ? 2 * row : 2 * (row - 32) + 1);
-                double v = 0.0;
-                if (l <= lmax && k0 + kk < nhalf) v = lam[lm_mmajor(lmax, l, m) * nhalf + k0 + kk];
-                As[row * kLdA + kk] = v;
-            }
+            for (int q = 0; q < 8; ++q) As[((tid >> 5) + 8 * q) * kLdA + kk] = ra[q];
 #pragma unroll
-            for (int x = tid; x < 32 * BW; x += kT) {
-                const int k2 = x / BW, c = x % BW, k = k0 + k2;
-                double fn = 0.0, fs = 0.0;
-                if (k < nhalf && c0 + c < ncol) {
-                    fn = Fm[(size_t)k * ncol + c0 + c];
-                    if (k != nhalf - 1) fs = Fm[(size_t)(nrings - 1 - k) * ncol + c0 + c];
-                }
-                Bp[k2 * LD + c] = fn + fs;
-                Bm[k2 * LD + c] = fn - fs;
+            for (int u = 0; u < NB; ++u) {
+                const int x = tid + u * kT, k2 = x / BW, c = x % BW;
+                Bp[k2 * LD + c] = rn[u] + rs[u];
+                Bm[k2 * LD + c] = rn[u] - rs[u];
             }
         }
         __syncthreads();
+        if (k0 + 32 < nhalf) prefetch(k0 + 32);
         warp_gemm_ss<2, NI>(acc, As + wm * 16 * kLdA, kLdA, Bsel + wn * 8 * NI, LD, 32);
         __syncthreads();
     }
@@ -833,27 +871,38 @@ __global__ void __launch_bounds__(kT) legendre_synthesis_kernel(const double* __
 #pragma unroll
         for (int j = 0; j < NI; ++j) accE[i][j][0] = accE[i][j][1] = accO[i][j][0] = accO[i][j][1] = 0.0;
 
+    // software pipeline: loads of the next 32 l's are in flight while the DMMAs of the current chunk run
+    constexpr int NB = (32 * BW) / kT;
+    double rl[8], rb[NB];
+    auto prefetch = [&](int l0) {
+        const int x = tid & 63;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int k2 = (tid >> 6) + 4 * q;
+            const int l = l0 + ((k2 < 16) ? 2 * k2 : 2 * (k2 - 16) + 1);
+            rl[q] = (l <= lmax && k0 + x < nhalf) ? lam[lm_mmajor(lmax, l, m) * nhalf + k0 + x] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+            const int y = tid + u * kT, k2 = y / BW, c = y % BW;
+            const int l = l0 + ((k2 < 16) ? 2 * k2 : 2 * (k2 - 16) + 1);
+            rb[u] = (l <= lmax && c0 + c < ncol) ? alm[lm_mmajor(lmax, l, m) * ncol + c0 + c] : 0.0;
+        }
+    };
+    prefetch(m);
     for (int l0 = m; l0 <= lmax; l0 += 32) {
         {
             const int x = tid & 63;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int k2 = (tid >> 6) + 4 * q;
-                const int l = l0 + ((k2 < 16) ? 2 * k2 : 2 * (k2 - 16) + 1);
-                double lv = 0.0;
-                if (l <= lmax && k0 + x < nhalf) lv = lam[lm_mmajor(lmax, l, m) * nhalf + k0 + x];
-                Ls[k2 * kLdB + x] = lv;
-            }
+            for (int q = 0; q < 8; ++q) Ls[((tid >> 6) + 4 * q) * kLdB + x] = rl[q];
 #pragma unroll
-            for (int y = tid; y < 32 * BW; y += kT) {
-                const int k2 = y / BW, c = y % BW;
-                const int l = l0 + ((k2 < 16) ? 2 * k2 : 2 * (k2 - 16) + 1);
-                double av = 0.0;
-                if (l <= lmax && c0 + c < ncol) av = alm[lm_mmajor(lmax, l, m) * ncol + c0 + c];
-                Bs[k2 * LD + c] = av;
+            for (int u = 0; u < NB; ++u) {
+                const int y = tid + u * kT;
+                Bs[(y / BW) * LD + (y % BW)] = rb[u];
             }
         }
         __syncthreads();
+        if (l0 + 32 <= lmax) prefetch(l0 + 32);
         warp_gemm_ts<2, NI>(accE, Ls + wm * 16, kLdB, Bs + wn * 8 * NI, LD, 16);
         warp_gemm_ts<2, NI>(accO, Ls + 16 * kLdB + wm * 16, kLdB, Bs + 16 * LD + wn * 8 * NI, LD, 16);
         __syncthreads();
@@ -1033,7 +1082,7 @@ static int run_analysis(ShtPlan* p, const double* map, int64_t ldw, int accumula
     }
     if (p->n_cap_rings > 0) {
         const int ni = pick_ni(nrp);
-        dim3 gc(p->n_cap_rings, (unsigned)ceil_div(lmax + 1, 32), (unsigned)ceil_div(nrp, 16 * ni));
+        dim3 gc((unsigned)ceil_div(lmax + 1, 32), p->n_cap_rings, (unsigned)ceil_div(nrp, 16 * ni));
         if (ni == 4)
             cap_analysis_kernel<4><<<gc, kT, 0, st>>>(map, ldw, p->nr, nrp, rt, p->d_cap_rings.p, p->nrings, lmax, p->d_FG.p);
         else if (ni == 2)
