@@ -375,6 +375,27 @@ def run_b200(args):
                "d2h_bytes_per_step": int(8 * n * n), "ms_per_step": dt * 1e3,
                "api": "sfb_b200.power_win_mix(win, wmodes, cmodes) -> sfb_power_win_mix (C ABI, host pointers)",
                "checksum": float(M[:: max(1, n // 97), :: max(1, n // 89)].sum())}
+        # the binned call of cfg4 (BASELINE.json: "binned ClnnBinnedModes output"): N = w̃ M v, Δl = 4
+        try:
+            wt, vv = sfb.bandpower_binning_weights(wl.cmodes, dl=4)
+            bc = sfb.ClnnBinnedModes(wt, vv, wl.cmodes)
+            outN_t = torch.empty((vv.shape[1], wt.shape[0]), dtype=torch.float64).pin_memory()
+            outN = outN_t.numpy().T
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore", RuntimeWarning)
+                sfb.power_win_mix(host_win, wt, vv, wl.wmodes, bc, out=outN)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(k):
+                    sfb.power_win_mix(host_win, wt, vv, wl.wmodes, bc, out=outN)
+                torch.cuda.synchronize()
+                dtb = (time.perf_counter() - t0) / k
+            e2e["binned"] = {"ms_per_step": dtb * 1e3, "value": n * n / dtb, "unit": UNIT, "LNN": int(wt.shape[0]),
+                             "d2h_bytes_per_step": int(8 * wt.shape[0] * vv.shape[1]),
+                             "note": "power_win_mix(win, w̃, v, wmodes, bcmodes) with Δl=4: all lnnsize² elements of M are "
+                                     "formed on the device, only N = w̃Mv returns to the host"}
+        except Exception as exc:  # noqa: BLE001
+            e2e["binned"] = {"error": str(exc)}
     elif world > 1:
         e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
                "note": "e2e is measured at N=1 through the host C ABI; multi-GPU runs keep shards device-resident"}

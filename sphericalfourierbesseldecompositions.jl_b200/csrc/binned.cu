@@ -31,6 +31,13 @@ __global__ void binned_product_kernel(const double* __restrict__ M, long long n,
     N[I + (size_t)m * LNN1] = c;
 }
 
+__global__ void nonfinite_flag_kernel(const double* __restrict__ x, size_t n, int* flag) {
+    int bad = 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        bad |= !isfinite(x[i]);
+    if (bad) atomicOr(flag, 1);
+}
+
 int binned_product_to_host(const double* d_M, int64_t n, const int64_t* wt_colptr, const int64_t* wt_rowval,
                            const double* wt_nzval, int64_t LNN1, const int64_t* v_colptr, const int64_t* v_rowval,
                            const double* v_nzval, int64_t LNN2, double* N_out, float* ms) {
@@ -108,14 +115,18 @@ int binned_product_to_host(const double* d_M, int64_t n, const int64_t* wt_colpt
     if (ms) *ms = t;
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    {  // @assert all(isfinite.(mix))  src/windows.jl:1013
-        std::vector<double> tmp;  // finite check on the host copy
+    {  // @assert all(isfinite.(mix))  src/windows.jl:1013 — checked on the device before the copy back
+        DevBuf<int> flag;
+        SFB_TRY(flag.alloc(1));
+        SFB_CUDA_OK(cudaMemset(flag.p, 0, sizeof(int)));
+        nonfinite_flag_kernel<<<512, 256>>>(d_N.p, (size_t)LNN1 * LNN2, flag.p);
+        int h = 0;
+        SFB_CUDA_OK(cudaMemcpy(&h, flag.p, sizeof(int), cudaMemcpyDeviceToHost));
+        if (h) {
+            set_error("AssertionError: all(isfinite.(mix))");
+            return 4;
+        }
         SFB_CUDA_OK(cudaMemcpy(N_out, d_N.p, (size_t)LNN1 * LNN2 * sizeof(double), cudaMemcpyDeviceToHost));
-        for (size_t k = 0; k < (size_t)LNN1 * LNN2; ++k)
-            if (!std::isfinite(N_out[k])) {
-                set_error("AssertionError: all(isfinite.(mix))");
-                return 4;
-            }
     }
     return 0;
 }

@@ -6,12 +6,27 @@
 #include "common.cuh"
 #include "sht.cuh"
 
+#include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
 namespace sfb {
 static thread_local std::string g_err;
 void set_error(const std::string& msg) { g_err = msg; }
+
+// SFB_TRACE=1: wall-clock of the phases of the host-pointer entry points on stderr
+struct Trace {
+    bool on = getenv("SFB_TRACE") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void mark(const char* what) {
+        if (!on) return;
+        cudaDeviceSynchronize();
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[sfb] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
 
 static std::mutex g_mutex;  // one call at a time (the Julia side calls from one task and blocks)
 static double g_times[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -103,7 +118,7 @@ static void record_cmix_times(const CmixPlan* p) {
 
 // Device workspace reused across host-pointer calls (cudaMalloc / cudaFree of multi-GB buffers is slow).
 struct Workspace {
-    DevBuf<double> win, alm1, alm2, slab[2];
+    DevBuf<double> win, alm1, alm2, slab[2], M;
     DevBuf<int> flag;
     cudaStream_t copy = nullptr;
     cudaEvent_t computed[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
@@ -170,12 +185,52 @@ static int cmix_to_host_pipelined(CmixPlan* p, const double* a1, const double* a
     return 0;
 }
 
-struct PlanGuard {
-    CmixPlan* p = nullptr;
-    ~PlanGuard() {
-        if (p) cmix_plan_destroy(p);
+// Host-pointer entry points reuse the stage-2/3 plan (index tables, radial basis, 3j table, Ŵ workspace) when the
+// caller passes the same tables again: keyed by the sizes and an FNV-1a hash of the lnn and G bytes.
+static uint64_t fnv1a(const void* data, size_t bytes, uint64_t h = 1469598103934665603ull) {
+    const uint64_t* w = static_cast<const uint64_t*>(data);
+    for (size_t i = 0; i < bytes / 8; ++i) {
+        h ^= w[i];
+        h *= 1099511628211ull;
     }
+    return h;
+}
+struct PlanCache {
+    CmixPlan* p = nullptr;
+    uint64_t key = 0;
+    int64_t dims[5] = {0, 0, 0, 0, 0};
+    int dev = -1;
 };
+static PlanCache g_plan_cache;
+
+struct PlanGuard {  // non-owning handle on the cached plan
+    CmixPlan* p = nullptr;
+};
+
+static int get_cmix_plan(CmixPlan** out, const int64_t* lnn, int64_t lnnsize, int64_t lnn_min, const double* G,
+                         int64_t nr, int64_t nmax, int64_t lmax) {
+    SFB_REQUIRE(lnn && G && lnnsize >= 1 && nr >= 1 && nmax >= 1 && lmax >= 0, "bad mode tables");
+    int dev = 0;
+    SFB_CUDA_OK(cudaGetDevice(&dev));
+    uint64_t key = fnv1a(lnn, (size_t)lnnsize * 3 * sizeof(int64_t));
+    key = fnv1a(G, (size_t)nr * nmax * (lmax + 1) * sizeof(double), key);
+    const int64_t dims[5] = {lnnsize, lnn_min, nr, nmax, lmax};
+    PlanCache& c = g_plan_cache;
+    if (c.p && c.dev == dev && c.key == key && std::memcmp(c.dims, dims, sizeof(dims)) == 0) {
+        *out = c.p;
+        return 0;
+    }
+    if (c.p) {
+        cmix_plan_destroy(c.p);
+        c.p = nullptr;
+    }
+    SFB_TRY(cmix_plan_create(&c.p, lnn, lnnsize, lnn_min, G, nr, nmax, lmax));
+    c.key = key;
+    c.dev = dev;
+    std::memcpy(c.dims, dims, sizeof(dims));
+    *out = c.p;
+    return 0;
+}
 
 // W_lm(r) of one or two windows on the device (planar), shared by the end-to-end entry points
 static int windows_to_alm(const double* win1, const double* win2, int64_t nr, int64_t npix_in, int64_t ld_win,
@@ -267,7 +322,7 @@ int32_t sfb_power_win_mix_from_wrlm(const double* w1r_lm, const double* w2r_lm, 
     SFB_REQUIRE(LMAX == 2 * lmax, "LMAX must equal 2*lmax (src/windows.jl:788)");
     SFB_REQUIRE(layout == 0 || layout == 1, "bad layout");
     PlanGuard pg;
-    SFB_TRY(cmix_plan_create(&pg.p, lnn, lnnsize, lnn_min, G, nr, nmax, lmax));
+    SFB_TRY(get_cmix_plan(&pg.p, lnn, lnnsize, lnn_min, G, nr, nmax, lmax));
     DevBuf<double> a1, a2, dM;
     SFB_TRY(alm_from_host(w1r_lm, nr, (int)LMAX, layout, a1, pg.p->nrp, 0));
     const bool same = (w2r_lm == nullptr || w2r_lm == w1r_lm);
@@ -289,13 +344,17 @@ int32_t sfb_power_win_mix(const double* win1, const double* win2, int64_t nr, in
                           double* M_out) {
     std::lock_guard<std::mutex> lk(g_mutex);
     SFB_REQUIRE(win1 && M_out, "null pointer");
+    Trace tr;
     PlanGuard pg;
-    SFB_TRY(cmix_plan_create(&pg.p, lnn, lnnsize, lnn_min, G, nr, nmax, lmax));
+    SFB_TRY(get_cmix_plan(&pg.p, lnn, lnnsize, lnn_min, G, nr, nmax, lmax));
+    tr.mark("plan");
     DevBuf<double>&a1 = g_ws.alm1, &a2 = g_ws.alm2;
     bool same = true;
     SFB_TRY(windows_to_alm(win1, win2, nr, npix_in, ld_win, nside, 2 * lmax, a1, a2, &same));
+    tr.mark("H2D + stage 1");
     SFB_TRY(cmix_to_host_pipelined(pg.p, a1.p, same ? a1.p : a2.p, div2Lp1, interchange_NN, M_out));
     record_cmix_times(pg.p);
+    tr.mark("stage 2+3 pipelined with D2H");
     return 0;
 }
 
@@ -307,20 +366,25 @@ int32_t sfb_power_win_mix_binned(const double* win1, int64_t nr, int64_t npix_in
                                  int32_t interchange_NN, double* N_out) {
     std::lock_guard<std::mutex> lk(g_mutex);
     SFB_REQUIRE(win1 && N_out, "null pointer");
+    Trace tr;
     PlanGuard pg;
-    SFB_TRY(cmix_plan_create(&pg.p, lnn, lnnsize, 1, G, nr, nmax, lmax));
-    DevBuf<double> a1, a2, dM;
+    SFB_TRY(get_cmix_plan(&pg.p, lnn, lnnsize, 1, G, nr, nmax, lmax));
+    tr.mark("binned: plan");
+    DevBuf<double>&a1 = g_ws.alm1, &a2 = g_ws.alm2, &dM = g_ws.M;
     bool same = true;
     // like the reference, W2r_lm is computed from win1 as well (src/windows.jl:1005-1006)
     SFB_TRY(windows_to_alm(win1, nullptr, nr, npix_in, ld_win, nside, 2 * lmax, a1, a2, &same));
+    tr.mark("binned: H2D + stage 1");
     const int64_t n = pg.p->nout;
     SFB_TRY(dM.alloc((size_t)n * n));
     SFB_TRY(cmix_run(pg.p, a1.p, a1.p, div2Lp1, interchange_NN, 0, n, 0, n, dM.p, n, 0));
     record_cmix_times(pg.p);
+    tr.mark("binned: stage 2+3");
     float t_bin = 0;
     SFB_TRY(binned_product_to_host(dM.p, n, wt_colptr, wt_rowval, wt_nzval, LNN1, v_colptr, v_rowval, v_nzval, LNN2,
                                    N_out, &t_bin));
     g_times[7] = t_bin;
+    tr.mark("binned: w~ M v + D2H");
     return 0;
 }
 
@@ -335,7 +399,7 @@ int32_t sfb_power_win_mix_separable(const double* phi, const double* mask, int64
     int64_t nside_in = 0;
     SFB_TRY(npix2nside(npix_in, &nside_in));
     PlanGuard pg;
-    SFB_TRY(cmix_plan_create(&pg.p, lnn, lnnsize, 1, G, nr, nmax, lmax));
+    SFB_TRY(get_cmix_plan(&pg.p, lnn, lnnsize, 1, G, nr, nmax, lmax));
     // one map2alm of the mask (src/windows.jl:540-545)
     ShtPlan* sp = nullptr;
     SFB_TRY(get_sht_plan(&sp, nside_in, nside, 2 * lmax, 1));

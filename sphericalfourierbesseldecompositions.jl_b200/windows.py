@@ -103,9 +103,10 @@ def check_nsamp(amodes, nr):
     need = 8 * (2 * nmax)
     if need > nr:
         nl = np.asarray(amodes.nmax_l)
-        # number of ((l,n),(L,N)) pairs with 8(n+N) > nr
-        n = np.concatenate([np.arange(1, k + 1) for k in nl])
-        num = int(np.sum(8 * (n[:, None] + n[None, :]) > nr))
+        # number of ((l,n),(L,N)) pairs with 8(n+N) > nr, from the histogram of n over the (n,l) modes
+        cnt = np.array([np.sum(nl >= k) for k in range(1, nmax + 1)], dtype=np.int64)
+        k = np.arange(1, nmax + 1)
+        num = int(np.sum(np.outer(cnt, cnt)[8 * (k[:, None] + k[None, :]) > nr]))
         warnings.warn(f"Radial integrals unlikely to converge: num_imprecise={num} max_nr_needed={need} nr={nr}",
                       RuntimeWarning, stacklevel=3)
 
