@@ -140,14 +140,23 @@ static Workspace g_ws;
 
 // Stage 2+3 for all columns, pipelined with the device->host copy: the matrix is produced in column slabs
 // (contiguous in column-major order); while slab k is copied to the caller's buffer, slab k+1 is computed.
+static bool mirror_enabled() { return getenv("SFB_NO_MIRROR") == nullptr; }
+
 static int cmix_to_host_pipelined(CmixPlan* p, const double* a1, const double* a2, int div2Lp1, int interchange,
                                   double* M_out) {
     SFB_TRY(g_ws.init());
     const int64_t n = p->nout;
-    const auto chunks = cmix_col_chunks(p, 8);
+    const bool mirror = (a1 == a2) && mirror_enabled();
+    // mirror mode: step k forms the blocks (l in chunk k, L >= l) and their mirror images in the full device
+    // matrix, after which the columns of chunk k are complete and can leave; otherwise plain column slabs.
+    const auto chunks = mirror ? cmix_row_chunks_mirror(p, 8) : cmix_col_chunks(p, 8);
     int64_t maxc = 0;
     for (auto& c : chunks) maxc = std::max(maxc, c.second - c.first);
-    for (int i = 0; i < 2 && i < (int)chunks.size(); ++i) SFB_TRY(g_ws.slab[i].alloc((size_t)maxc * n));
+    if (mirror) {
+        SFB_TRY(g_ws.M.alloc((size_t)n * n));
+    } else {
+        for (int i = 0; i < 2 && i < (int)chunks.size(); ++i) SFB_TRY(g_ws.slab[i].alloc((size_t)maxc * n));
+    }
     SFB_TRY(g_ws.flag.alloc(1));
     SFB_CUDA_OK(cudaMemsetAsync(g_ws.flag.p, 0, sizeof(int), 0));
     float t_wl = 0, t_what = 0, t_block = 0;
@@ -156,18 +165,25 @@ static int cmix_to_host_pipelined(CmixPlan* p, const double* a1, const double* a
     for (size_t k = 0; k < chunks.size(); ++k) {
         const int b = (int)(k & 1);
         const int64_t c0 = chunks[k].first, c1 = chunks[k].second;
-        if (k >= 2) SFB_CUDA_OK(cudaEventSynchronize(g_ws.copied[b]));  // slab free again
-        SFB_TRY(cmix_run(p, a1, a2, div2Lp1, interchange, 0, n, c0, c1, g_ws.slab[b].p, n, 0, nullptr, 0, k > 0));
+        double* src = nullptr;
+        if (mirror) {
+            SFB_TRY(cmix_run(p, a1, a2, div2Lp1, interchange, c0, c1, 0, n, g_ws.M.p, n, 0, nullptr, 0, k > 0, true));
+            src = g_ws.M.p + c0 * n;
+        } else {
+            if (k >= 2) SFB_CUDA_OK(cudaEventSynchronize(g_ws.copied[b]));  // slab free again
+            SFB_TRY(cmix_run(p, a1, a2, div2Lp1, interchange, 0, n, c0, c1, g_ws.slab[b].p, n, 0, nullptr, 0, k > 0));
+            src = g_ws.slab[b].p;
+        }
         t_wl += p->t_wl;
         t_what += p->t_what;
         t_block += p->t_block;
         flops += p->flops_executed;
         launches += p->launches;
-        finite_check_kernel<<<512, 256, 0, 0>>>(g_ws.slab[b].p, (size_t)(c1 - c0) * n, g_ws.flag.p);
+        finite_check_kernel<<<512, 256, 0, 0>>>(src, (size_t)(c1 - c0) * n, g_ws.flag.p);
         SFB_CUDA_OK(cudaEventRecord(g_ws.computed[b], 0));
         SFB_CUDA_OK(cudaStreamWaitEvent(g_ws.copy, g_ws.computed[b], 0));
-        SFB_CUDA_OK(cudaMemcpyAsync(M_out + c0 * n, g_ws.slab[b].p, (size_t)(c1 - c0) * n * sizeof(double),
-                                    cudaMemcpyDeviceToHost, g_ws.copy));
+        SFB_CUDA_OK(cudaMemcpyAsync(M_out + c0 * n, src, (size_t)(c1 - c0) * n * sizeof(double), cudaMemcpyDeviceToHost,
+                                    g_ws.copy));
         SFB_CUDA_OK(cudaEventRecord(g_ws.copied[b], g_ws.copy));
     }
     SFB_CUDA_OK(cudaStreamSynchronize(g_ws.copy));
@@ -331,7 +347,8 @@ int32_t sfb_power_win_mix_from_wrlm(const double* w1r_lm, const double* w2r_lm, 
     SFB_TRY(dM.alloc((size_t)n * n));
     g_times[0] = 0;
     g_times[6] = 0;
-    SFB_TRY(cmix_run(pg.p, a1.p, same ? a1.p : a2.p, div2Lp1, interchange_NN, 0, n, 0, n, dM.p, n, 0));
+    SFB_TRY(cmix_run(pg.p, a1.p, same ? a1.p : a2.p, div2Lp1, interchange_NN, 0, n, 0, n, dM.p, n, 0, nullptr, 0, false,
+                     same && mirror_enabled()));
     record_cmix_times(pg.p);
     SFB_TRY(check_finite(dM.p, (size_t)n * n, "mix"));
     SFB_CUDA_OK(cudaMemcpy(M_out, dM.p, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost));
@@ -377,7 +394,7 @@ int32_t sfb_power_win_mix_binned(const double* win1, int64_t nr, int64_t npix_in
     tr.mark("binned: H2D + stage 1");
     const int64_t n = pg.p->nout;
     SFB_TRY(dM.alloc((size_t)n * n));
-    SFB_TRY(cmix_run(pg.p, a1.p, a1.p, div2Lp1, interchange_NN, 0, n, 0, n, dM.p, n, 0));
+    SFB_TRY(cmix_run(pg.p, a1.p, a1.p, div2Lp1, interchange_NN, 0, n, 0, n, dM.p, n, 0, nullptr, 0, false, mirror_enabled()));
     record_cmix_times(pg.p);
     tr.mark("binned: stage 2+3");
     float t_bin = 0;
@@ -496,8 +513,9 @@ int32_t sfb_power_win_mix_dev(sfb_cmix_plan* plan, const double* d_alm1, const d
     std::lock_guard<std::mutex> lk(g_mutex);
     auto* p = reinterpret_cast<CmixPlan*>(plan);
     const double t0 = g_times[6];
+    const bool mirror = (d_alm1 == d_alm2) && row_lo == 0 && row_hi == p->nout && ldM >= p->nout && mirror_enabled();
     SFB_TRY(cmix_run(p, d_alm1, d_alm2, div2Lp1, interchange_NN, row_lo, row_hi, 0, p->nout, d_M, ldM,
-                     (cudaStream_t)stream));
+                     (cudaStream_t)stream, nullptr, 0, false, mirror));
     record_cmix_times(p);
     g_times[6] = t0 + p->launches;
     return 0;

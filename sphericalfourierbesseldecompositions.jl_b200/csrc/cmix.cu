@@ -99,11 +99,12 @@ constexpr int kWhatGroup = 8;  // L values (same parity) per CTA: every W_{L1} e
 
 __global__ void __launch_bounds__(256) what_build_kernel(const double* __restrict__ W, const double* __restrict__ w2,
                                                          double* __restrict__ What, const int* __restrict__ ells,
-                                                         int ell0, int lmax, int nrp, int Llo, int Lhi) {
+                                                         int ell0, int lmax, int nrp, int Llo, int Lhi, int mirror) {
     extern __shared__ double wsm[];  // [kWhatGroup][lmax+1]
     const int ell = ells[blockIdx.y];
     const int gi = blockIdx.x, p = gi & 1, base = (gi >> 1) * (2 * kWhatGroup) + p;
-    if (base > Lhi || base + 2 * (kWhatGroup - 1) < Llo) return;  // no L of this group is needed by the column shard
+    if (base > Lhi || base + 2 * (kWhatGroup - 1) < Llo) return;
+    if (mirror && base + 2 * (kWhatGroup - 1) < ell) return;  // only L >= l blocks are formed  // no L of this group is needed by the column shard
     const int par = (ell + p) & 1;
     const int KW = lmax + 1;
     for (int x = threadIdx.x; x < kWhatGroup * KW; x += blockDim.x) wsm[x] = 0.0;
@@ -166,6 +167,7 @@ struct CmixArgs {
     int ell0, lmax, nmax, nrp, S, NC;
     int col_lo, col_hi;     // output columns [col_lo, col_hi) are written, relative to col_lo
     int div2Lp1, interchange;
+    int mirror;             // 1: only blocks with L >= l are formed; each tile also fills M[(L,N,N'),(l,n,n')]
     int dbg;                // profiling aid (SFB_CMIX_DBG): 1 skip epilogue stores, 2 skip Z phase, 4 skip T-phase DMMA
 };
 
@@ -181,6 +183,7 @@ __global__ void __launch_bounds__(kCmixThreads, 2) cmix_block_kernel(CmixArgs p)
     const int L = p.ch_L[blockIdx.x], N0 = p.ch_N0[blockIdx.x], N1 = p.ch_N1[blockIdx.x];
     const int a = p.a_of_ell[ell], b = p.a_of_ell[L];
     if (a == 0 || N0 >= b) return;
+    if (p.mirror && L < ell) return;  // obtained from block (L, l) by the symmetry of the un-symmetrised kernel
     constexpr int AP = AT * 8;
     constexpr int TLD = cmix_tld(AP);       // staging leading dimension: double2 stores are conflict free
     constexpr int P = SYM ? 2 : 1;          // N' tiles per warp pass (shares the Z and G_l fragment loads)
@@ -315,6 +318,8 @@ __global__ void __launch_bounds__(kCmixThreads, 2) cmix_block_kernel(CmixArgs p)
 
     // ---- T phase: (N, N') tiles of the chunk dealt round-robin, P consecutive N' per pass -----------------
     const double scale = (p.div2Lp1 ? 1.0 : (2.0 * L + 1.0)) * 0.07957747154594767;  // 1/(4π)
+    const double scale_l = (p.div2Lp1 ? 1.0 : (2.0 * ell + 1.0)) * 0.07957747154594767;
+    const bool domirror = p.mirror && (L > ell);
     double* Tw = Ts + warp * NZ * AP * TLD;
     int cnt = 0;
     for (int Nloc = 0; Nloc < nN; ++Nloc) {
@@ -402,28 +407,30 @@ __global__ void __launch_bounds__(kCmixThreads, 2) cmix_block_kernel(CmixArgs p)
                         orow[u] = (idx < nrows) ? rowtab[idx] : -1;
                         code[u] = (idx < nrows) ? rowtab[nrows + idx] : 0;
                     }
+                    double vm[4];  // mirrored element M[(L,N,N'),(l,n,n')] = c_l (A + [n≠n'] B), A = T[n][n'], B = T[n'][n]
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         const int n = code[u] & 0xffff, n2 = code[u] >> 16;
+                        const double A = T1[n * TLD + n2], B = T2[n2 * TLD + n];
                         if (p.interchange) {
-                            v[u] = T2[n2 * TLD + n];
+                            v[u] = B;
+                            vm[u] = B;
                         } else {
-                            v[u] = T1[n * TLD + n2];
-                            if (offdiag) v[u] += T2[n2 * TLD + n];
+                            v[u] = offdiag ? A + B : A;
+                            vm[u] = (n != n2) ? A + B : A;
                         }
                     }
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         if (orow[u] < 0) continue;
                         const double val = v[u] * scale;
-                        // own copy first, then (optional, row-sharded "stores" mode) the same element straight into
-                        // every peer's matrix over NVLink
                         p.M[0][coff + orow[u]] = val;
                         if (p.npeers > 1) {
 #pragma unroll
                             for (int d = 1; d < 8; ++d)
                                 if (d < p.npeers) p.M[d][coff + orow[u]] = val;
                         }
+                        if (domirror) p.M[0][(size_t)orow[u] * p.ldM + col[q]] = vm[u] * scale_l;
                     }
                 }
                 __syncwarp();
@@ -606,7 +613,7 @@ void cmix_plan_destroy(CmixPlan* p) { delete p; }
 
 int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp1, int interchange, int64_t row_lo,
              int64_t row_hi, int64_t col_lo, int64_t col_hi, double* d_M, int64_t ldM, cudaStream_t stream,
-             double* const* peers, int npeers, bool reuse_wl) {
+             double* const* peers, int npeers, bool reuse_wl, bool mirror) {
     SFB_REQUIRE(p && d_alm1 && d_alm2 && d_M, "cmix_run: null pointer");
     SFB_REQUIRE(npeers >= 0 && npeers <= 7, "cmix_run: at most 7 peers");
     SFB_REQUIRE(0 <= row_lo && row_lo <= row_hi && row_hi <= p->nout, "cmix_run: bad row range");
@@ -617,6 +624,11 @@ int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp
     p->launches = 0;
     if (row_hi == row_lo || col_hi == col_lo) return 0;
     const bool sym = (d_alm1 == d_alm2);
+    if (mirror) {
+        // mirror mode fills the FULL matrix: d_M is its base, rows are an l-aligned range, all columns
+        SFB_REQUIRE(sym && npeers == 0 && col_lo == 0 && col_hi == p->nout && ldM >= p->nout,
+                    "cmix_run: mirror mode needs the auto-correlation path and the full matrix");
+    }
     const int lmax = p->lmax, nrp = p->nrp;
     cudaEvent_t ev[4];
     for (auto& e : ev) SFB_CUDA_OK(cudaEventCreate(&e));
@@ -628,7 +640,7 @@ int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp
         for (int s = p->ell_ptr[l]; s < p->ell_ptr[l + 1]; ++s) {
             const int o = p->h_row_out[s];
             const bool in = (o >= row_lo && o < row_hi);
-            row_out[s] = in ? (int)(o - row_lo) : -1;
+            row_out[s] = in ? (int)(mirror ? o : o - row_lo) : -1;
             if (in) ell_used[l] = 1;
         }
     SFB_CUDA_OK(cudaMemcpyAsync(p->d_row_out.p, row_out.data(), row_out.size() * sizeof(int), cudaMemcpyHostToDevice,
@@ -685,6 +697,7 @@ int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp
     args.interchange = interchange;
     args.col_lo = (int)col_lo;
     args.col_hi = (int)col_hi;
+    args.mirror = mirror ? 1 : 0;
     args.dbg = getenv("SFB_CMIX_DBG") ? atoi(getenv("SFB_CMIX_DBG")) : 0;
 
     float t_what = 0.f, t_block = 0.f;
@@ -709,7 +722,7 @@ int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp
         SFB_CUDA_OK(cudaMemcpyAsync(p->d_what_ells.p, wells.data(), wells.size() * sizeof(int), cudaMemcpyHostToDevice,
                                     stream));
         what_build_kernel<<<dim3(ngroups, (unsigned)wells.size()), 256, kWhatGroup * (lmax + 1) * sizeof(double), stream>>>(
-            p->d_W.p, p->d_w2.p, p->d_What.p, p->d_what_ells.p, ell0, lmax, nrp, Llo, Lhi);
+            p->d_W.p, p->d_w2.p, p->d_What.p, p->d_what_ells.p, ell0, lmax, nrp, Llo, Lhi, mirror ? 1 : 0);
         SFB_CUDA_OK(cudaGetLastError());
         p->launches++;
         SFB_CUDA_OK(cudaEventRecord(e1, stream));
@@ -759,7 +772,7 @@ int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp
             p->launches++;
             for (int l : ells)
                 for (int L = 0; L <= lmax; ++L) {
-                    if (!L_used[L]) continue;
+                    if (!L_used[L] || (mirror && L < l)) continue;
                     const double b = p->a_of_ell[L], ap = AT * 8.0;
                     flops += (sym ? 1.0 : 2.0) * (2.0 * ap * nrp * nrp * b + 2.0 * ap * ap * nrp * b * (b + 1) / 2);
                 }
@@ -819,6 +832,48 @@ std::vector<std::pair<int64_t, int64_t>> cmix_col_chunks(const CmixPlan* p, int 
         if (acc >= total * (made + 1) / k && first[L + 1] > start && made < k - 1) {
             out.emplace_back(start, first[L + 1]);
             start = first[L + 1];
+            ++made;
+        }
+    }
+    if (start < p->nout) out.emplace_back(start, p->nout);
+    return out;
+}
+
+// l-block aligned ranges of rows (== columns: same index set) with roughly equal mirror-mode cost
+// (block (l, L) is only formed for L >= l).  One range when the table does not keep l-blocks contiguous.
+std::vector<std::pair<int64_t, int64_t>> cmix_row_chunks_mirror(const CmixPlan* p, int k) {
+    std::vector<std::pair<int64_t, int64_t>> out;
+    const int lmax = p->lmax;
+    std::vector<int64_t> first(lmax + 2, 0);
+    std::vector<double> cost(lmax + 1, 0.0);
+    bool contiguous = true;
+    int64_t expect = 0;
+    for (int l = 0; l <= lmax; ++l) {
+        first[l] = expect;
+        for (int s = p->ell_ptr[l]; s < p->ell_ptr[l + 1]; ++s)
+            if (p->h_row_out[s] != expect++) contiguous = false;
+        if (p->ell_ptr[l + 1] == p->ell_ptr[l]) continue;
+        const double ap = 8.0 * ((p->a_of_ell[l] + 7) / 8);
+        for (int L = l; L <= lmax; ++L) {
+            const double b = p->a_of_ell[L];
+            cost[l] += 2.0 * ap * p->nrp * p->nrp * b + 2.0 * ap * ap * p->nrp * b * (b + 1) / 2;
+        }
+    }
+    first[lmax + 1] = expect;
+    if (!contiguous || k <= 1) {
+        out.emplace_back(0, p->nout);
+        return out;
+    }
+    double total = 0;
+    for (double c : cost) total += c;
+    double acc = 0;
+    int64_t start = 0;
+    int made = 0;
+    for (int l = 0; l <= lmax; ++l) {
+        acc += cost[l];
+        if (acc >= total * (made + 1) / k && first[l + 1] > start && made < k - 1) {
+            out.emplace_back(start, first[l + 1]);
+            start = first[l + 1];
             ++made;
         }
     }

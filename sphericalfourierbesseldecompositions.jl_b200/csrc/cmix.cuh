@@ -57,11 +57,17 @@ void cmix_plan_destroy(CmixPlan* p);
 // alm layout (device): planar [lm (m-major, lmax2 = 2*lmax)][comp (re,im)][nrp], padded shells zero.
 // Writes the block rows [row_lo,row_hi) x columns [col_lo,col_hi) (0-based, of the nout x nout matrix) into d_M
 // (column-major, leading dim ldM, element (row_lo, col_lo) at offset 0).
+// mirror = true (auto-correlation only): d_M is the base of the FULL matrix; for the l-blocks of the row range only
+// the blocks with L >= l are formed and every tile also fills the mirrored block, using
+//   M[(L,N,N'),(l,n,n')] = c_l (A + [n≠n'] B),  M[(l,n,n'),(L,N,N')] = c_L (A + [N≠N'] B)   (same A, B).
 // `peers` (optional): up to 7 more device pointers (peer-mapped, same offset/ldM semantics as d_M); every element
 // is also stored there, which fuses the all-gather of row shards into the kernel epilogue.
 int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp1, int interchange,
              int64_t row_lo, int64_t row_hi, int64_t col_lo, int64_t col_hi, double* d_M, int64_t ldM,
-             cudaStream_t stream, double* const* peers = nullptr, int npeers = 0, bool reuse_wl = false);
+             cudaStream_t stream, double* const* peers = nullptr, int npeers = 0, bool reuse_wl = false,
+             bool mirror = false);
+// l-block aligned row ranges of roughly equal cost for the mirrored, pipelined host path
+std::vector<std::pair<int64_t, int64_t>> cmix_row_chunks_mirror(const CmixPlan* p, int k);
 // column ranges of roughly equal cost (L-block aligned) for pipelining compute with the D2H of finished slabs
 std::vector<std::pair<int64_t, int64_t>> cmix_col_chunks(const CmixPlan* p, int k);
 

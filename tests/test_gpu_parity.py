@@ -200,13 +200,13 @@ def test_device_pipeline_row_shards():
     ranges = shard_rows(pipe.row_costs, pipe.ell_of_row, 3)
     assert ranges[0][0] == 0 and ranges[-1][1] == pipe.nout
     parts = [pipe.power_win_mix_rows(lo, hi).cpu().numpy().T for lo, hi in ranges]
-    assert np.array_equal(np.concatenate(parts, axis=0), M)
+    assert relerr(np.concatenate(parts, axis=0), M) < 1e-13    # full call uses the mirrored (L >= l) path
     # an arbitrary range that cuts through an l-block
     lo, hi = 7, pipe.nout - 5
-    assert np.array_equal(pipe.power_win_mix_rows(lo, hi).cpu().numpy().T, M[lo:hi])
+    assert relerr(pipe.power_win_mix_rows(lo, hi).cpu().numpy().T, M[lo:hi]) < 1e-13
     cr = shard_rows(pipe.col_costs, pipe.ell_of_row, 3)
     cparts = [pipe.power_win_mix_cols(lo, hi).cpu().numpy().T for lo, hi in cr]     # each (nout, hi-lo)
-    assert np.array_equal(np.concatenate(cparts, axis=1), M)
+    assert relerr(np.concatenate(cparts, axis=1), M) < 1e-13
     wc = pipe.wr_lm_complex().cpu().numpy().T
     assert relerr(wc, sfb.calc_Wr_lm(win, 2 * a.lmax, a.nside)) < 1e-13
     pipe.close()
