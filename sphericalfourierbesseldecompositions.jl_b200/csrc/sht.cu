@@ -768,6 +768,7 @@ template <int NI>
 __global__ void __launch_bounds__(kT) legendre_analysis_kernel(const double* __restrict__ F,
                                                                const double* __restrict__ lam, int nrings, int nhalf,
                                                                int lmax, int nrp, double w, int accumulate,
+                                                               const double* __restrict__ add,
                                                                double* __restrict__ alm) {
     constexpr int BW = ColTile<NI>::BW, LD = ColTile<NI>::LD;
     extern __shared__ double la_smem[];
@@ -836,18 +837,23 @@ __global__ void __launch_bounds__(kT) legendre_analysis_kernel(const double* __r
         const int row = wm * 16 + i * 8 + g;
         const int l = l0 + ((row < 32) ? 2 * row : 2 * (row - 32) + 1);
         if (l > lmax) continue;
-        double* dst = alm + lm_mmajor(lmax, l, m) * ncol + c0;
+        const size_t off = lm_mmajor(lmax, l, m) * ncol + c0;
+        double* dst = alm + off;
 #pragma unroll
         for (int j = 0; j < NI; ++j) {
             const int col = wn * 8 * NI + j * 8 + 2 * t;
             if (c0 + col < ncol) {
-                if (accumulate) {
-                    dst[col] += w * acc[i][j][0];
-                    dst[col + 1] += w * acc[i][j][1];
-                } else {
-                    dst[col] = w * acc[i][j][0];
-                    dst[col + 1] = w * acc[i][j][1];
+                double v0 = w * acc[i][j][0], v1 = w * acc[i][j][1];
+                if (add) {
+                    v0 += add[off + col];
+                    v1 += add[off + col + 1];
                 }
+                if (accumulate) {
+                    v0 += dst[col];
+                    v1 += dst[col + 1];
+                }
+                dst[col] = v0;
+                dst[col + 1] = v1;
             }
         }
     }
@@ -926,6 +932,44 @@ __global__ void __launch_bounds__(kT) legendre_synthesis_kernel(const double* __
                 }
             }
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Ring-space form of the Jacobi refinement.  Re-analysing a synthesised ring needs no pixels: with
+// f_j = Σ_{m'} c_{m'} Re(G_{m'} e^{im'φ_j}) and Σ_j e^{ikφ_j} = nφ e^{ikφ0} [k ≡ 0 mod nφ],
+//   F'_m = Σ_j f_j e^{-imφ_j}
+//        = nφ Σ_{m'≡m} (c_{m'}/2) G_{m'} σ^{(m'-m)/nφ} + nφ Σ_{m'≡-m} (c_{m'}/2) conj(G_{m'}) σ^{(m'+m)/nφ},
+// m' in [0, lmax], congruences mod nφ, σ = -1 on shifted rings (φ0 = π/nφ) and +1 otherwise.  For nφ > 2 lmax this is
+// F'_m = nφ G_m; short polar rings pick up their exact aliases.  So map - S(alm) is never formed in the iterations:
+//   alm <- alm + A f - LegendreAnalysis(F'(LegendreSynthesis(alm))).
+// thread = (ring, m, column c of the re plane); G and F2 are [m][ring][re/im][nrp].
+__global__ void ring_alias_kernel(const double* __restrict__ G, double* __restrict__ F2, const int* __restrict__ nphi_tab,
+                                  const int* __restrict__ shift_tab, int nrings, int lmax, int nrp) {
+    const int ring = blockIdx.x, m = blockIdx.y;
+    const int n = nphi_tab[ring];
+    const double sig = shift_tab[ring] ? -1.0 : 1.0;
+    const size_t stride_m = (size_t)nrings * 2 * nrp;
+    const double* g = G + (size_t)ring * 2 * nrp;
+    double* f = F2 + (size_t)m * stride_m + (size_t)ring * 2 * nrp;
+    for (int c = threadIdx.x; c < nrp; c += blockDim.x) {
+        double re = 0.0, im = 0.0;
+        // m' ≡ m  (mod n)
+        for (int mp = m % n; mp <= lmax; mp += n) {
+            const int tt = (mp - m) / n;  // may be negative
+            const double s = ((tt & 1) ? sig : 1.0) * ((mp == 0) ? 0.5 : 1.0);
+            re += s * g[(size_t)mp * stride_m + c];
+            im += s * g[(size_t)mp * stride_m + nrp + c];
+        }
+        // m' ≡ -m (mod n)
+        for (int mp = (n - m % n) % n; mp <= lmax; mp += n) {
+            const int tt = (mp + m) / n;
+            const double s = ((tt & 1) ? sig : 1.0) * ((mp == 0) ? 0.5 : 1.0);
+            re += s * g[(size_t)mp * stride_m + c];
+            im -= s * g[(size_t)mp * stride_m + nrp + c];
+        }
+        f[c] = n * re;
+        f[nrp + c] = n * im;
     }
 }
 
@@ -1050,7 +1094,6 @@ int sht_plan_create(ShtPlan** out, int64_t nside_in, int64_t nside_out, int64_t 
     rc = rc ? rc : p->d_tw.alloc((size_t)4 * ns * (ns + 1));
     rc = rc ? rc : p->d_lam.alloc(p->lmsize * p->nhalf);
     rc = rc ? rc : p->d_FG.alloc((size_t)(lmax + 1) * p->nrings * 2 * p->nrp);
-    rc = rc ? rc : p->d_resid.alloc((size_t)p->npix * p->nrp);
     if (!rc && nside_in != nside_out) rc = p->d_map.alloc((size_t)p->npix * p->nrp);
     if (rc) {
         delete p;
@@ -1071,9 +1114,10 @@ int sht_plan_create(ShtPlan** out, int64_t nside_in, int64_t nside_out, int64_t 
 
 void sht_plan_destroy(ShtPlan* p) { delete p; }
 
-static int run_analysis(ShtPlan* p, const double* map, int64_t ldw, int accumulate, double* d_alm, cudaStream_t st) {
-    RingTabs rt{p->d_nphi.p, p->d_start.p, p->d_shift.p, p->d_twoff.p, p->d_tw.p};
+// map -> ring-Fourier coefficients F (d_FG)
+static int run_ring_analysis(ShtPlan* p, const double* map, int64_t ldw, cudaStream_t st) {
     const int lmax = p->lmax, nrp = p->nrp;
+    RingTabs rt{p->d_nphi.p, p->d_start.p, p->d_shift.p, p->d_twoff.p, p->d_tw.p};
     if (p->n_gemm_rings > 0) {
         dim3 g1(p->n_gemm_rings, (unsigned)ceil_div(lmax + 1, 32), (unsigned)ceil_div(nrp, 64));
         ring_analysis_kernel<<<g1, kT, 0, st>>>(map, ldw, p->nr, nrp, rt, p->d_gemm_rings.p, p->nrings, lmax, p->d_FG.p);
@@ -1102,16 +1146,22 @@ static int run_analysis(ShtPlan* p, const double* map, int64_t ldw, int accumula
         SFB_CUDA_OK(cudaGetLastError());
         p->launches++;
     }
+    return 0;
+}
+
+// F (ring-Fourier coefficients, in `Fsrc`) -> alm:  alm = [accumulate ? alm : 0] + [add ? add : 0] + w Λ F
+static int run_legendre_analysis(ShtPlan* p, const double* Fsrc, double w, int accumulate, const double* add,
+                                 double* d_alm, cudaStream_t st) {
+    const int lmax = p->lmax, nrp = p->nrp;
     const int nil = pick_ni(2 * nrp);
     dim3 g2((unsigned)ceil_div(lmax + 1, 64), (unsigned)ceil_div(2 * nrp, 16 * nil), lmax + 1);
-    const double w = 4.0 * 3.14159265358979323846 / (double)p->npix;
     const int la_smem_bytes = (64 * kLdA + 2 * 32 * (16 * nil + 4)) * (int)sizeof(double);
 #define SFB_LAUNCH_LA(NI_)                                                                                            \
     do {                                                                                                              \
         SFB_CUDA_OK(cudaFuncSetAttribute(legendre_analysis_kernel<NI_>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                          la_smem_bytes));                                                             \
-        legendre_analysis_kernel<NI_><<<g2, kT, la_smem_bytes, st>>>(p->d_FG.p, p->d_lam.p, p->nrings, p->nhalf, lmax, \
-                                                                     nrp, w, accumulate, d_alm);                      \
+        legendre_analysis_kernel<NI_><<<g2, kT, la_smem_bytes, st>>>(Fsrc, p->d_lam.p, p->nrings, p->nhalf, lmax, nrp, \
+                                                                     w, accumulate, add, d_alm);                     \
     } while (0)
     if (nil == 4)
         SFB_LAUNCH_LA(4);
@@ -1123,6 +1173,12 @@ static int run_analysis(ShtPlan* p, const double* map, int64_t ldw, int accumula
     SFB_CUDA_OK(cudaGetLastError());
     p->launches += 1;
     return 0;
+}
+
+static int run_analysis(ShtPlan* p, const double* map, int64_t ldw, int accumulate, double* d_alm, cudaStream_t st) {
+    SFB_TRY(run_ring_analysis(p, map, ldw, st));
+    return run_legendre_analysis(p, p->d_FG.p, 4.0 * 3.14159265358979323846 / (double)p->npix, accumulate, nullptr, d_alm,
+                                 st);
 }
 
 int sht_map2alm(ShtPlan* p, const double* d_win, int64_t ldw, int niter, double* d_alm, cudaStream_t st) {
@@ -1144,8 +1200,9 @@ int sht_map2alm(ShtPlan* p, const double* d_win, int64_t ldw, int niter, double*
         ldm = p->nrp;
     }
     RingTabs rt{p->d_nphi.p, p->d_start.p, p->d_shift.p, p->d_twoff.p, p->d_tw.p};
-    SFB_TRY(run_analysis(p, map, ldm, 0, d_alm, st));
-    for (int it = 0; it < niter; ++it) {
+    const double w = 4.0 * 3.14159265358979323846 / (double)p->npix;
+    const bool pixel_iter = getenv("SFB_SHT_PIXEL_ITER") != nullptr;  // cross-check: refine through pixel space
+    auto legendre_synthesis = [&]() -> int {
         const int nil = pick_ni(2 * p->nrp);
         dim3 gs(p->lmax + 1, (unsigned)ceil_div(p->nhalf, 64), (unsigned)ceil_div(2 * p->nrp, 16 * nil));
         if (nil == 4)
@@ -1156,6 +1213,29 @@ int sht_map2alm(ShtPlan* p, const double* d_win, int64_t ldw, int niter, double*
             legendre_synthesis_kernel<1><<<gs, kT, 0, st>>>(d_alm, p->d_lam.p, p->nrings, p->nhalf, p->lmax, p->nrp, p->d_FG.p);
         SFB_CUDA_OK(cudaGetLastError());
         p->launches += 1;
+        return 0;
+    };
+    if (niter > 0 && !pixel_iter) {
+        // alm <- alm + A f - Λ F'(Λᵀ alm): the refinement never leaves ring-Fourier space (ring_alias_kernel)
+        const size_t nalm = p->lmsize * 2 * p->nrp;
+        SFB_TRY(p->d_F2.alloc((size_t)(p->lmax + 1) * p->nrings * 2 * p->nrp));
+        SFB_TRY(p->d_a0.alloc(nalm));
+        SFB_TRY(run_ring_analysis(p, map, ldm, st));
+        SFB_TRY(run_legendre_analysis(p, p->d_FG.p, w, 0, nullptr, p->d_a0.p, st));
+        SFB_CUDA_OK(cudaMemcpyAsync(d_alm, p->d_a0.p, nalm * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        for (int it = 0; it < niter; ++it) {
+            SFB_TRY(legendre_synthesis());
+            ring_alias_kernel<<<dim3(p->nrings, p->lmax + 1), 64, 0, st>>>(p->d_FG.p, p->d_F2.p, p->d_nphi.p, p->d_shift.p,
+                                                                          p->nrings, p->lmax, p->nrp);
+            SFB_CUDA_OK(cudaGetLastError());
+            p->launches++;
+            SFB_TRY(run_legendre_analysis(p, p->d_F2.p, -w, 1, p->d_a0.p, d_alm, st));
+        }
+    } else {
+    SFB_TRY(run_analysis(p, map, ldm, 0, d_alm, st));
+    if (niter > 0) SFB_TRY(p->d_resid.alloc((size_t)p->npix * p->nrp));
+    for (int it = 0; it < niter; ++it) {
+        SFB_TRY(legendre_synthesis());
         if (p->ntiles > 0) {
             dim3 gr(p->ntiles, (unsigned)ceil_div(p->nrp, 64));
             ring_synthesis_kernel<<<gr, kT, 0, st>>>(p->d_FG.p, rt, p->d_tile_ring.p, p->d_tile_j0.p, p->nrings,
@@ -1197,6 +1277,7 @@ int sht_map2alm(ShtPlan* p, const double* d_win, int64_t ldw, int niter, double*
             p->launches++;
         }
         SFB_TRY(run_analysis(p, p->d_resid.p, p->nrp, 1, d_alm, st));
+    }
     }
     SFB_CUDA_OK(cudaEventRecord(e1, st));
     SFB_CUDA_OK(cudaEventSynchronize(e1));

@@ -29,7 +29,9 @@ struct ShtPlan {
     DevBuf<double> d_lam;    // λ_lm(θ_k): [lm (m-major)][nhalf]
     DevBuf<double> d_FG;     // ring-space intermediates [m][ring][2*nrp]
     DevBuf<double> d_map;    // udgraded maps [npix][nrp] (only if nside_in != nside)
-    DevBuf<double> d_resid;  // residual maps [npix][nrp]
+    DevBuf<double> d_resid;  // residual maps [npix][nrp] (pixel-space refinement only)
+    DevBuf<double> d_F2;     // aliased ring-Fourier coefficients of the synthesised field (ring-space refinement)
+    DevBuf<double> d_a0;     // A f, the first-pass alm
 
     float t_total = 0;
     int launches = 0;
