@@ -122,21 +122,50 @@ __global__ void __launch_bounds__(256) what_build_kernel(const double* __restric
     __syncthreads();
     if (L1hi < 0) return;
     const int n2 = nrp * nrp;
-    for (int e = threadIdx.x; e < n2; e += blockDim.x) {
-        double acc[kWhatGroup];
+    // two elements per thread and four L1 terms per iteration: 8 independent L2 loads in flight per thread
+    for (int e = threadIdx.x; e < n2; e += 2 * blockDim.x) {
+        const int e2 = e + blockDim.x;
+        const bool has2 = e2 < n2;
+        double acc[kWhatGroup], acc2[kWhatGroup];
 #pragma unroll
-        for (int q = 0; q < kWhatGroup; ++q) acc[q] = 0.0;
-#pragma unroll 2
-        for (int L1 = L1lo; L1 <= L1hi; L1 += 2) {
+        for (int q = 0; q < kWhatGroup; ++q) acc[q] = acc2[q] = 0.0;
+        int L1 = L1lo;
+        for (; L1 + 6 <= L1hi; L1 += 8) {
+            double x[4], y[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                x[u] = __ldg(W + (size_t)(L1 + 2 * u) * n2 + e);
+                y[u] = has2 ? __ldg(W + (size_t)(L1 + 2 * u) * n2 + e2) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int h = (L1 + 2 * u - par) >> 1;
+#pragma unroll
+                for (int q = 0; q < kWhatGroup; ++q) {
+                    const double wv = wsm[q * KW + h];
+                    acc[q] = fma(wv, x[u], acc[q]);
+                    acc2[q] = fma(wv, y[u], acc2[q]);
+                }
+            }
+        }
+        for (; L1 <= L1hi; L1 += 2) {
             const double x = __ldg(W + (size_t)L1 * n2 + e);
+            const double y = has2 ? __ldg(W + (size_t)L1 * n2 + e2) : 0.0;
             const int h = (L1 - par) >> 1;
 #pragma unroll
-            for (int q = 0; q < kWhatGroup; ++q) acc[q] = fma(wsm[q * KW + h], x, acc[q]);
+            for (int q = 0; q < kWhatGroup; ++q) {
+                acc[q] = fma(wsm[q * KW + h], x, acc[q]);
+                acc2[q] = fma(wsm[q * KW + h], y, acc2[q]);
+            }
         }
 #pragma unroll
         for (int q = 0; q < kWhatGroup; ++q) {
             const int L = base + 2 * q;
-            if (L <= lmax) What[((size_t)(ell - ell0) * (lmax + 1) + L) * n2 + e] = acc[q];
+            if (L <= lmax) {
+                double* dst = What + ((size_t)(ell - ell0) * (lmax + 1) + L) * n2;
+                dst[e] = acc[q];
+                if (has2) dst[e2] = acc2[q];
+            }
         }
     }
 }
