@@ -282,7 +282,7 @@ def run_b200(args):
         full = step()
     barrier()
     tim = _lib.timings()
-    stage_ms = {"stage1": [], "wl": [], "what": [], "block": [], "stage1_incl_gather": [], "stage23_incl_exchange": []}
+    stage_ms = {"stage1": [], "wl": [], "what": [], "block": [], "fill": [], "stage1_incl_gather": [], "stage23_incl_exchange": []}
     launches_per_step = 0
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -297,6 +297,7 @@ def run_b200(args):
         stage_ms["wl"].append(tim["wl_ms"])
         stage_ms["what"].append(tim["what_ms"])
         stage_ms["block"].append(tim["block_ms"])
+        stage_ms["fill"].append(tim["fill_ms"])
         torch.cuda.synchronize()
         stage_ms["stage1_incl_gather"].append(evs[0].elapsed_time(evs[1]))
         stage_ms["stage23_incl_exchange"].append(evs[1].elapsed_time(evs[2]))

@@ -89,5 +89,5 @@ def timings():
     import numpy as np
     out = np.zeros(8)
     check(load().sfb_get_timings(ptr(out), 8))
-    keys = ["stage1_ms", "wl_ms", "w3j_ms", "what_ms", "block_ms", "block_flops", "launches", "binned_ms"]
+    keys = ["stage1_ms", "wl_ms", "fill_ms", "what_ms", "block_ms", "block_flops", "launches", "binned_ms"]
     return dict(zip(keys, out.tolist()))

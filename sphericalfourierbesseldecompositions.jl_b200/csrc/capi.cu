@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(256) dmma_probe_kernel(double* out, int iters,
 
 static void record_cmix_times(const CmixPlan* p) {
     g_times[1] = p->t_wl;
-    g_times[2] = p->t_w3j;
+    g_times[2] = p->t_fill;
     g_times[3] = p->t_what;
     g_times[4] = p->t_block;
     g_times[5] = p->flops_executed;

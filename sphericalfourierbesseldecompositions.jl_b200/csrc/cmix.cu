@@ -566,6 +566,13 @@ int cmix_plan_create(CmixPlan** out, const int64_t* lnn, int64_t lnnsize, int64_
         p->h_row_n2[slot] = n2;
         pairidx[((size_t)l * nmax + n1) * nmax + n2] = (int)(i - (lnn_min - 1));
     }
+    // per output index: l | [n≠n'] << 30 (mirror fill), and whether l is non-decreasing in output order
+    std::vector<int> es((size_t)p->nout, 0);
+    p->ell_sorted = true;
+    for (int64_t i = lnn_min - 1; i < lnnsize; ++i) {
+        es[i - (lnn_min - 1)] = (int)lnn[3 * i] | ((lnn[3 * i + 1] != lnn[3 * i + 2]) ? (1 << 30) : 0);
+        if (i > lnn_min - 1 && lnn[3 * i] < lnn[3 * (i - 1)]) p->ell_sorted = false;
+    }
     std::vector<int> nl_L, nl_N;
     int amax = 0;
     for (int L = 0; L <= lmax; ++L) {
@@ -615,6 +622,7 @@ int cmix_plan_create(CmixPlan** out, const int64_t* lnn, int64_t lnnsize, int64_
     rc = rc ? rc : up(p->d_pairidx, pairidx);
     rc = rc ? rc : up(p->d_nl_L, nl_L);
     rc = rc ? rc : up(p->d_nl_N, nl_N);
+    rc = rc ? rc : up(p->d_es, es);
     rc = rc ? rc : p->d_row_out.alloc(nrows);
     rc = rc ? rc : p->d_ell_list.alloc(lmax + 1);
     rc = rc ? rc : p->d_w2.alloc((size_t)(lmax + 1) * (lmax + 1) * (lmax + 1));
@@ -659,6 +667,9 @@ int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp
                     "cmix_run: mirror mode needs the auto-correlation path and the full matrix");
     }
     const int lmax = p->lmax, nrp = p->nrp;
+    // register-Z kernel (cmix_regz.cu) for the auto-correlation path with nr <= 64; in mirror mode it forms the L >= l
+    // blocks only and cmix_mirror_fill writes the blocks below the block diagonal afterwards
+    const bool regz = cmix_regz_eligible(p, sym, npeers);
     cudaEvent_t ev[4];
     for (auto& e : ev) SFB_CUDA_OK(cudaEventCreate(&e));
 
@@ -757,7 +768,19 @@ int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp
         SFB_CUDA_OK(cudaEventRecord(e1, stream));
         args.ell0 = ell0;
         chunk_fill = 0;  // the previous l-chunk's kernels have completed (event sync below)
-        for (int AT = p->amax_tiles; AT >= 1; --AT) {
+        if (regz) {
+            std::vector<int> blocks;
+            for (int l : wells)
+                for (int L = mirror ? l : 0; L <= lmax; ++L) {
+                    if (!L_used[L] || p->a_of_ell[L] == 0) continue;
+                    const int desc[8] = {l, L, p->a_of_ell[l], p->a_of_ell[L], p->ell_ptr[l],
+                                         p->ell_ptr[l + 1] - p->ell_ptr[l], (l - ell0) * (lmax + 1) + L, 0};
+                    blocks.insert(blocks.end(), desc, desc + 8);
+                }
+            SFB_TRY(cmix_regz_run(p, blocks, p->d_What.p, div2Lp1, interchange, col_lo, col_hi, d_M, ldM, stream, &flops,
+                                  &p->launches));
+        }
+        for (int AT = regz ? 0 : p->amax_tiles; AT >= 1; --AT) {
             std::vector<int> ells;
             for (int l = ell0; l < ell1; ++l)
                 if (ell_used[l] && p->a_of_ell[l] > 0 && (p->a_of_ell[l] + 7) / 8 == AT) ells.push_back(l);
@@ -817,7 +840,18 @@ int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp
         cudaEventDestroy(e1);
         cudaEventDestroy(e2);
     }
+    p->t_fill = 0;
+    if (regz && mirror) {
+        SFB_CUDA_OK(cudaEventRecord(ev[2], stream));
+        SFB_TRY(cmix_mirror_fill(p, row_lo, row_hi, div2Lp1, interchange, d_M, ldM, stream));
+        p->launches++;
+        SFB_CUDA_OK(cudaEventRecord(ev[3], stream));
+    }
     SFB_CUDA_OK(cudaStreamSynchronize(stream));
+    if (regz && mirror) {
+        cudaEventElapsedTime(&p->t_fill, ev[2], ev[3]);
+        t_block += p->t_fill;
+    }
     cudaEventElapsedTime(&p->t_wl, ev[0], ev[1]);
     p->t_what = t_what;
     p->t_block = t_block;

@@ -39,10 +39,13 @@ struct CmixPlan {
     DevBuf<int> d_ell_list;           // per-launch list of ells
     DevBuf<int> d_chunks;             // per-launch (L, N0, N1) chunk lists
     DevBuf<int> d_what_ells;          // l-blocks whose Ŵ is built for the current row shard
+    DevBuf<int> d_es;                 // per output index: l | [n≠n'] << 30 (mirror fill)
+    bool ell_sorted = false;          // l non-decreasing in output order
+    DevBuf<int> d_regz_blocks;        // per-launch block descriptors of the register-Z kernel (cmix_regz.cu)
     size_t what_budget_bytes = size_t(2) << 30;
 
     // last-run stage times (ms): wl, w3j, what, block
-    float t_wl = 0, t_w3j = 0, t_what = 0, t_block = 0;
+    float t_wl = 0, t_fill = 0, t_what = 0, t_block = 0;  // t_block includes t_fill
     double flops_executed = 0;
     int launches = 0;
 };
@@ -66,6 +69,13 @@ int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp
              int64_t row_lo, int64_t row_hi, int64_t col_lo, int64_t col_hi, double* d_M, int64_t ldM,
              cudaStream_t stream, double* const* peers = nullptr, int npeers = 0, bool reuse_wl = false,
              bool mirror = false);
+// Register-resident-Z block kernel (cmix_regz.cu): auto-correlation, nr <= 64, no peer stores.
+bool cmix_regz_eligible(const CmixPlan* p, bool sym, int npeers);
+int cmix_regz_run(CmixPlan* p, const std::vector<int>& blocks, const double* d_What, int div2Lp1, int interchange,
+                  int64_t col_lo, int64_t col_hi, double* d_M, int64_t ldM, cudaStream_t stream, double* flops,
+                  int* launches);
+int cmix_mirror_fill(CmixPlan* p, int64_t c0, int64_t c1, int div2Lp1, int interchange, double* d_M, int64_t ldM,
+                     cudaStream_t stream);
 // l-block aligned row ranges of roughly equal cost for the mirrored, pipelined host path
 std::vector<std::pair<int64_t, int64_t>> cmix_row_chunks_mirror(const CmixPlan* p, int k);
 // column ranges of roughly equal cost (L-block aligned) for pipelining compute with the D2H of finished slabs

@@ -1,0 +1,410 @@
+// Coupling-matrix block kernel, register-resident Z variant (auto-correlation, nr <= 64).
+//
+// Replaces calc_cmixlnnLNN! + calc_cmix (reference src/windows.jl:613-627, 700-746) for one (l, L) block per CTA:
+//   Z_N[n][r']      = Σ_r  G_ln[r] G_LN[r] Ŵ_lL[r][r']                (DMMA; accumulators STAY in registers)
+//   T_NN'[n][n']    = Σ_r' Z_N[n][r'] G_LN'[r'] G_ln'[r']   N' >= N   (DMMA; Z_N is the A operand straight from
+//                                                                      the accumulator registers)
+//   M[(l,n,n'),(L,N,N')] = c_L (T[n][n'] + [N≠N'] T[n'][n])            (src/windows.jl:727-736)
+// In mirror mode only the blocks with L >= l are formed; cmix_mirror_fill_kernel then fills the blocks below the
+// block diagonal from M[i',i] = M[i,i'] f_i / f_i', f = c_l (1 + [n≠n'])  (the un-symmetrised kernel is
+// symmetric).  Storing the mirror image from the tile itself (one 8-byte store per 32-byte sector) made the kernel
+// store-bound: 5.2 ms against 3.0 ms + 0.x ms for the separate coalesced pass (cfg4, tools/ablate_regz.sh).
+//
+// Chaining the two GEMMs through registers works because the contraction index of an m8n8k4 DMMA can be permuted
+// freely as long as A and B agree: the C fragment of lane (g,t) holds columns r' = 8jt+2t+{0,1}, so the T phase
+// contracts "k-step (jt,e)" over r' = 8jt+2t+e and reads its B fragments (G_ln'[r']) at the same permuted index.
+// The same permutation is used for the r contraction of the Z phase, which makes every operand a 16-byte
+// shared-memory load (row stride ≡ 8 mod 16 doubles: conflict free) feeding two k-steps.
+//
+// A warp owns one N at a time (grabbed from a shared-memory counter, heaviest first), so after the block's operands
+// are staged (cp.async) there is no CTA-wide synchronisation: each warp runs Z -> tiles -> epilogue on its own.
+#include "cmix.cuh"
+
+#include <algorithm>
+#include <cstdlib>
+
+namespace sfb {
+
+struct RegzArgs {
+    const double* G;       // [ell][nmax][nrp]
+    const double* What;    // [what_index][nrp][nrp]
+    const int* blocks;     // 8 ints per block: rowell, colell, a, b, r0, nrows, what_index, unused
+    const int* row_out;    // output row per CSR slot (absolute in mirror mode, relative to the shard otherwise) or -1
+    const int* row_n;
+    const int* row_n2;
+    const int* pairidx;    // [L][nmax][nmax] -> output column or -1
+    double* M;
+    long long ldM;
+    int nmax, nrp;
+    int col_lo, col_hi;
+    int div2Lp1, interchange;
+    int dbg;
+};
+
+constexpr int kRegzU = 8;              // rows per lane per epilogue iteration
+constexpr int kRegzNoRow = 0x3FFFFF;   // packed row-table marker: row not in the shard
+
+__host__ __device__ constexpr int regz_tld(int AP) { return (AP % 16 == 8) ? AP : AP + 8; }  // ≡ 8 (mod 16)
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+template <int AT, int NT, int NW, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB) cmix_regz_kernel(RegzArgs p) {
+    extern __shared__ __align__(16) double sm[];
+    constexpr int AP = AT * 8;
+    constexpr int K = NT * 8;          // padded radial length
+    constexpr int S = K + 8;           // row stride ≡ 8 (mod 16): conflict-free 16-byte fragment loads
+    constexpr int TLD = regz_tld(AP);
+    constexpr int NTHR = NW * 32;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+
+    const int4 d0 = reinterpret_cast<const int4*>(p.blocks)[2 * blockIdx.x];
+    const int4 d1 = reinterpret_cast<const int4*>(p.blocks)[2 * blockIdx.x + 1];
+    const int rowell = d0.x, colell = d0.y, a = d0.z, b = d0.w;
+    const int r0 = d1.x, nrows = d1.y, widx = d1.z;
+    const int nrp = p.nrp, nmax = p.nmax;
+
+    double* Gl = sm;                       // [AP][S]   G_ln[r], rows >= a zero
+    double* GL = Gl + AP * S;              // [nmax][S] G_LN[r]
+    double* Ws = GL + nmax * S;            // [K][S]    Ŵ_lL (symmetric)
+    double* Ts = Ws + K * S;               // [NW][AP][TLD]
+    int* rowtab = reinterpret_cast<int*>(Ts + NW * AP * TLD);  // [nrows] orow | n << 22 | n' << 27
+    int* counter = rowtab + nrows;
+
+    // ---- stage operands: one round of 16-byte async copies, zero fill of the padding --------------------------
+    const int cpr = nrp / 2;  // 16-byte chunks per row
+    {
+        const double* src = p.G + (size_t)rowell * nmax * nrp;
+        for (int x = tid; x < a * cpr; x += NTHR) {
+            const int n = x / cpr, c = x - n * cpr;
+            cp_async16(Gl + n * S + 2 * c, src + (size_t)n * nrp + 2 * c);
+        }
+        src = p.G + (size_t)colell * nmax * nrp;
+        for (int x = tid; x < b * cpr; x += NTHR) {
+            const int n = x / cpr, c = x - n * cpr;
+            cp_async16(GL + n * S + 2 * c, src + (size_t)n * nrp + 2 * c);
+        }
+        src = p.What + (size_t)widx * nrp * nrp;
+        for (int x = tid; x < nrp * cpr; x += NTHR) {
+            const int r = x / cpr, c = x - r * cpr;
+            cp_async16(Ws + r * S + 2 * c, src + (size_t)r * nrp + 2 * c);
+        }
+    }
+    for (int x = tid; x < (AP - a) * K; x += NTHR) {
+        const int n = a + x / K, c = x % K;
+        Gl[n * S + c] = 0.0;
+    }
+    if (nrp < K) {
+        const int padc = K - nrp;
+        for (int x = tid; x < a * padc; x += NTHR) Gl[(x / padc) * S + nrp + x % padc] = 0.0;
+        for (int x = tid; x < b * padc; x += NTHR) GL[(x / padc) * S + nrp + x % padc] = 0.0;
+        for (int x = tid; x < nrp * padc; x += NTHR) Ws[(x / padc) * S + nrp + x % padc] = 0.0;
+        for (int x = tid; x < padc * K; x += NTHR) Ws[(nrp + x / K) * S + x % K] = 0.0;
+    }
+    for (int x = tid; x < nrows; x += NTHR) {
+        const int o = p.row_out[r0 + x];
+        rowtab[x] = (o < 0 ? kRegzNoRow : o) | (p.row_n[r0 + x] << 22) | (p.row_n2[r0 + x] << 27);
+    }
+    if (tid == 0) *counter = 0;
+    cp_async_wait_all();
+    __syncthreads();
+
+    const double inv4pi = 0.07957747154594767;
+    const double scale = (p.div2Lp1 ? 1.0 : (2.0 * colell + 1.0)) * inv4pi;
+    double* Tw = Ts + warp * AP * TLD;
+
+    for (;;) {
+        int N = 0;
+        if (lane == 0) N = atomicAdd(counter, 1);
+        N = __shfl_sync(0xffffffffu, N, 0);
+        if (N >= b) break;
+        // output columns of (N, N') for N' = N + lane
+        int mycol = -1;
+        if (lane < b - N) {
+            const int c = __ldg(p.pairidx + ((size_t)colell * nmax + N) * nmax + N + lane);
+            mycol = (c >= p.col_lo && c < p.col_hi) ? c - p.col_lo : -1;
+        }
+        if (__ballot_sync(0xffffffffu, mycol >= 0) == 0u) continue;
+
+        // ---- Z phase: Z[i][jt][e] = Z_N[8i+g][8jt+2t+e] ------------------------------------------------------
+        double Z[AT][NT][2];
+#pragma unroll
+        for (int i = 0; i < AT; ++i)
+#pragma unroll
+            for (int jt = 0; jt < NT; ++jt) Z[i][jt][0] = Z[i][jt][1] = 0.0;
+        if (!(p.dbg & 2)) {
+            const double* glN = GL + N * S + 2 * t;
+            const double* glA = Gl + g * S + 2 * t;
+            const double* wsB = Ws + g * S + 2 * t;
+#pragma unroll 2
+            for (int kt = 0; kt < NT; ++kt) {
+                const double2 sN = *reinterpret_cast<const double2*>(glN + 8 * kt);
+                double av0[AT], av1[AT];
+#pragma unroll
+                for (int i = 0; i < AT; ++i) {
+                    const double2 x = *reinterpret_cast<const double2*>(glA + i * 8 * S + 8 * kt);
+                    av0[i] = x.x * sN.x;
+                    av1[i] = x.y * sN.y;
+                }
+#pragma unroll
+                for (int jt = 0; jt < NT; ++jt) {
+                    const double2 w = *reinterpret_cast<const double2*>(wsB + jt * 8 * S + 8 * kt);
+#pragma unroll
+                    for (int i = 0; i < AT; ++i) {
+                        dmma884(Z[i][jt], av0[i], w.x);
+                        dmma884(Z[i][jt], av1[i], w.y);
+                    }
+                }
+            }
+        }
+
+        // ---- T phase over N' >= N -------------------------------------------------------------------------
+        for (int N2 = N; N2 < b; ++N2) {
+            const int col = __shfl_sync(0xffffffffu, mycol, N2 - N);
+            if (col < 0) continue;  // warp-uniform
+            double acc[AT][AT][2];
+#pragma unroll
+            for (int i = 0; i < AT; ++i)
+#pragma unroll
+                for (int j = 0; j < AT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+            const double* glS = GL + N2 * S + 2 * t;
+            const double* glB = Gl + g * S + 2 * t;
+            if (!(p.dbg & 4)) {
+#pragma unroll
+                for (int jt = 0; jt < NT; ++jt) {
+                    const double2 s2 = *reinterpret_cast<const double2*>(glS + 8 * jt);
+                    double2 gv[AT];
+#pragma unroll
+                    for (int j = 0; j < AT; ++j) gv[j] = *reinterpret_cast<const double2*>(glB + j * 8 * S + 8 * jt);
+#pragma unroll
+                    for (int i = 0; i < AT; ++i) {
+                        const double a0 = Z[i][jt][0] * s2.x, a1 = Z[i][jt][1] * s2.y;
+#pragma unroll
+                        for (int j = 0; j < AT; ++j) {
+                            dmma884(acc[i][j], a0, gv[j].x);
+                            dmma884(acc[i][j], a1, gv[j].y);
+                        }
+                    }
+                }
+            }
+            if (p.dbg & 1) continue;
+            // ---- epilogue: tile -> per-warp shared staging -> rows of this l-block ----------------------------
+#pragma unroll
+            for (int i = 0; i < AT; ++i)
+#pragma unroll
+                for (int j = 0; j < AT; ++j)
+                    *reinterpret_cast<double2*>(Tw + (i * 8 + g) * TLD + j * 8 + 2 * t) =
+                        make_double2(acc[i][j][0], acc[i][j][1]);
+            __syncwarp();
+            const size_t coff = (size_t)col * p.ldM;
+            const bool offdiag = (N2 != N);
+            // eight rows per lane per iteration: all table and tile loads of an iteration are independent
+            for (int idx0 = lane; idx0 < nrows; idx0 += 32 * kRegzU) {
+                int pk[kRegzU];
+#pragma unroll
+                for (int u = 0; u < kRegzU; ++u) {
+                    const int idx = idx0 + 32 * u;
+                    pk[u] = (idx < nrows) ? rowtab[idx] : kRegzNoRow;
+                }
+                double v[kRegzU];
+#pragma unroll
+                for (int u = 0; u < kRegzU; ++u) {
+                    const int n = (pk[u] >> 22) & 31, n2 = (pk[u] >> 27) & 31;
+                    const double A = Tw[n * TLD + n2], B = Tw[n2 * TLD + n];
+                    v[u] = p.interchange ? B : (offdiag ? A + B : A);
+                }
+#pragma unroll
+                for (int u = 0; u < kRegzU; ++u) {
+                    const int orow = pk[u] & kRegzNoRow;
+                    if (orow != kRegzNoRow) p.M[coff + orow] = v[u] * scale;
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+
+// =============================================================================================
+// Mirror fill: for the output columns c in [c0, c1) (an l-aligned range) write every element below the block diagonal,
+//   M[r, c] = M[c, r] · f_c / f_r   for l(r) > l(c),   f = (div2Lp1 ? 1 : 2l+1) · (interchange ? 1 : 1 + [n≠n']),
+// from the directly formed element M[c, r] (block (l(c), l(r)), L >= l).  64 x 64 tiles through shared memory: both
+// the read (along the source column) and the write (along the destination column) are coalesced.
+// es[o] = l | [n≠n'] << 30 per output index.  `sorted` = l is non-decreasing in output order, so tiles entirely
+// above the diagonal can be skipped without looking at the table.
+constexpr int kFillT = 64;  // tile edge: 16 independent 8-byte loads in flight per thread
+
+__global__ void __launch_bounds__(256) cmix_mirror_fill_kernel(double* __restrict__ M, long long ld, int n, int c0,
+                                                               int c1, int rbase, const int* __restrict__ es,
+                                                               int div2Lp1, int interchange, int sorted) {
+    __shared__ double tile[kFillT][kFillT + 1];
+    __shared__ int esr[kFillT], esc[kFillT];
+    const int cb = c0 + blockIdx.x * kFillT, rb = rbase + blockIdx.y * kFillT;
+    if (sorted && rb + kFillT - 1 <= cb) return;
+    const int x = threadIdx.x & 31, y0 = threadIdx.x >> 5;
+    if (threadIdx.x < kFillT) esr[threadIdx.x] = (rb + threadIdx.x < n) ? es[rb + threadIdx.x] : -1;
+    else if (threadIdx.x < 2 * kFillT)
+        esc[threadIdx.x - kFillT] = (cb + threadIdx.x - kFillT < c1) ? es[cb + threadIdx.x - kFillT] : -1;
+    __syncthreads();
+    // whole tile strictly above / on the block diagonal: nothing to fill
+    int lrmax = -1, lcmin = 1 << 30;
+    if (sorted) {
+        lrmax = esr[kFillT - 1] >= 0 ? (esr[kFillT - 1] & 0x3fffffff) : (1 << 29);
+        lcmin = esc[0] & 0x3fffffff;
+        if (lrmax <= lcmin) return;
+    }
+    // source element (row cb+xx, column rb+y) -> tile[y][xx]
+    bool any = false;
+#pragma unroll
+    for (int kx = 0; kx < kFillT / 32; ++kx) {
+        const int xx = x + 32 * kx;
+        const int ec = esc[xx];
+#pragma unroll
+        for (int k = 0; k < kFillT / 8; ++k) {
+            const int y = y0 + 8 * k;
+            const int er = esr[y];
+            const bool need = (ec >= 0 && er >= 0 && (er & 0x3fffffff) > (ec & 0x3fffffff));
+            if (need) tile[y][xx] = M[(size_t)(rb + y) * ld + cb + xx];
+            any = any || need;
+        }
+    }
+    if (!__syncthreads_or(any)) return;
+    // destination element (row rb+xx, column cb+y) = tile[xx][y]
+#pragma unroll
+    for (int kx = 0; kx < kFillT / 32; ++kx) {
+        const int xx = x + 32 * kx;
+        const int er = esr[xx];
+        if (er < 0) continue;
+        const int lr = er & 0x3fffffff;
+        const double fr = (div2Lp1 ? 1.0 : 2.0 * lr + 1.0) * ((!interchange && (er >> 30)) ? 2.0 : 1.0);
+        const double ifr = 1.0 / fr;
+#pragma unroll
+        for (int k = 0; k < kFillT / 8; ++k) {
+            const int y = y0 + 8 * k;
+            const int e2 = esc[y];
+            if (e2 < 0) continue;
+            const int lc = e2 & 0x3fffffff;
+            if (lr <= lc) continue;
+            const double fc = (div2Lp1 ? 1.0 : 2.0 * lc + 1.0) * ((!interchange && (e2 >> 30)) ? 2.0 : 1.0);
+            M[(size_t)(cb + y) * ld + rb + xx] = tile[xx][y] * (fc * ifr);
+        }
+    }
+}
+
+int cmix_mirror_fill(CmixPlan* p, int64_t c0, int64_t c1, int div2Lp1, int interchange, double* d_M, int64_t ldM,
+                     cudaStream_t stream) {
+    if (c1 <= c0) return 0;
+    const int n = (int)p->nout;
+    const int rbase = p->ell_sorted ? (int)(c0 / kFillT) * kFillT : 0;
+    dim3 grid((unsigned)ceil_div(c1 - c0, kFillT), (unsigned)ceil_div(n - rbase, kFillT));
+    cmix_mirror_fill_kernel<<<grid, 256, 0, stream>>>(d_M, ldM, n, (int)c0, (int)c1, rbase, p->d_es.p, div2Lp1,
+                                                      interchange, p->ell_sorted ? 1 : 0);
+    SFB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+template <int AT, int NT, int NW>
+static size_t regz_smem_bytes(int nmax, int max_rows) {
+    constexpr int AP = AT * 8, K = NT * 8, S = K + 8;
+    return sizeof(double) * ((size_t)AP * S + (size_t)nmax * S + (size_t)K * S + (size_t)NW * AP * regz_tld(AP)) +
+           sizeof(int) * ((size_t)max_rows + 4);
+}
+
+template <int AT, int NT, int NW, int MINB>
+static int launch_regz(const RegzArgs& args, int nblocks, int nmax, int max_rows, cudaStream_t stream) {
+    const size_t smem = regz_smem_bytes<AT, NT, NW>(nmax, max_rows);
+    SFB_REQUIRE(smem <= 227 * 1024, "cmix_regz_kernel: shared memory footprint exceeds 227 KB");
+    SFB_CUDA_OK(cudaFuncSetAttribute(cmix_regz_kernel<AT, NT, NW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem));
+    cmix_regz_kernel<AT, NT, NW, MINB><<<nblocks, NW * 32, smem, stream>>>(args);
+    SFB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+template <int NT>
+static int launch_regz_at(int AT, const RegzArgs& args, int nblocks, int nmax, int max_rows, cudaStream_t stream) {
+    switch (AT) {
+        case 1: return launch_regz<1, NT, 4, 4>(args, nblocks, nmax, max_rows, stream);
+        case 2: return launch_regz<2, NT, 6, 2>(args, nblocks, nmax, max_rows, stream);
+        case 3: return launch_regz<3, NT, 6, 2>(args, nblocks, nmax, max_rows, stream);
+        case 4: return launch_regz<4, NT, 8, 1>(args, nblocks, nmax, max_rows, stream);
+        default: break;
+    }
+    set_error("cmix: nmax_l > 32 is not supported by this build");
+    return 2;
+}
+
+bool cmix_regz_eligible(const CmixPlan* p, bool sym, int npeers) {
+    if (getenv("SFB_CMIX_OLD")) return false;
+    return sym && npeers == 0 && p->nrp <= 64 && p->amax_tiles <= 4 && p->nmax <= 32 && p->nout < kRegzNoRow;
+}
+
+// Launch the register-Z kernel over the listed (row-ell, col-ell) blocks of one Ŵ chunk.
+// `blocks` holds 8 ints per block (see RegzArgs); they are grouped by the row side's tile count here.
+int cmix_regz_run(CmixPlan* p, const std::vector<int>& blocks, const double* d_What, int div2Lp1, int interchange,
+                  int64_t col_lo, int64_t col_hi, double* d_M, int64_t ldM, cudaStream_t stream, double* flops,
+                  int* launches) {
+    const int nb = (int)(blocks.size() / 8);
+    if (nb == 0) return 0;
+    const int NT = (p->nrp <= 32) ? 4 : 8;
+    // order: tile class (descending), then cost (descending) so the heavy CTAs start first
+    std::vector<int> order(nb);
+    for (int i = 0; i < nb; ++i) order[i] = i;
+    auto at_of = [&](int i) { return (blocks[8 * i + 2] + 7) / 8; };
+    auto cost_of = [&](int i) {
+        const double ap = 8.0 * at_of(i), b = blocks[8 * i + 3];
+        return ap * b + ap * ap * b * (b + 1) / (2.0 * 8 * NT);
+    };
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+        if (at_of(x) != at_of(y)) return at_of(x) > at_of(y);
+        return cost_of(x) > cost_of(y);
+    });
+    std::vector<int> sorted((size_t)nb * 8);
+    for (int i = 0; i < nb; ++i) std::copy(blocks.begin() + 8 * order[i], blocks.begin() + 8 * order[i] + 8,
+                                           sorted.begin() + 8 * (size_t)i);
+    SFB_TRY(p->d_regz_blocks.alloc(sorted.size()));
+    SFB_CUDA_OK(cudaMemcpyAsync(p->d_regz_blocks.p, sorted.data(), sorted.size() * sizeof(int), cudaMemcpyHostToDevice,
+                                stream));
+    RegzArgs args;
+    args.G = p->d_G.p;
+    args.What = d_What;
+    args.row_out = p->d_row_out.p;
+    args.row_n = p->d_row_n.p;
+    args.row_n2 = p->d_row_n2.p;
+    args.pairidx = p->d_pairidx.p;
+    args.M = d_M;
+    args.ldM = ldM;
+    args.nmax = p->nmax;
+    args.nrp = p->nrp;
+    args.col_lo = (int)col_lo;
+    args.col_hi = (int)col_hi;
+    args.div2Lp1 = div2Lp1;
+    args.interchange = interchange;
+    args.dbg = getenv("SFB_CMIX_DBG") ? atoi(getenv("SFB_CMIX_DBG")) : 0;
+    int i0 = 0;
+    while (i0 < nb) {
+        const int AT = (sorted[8 * (size_t)i0 + 2] + 7) / 8;
+        int i1 = i0, max_rows = 0;
+        while (i1 < nb && (sorted[8 * (size_t)i1 + 2] + 7) / 8 == AT) {
+            max_rows = std::max(max_rows, sorted[8 * (size_t)i1 + 5]);
+            const double b = sorted[8 * (size_t)i1 + 3];
+            // executed DMMA flops: Z = AT*NT*2NT DMMAs per N, T = AT*AT*2NT DMMAs per (N <= N') tile
+            *flops += 512.0 * (AT * NT * 2.0 * NT * b + AT * AT * 2.0 * NT * b * (b + 1) / 2);
+            ++i1;
+        }
+        args.blocks = p->d_regz_blocks.p + 8 * (size_t)i0;
+        if (NT == 4)
+            SFB_TRY(launch_regz_at<4>(AT, args, i1 - i0, p->nmax, max_rows, stream));
+        else
+            SFB_TRY(launch_regz_at<8>(AT, args, i1 - i0, p->nmax, max_rows, stream));
+        ++*launches;
+        i0 = i1;
+    }
+    return 0;
+}
+
+}  // namespace sfb
