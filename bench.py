@@ -319,32 +319,52 @@ def run_b200(args):
 
     # ---- roofline of the dominant kernel (measured live: CUDA events on the launching stream, inside the lib) ----
     block_ms = statistics.mean(stage_ms["block"])
+    fill_ms = statistics.mean(stage_ms["fill"])
+    kern_ms = block_ms - fill_ms            # the DMMA block kernel(s) alone; block_ms includes the mirror-fill pass
     stage1_ms = statistics.mean(stage_ms["stage1"])
     dmma = np.zeros(1)
     _lib.check(lib.sfb_probe_dmma_tflops(_lib.ptr(dmma)))
-    peaks = {}
+    peaks, traffic = {}, {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except OSError:
+        pass
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["kernels"]
+    except (OSError, KeyError):
         pass
     # algorithmic flops of the block kernel's share of F_alg: the two GEMM terms, for this rank's rows
     nl = np.asarray(wl.amodes.nmax_l, dtype=np.float64)
     ells_mine = np.unique(wl.cmodes.lnn[0, lo:hi])      # l-blocks (row shard) or L-blocks (column shard): same model
     nn = nl[ells_mine][:, None] * nl[None, :]
     f_alg_block = float(np.sum(2 * nn * wl.nr ** 2 + 2 * nn * nn * wl.nr))
-    exec_tflops = tim["block_flops"] / (block_ms * 1e-3) / 1e12
+    exec_tflops = tim["block_flops"] / (kern_ms * 1e-3) / 1e12
+    # ncu dram traffic of the block kernel launches (cfg4, N = 1 capture): only comparable for that workload
+    regz_traffic = sum(v["traffic_bytes"] for k, v in traffic.items() if k.startswith("cmix_regz_kernel")) or None
+    if world > 1 or str(args.config) != "4":
+        regz_traffic = None
     roofline = {
-        "kernel": "cmix_block_kernel (stage 2+3 block GEMMs, FP64 DMMA)", "bound": "tensor",
+        "kernel": "cmix_regz_kernel (stage 2+3 block GEMMs, FP64 DMMA, all tile classes of one step)", "bound": "tensor",
         "achieved": exec_tflops, "peak": float(dmma[0]), "unit": "TFLOP/s", "frac": exec_tflops / float(dmma[0]),
-        "traffic": None,
+        "traffic": regz_traffic,
+        "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the block-kernel launches of one step from the "
+                        "ncu --set full capture in profiles/r01_traffic.json; algorithmic bytes of these launches = the "
+                        "directly formed half of M (8·n²/2) + the Ŵ blocks read once",
+        "algorithmic_bytes": 8.0 * (hi - lo) * n / (2 if world == 1 else 1),
         "peak_source": "FP64 DMMA probe measured in this run (MEASURED_PEAKS.json has no FP64 figure; nominal B200 "
                        "FP64 tensor peak is 37-40 TFLOP/s)",
-        "algorithmic_tflops": f_alg_block / (block_ms * 1e-3) / 1e12,
-        "algorithmic_flops": f_alg_block, "executed_flops": tim["block_flops"], "launch_ms": block_ms,
-        "note": "achieved/frac count the DMMA flops the kernel EXECUTES (padded tiles included).  SURVEY §8d's algorithmic "
-                "count (2·nn·nr² + 2·nn²·nr per (l,L) block) is larger than the executed one because the kernel only forms "
-                "N<=N' tiles and, at N=1, only the L>=l blocks (the mirrored block comes from the same tile): "
-                "algorithmic_tflops can therefore exceed the peak and is not a utilisation figure",
+        "algorithmic_tflops": f_alg_block / (kern_ms * 1e-3) / 1e12,
+        "algorithmic_flops": f_alg_block, "executed_flops": tim["block_flops"], "launch_ms": kern_ms,
+        "note": "achieved/frac count the DMMA flops the kernel EXECUTES (n padded to multiples of 8, +9% at cfg4) over its "
+                "own launch time.  SURVEY §8d's algorithmic count (2·nn·nr² + 2·nn²·nr per (l,L) block) is larger than the "
+                "executed one because only N<=N' tiles are formed and, at N=1, only the L>=l blocks (the mirror-fill pass "
+                "writes the other half): algorithmic_tflops can therefore exceed the peak and is not a utilisation figure",
+        "mirror_fill": {"ms": fill_ms, "bound": "hbm", "algorithmic_bytes": 8.0 * n * n if world == 1 else 0.0,
+                        "achieved_gbs": (8.0 * n * n / (fill_ms * 1e-3) / 1e9) if fill_ms > 0 else None,
+                        "hbm_peak_gbs": peaks.get("hbm_gbs"),
+                        "frac": (8.0 * n * n / (fill_ms * 1e-3) / 1e9 / peaks["hbm_gbs"])
+                        if (fill_ms > 0 and peaks.get("hbm_gbs")) else None,
+                        "traffic": traffic.get("cmix_mirror_fill_kernel", {}).get("traffic_bytes") if world == 1 else None},
         "stage1": {"ms": stage1_ms, "alg_tflops": wl.flops_alg_stage1() / (stage1_ms * 1e-3) / 1e12,
                    "alg_gbs": wl.bytes_alg_stage1() / (stage1_ms * 1e-3) / 1e9,
                    "hbm_peak_gbs": peaks.get("hbm_gbs"), "hbm_frac": (wl.bytes_alg_stage1() / (stage1_ms * 1e-3) / 1e9 /
