@@ -15,6 +15,8 @@ largest that is quoted for one GPU; cfg5 needs `--config 5`.
 from __future__ import annotations
 
 import argparse
+import contextlib
+import io
 import json
 import os
 import statistics
@@ -225,18 +227,29 @@ def run_b200(args):
     # exchange variants (default first): cols = column slabs + in-place NCCL send/recv; cols_dma = column slabs +
     # IPC copy-engine pushes; dma / stores = row shards via pitched P2P copies / in-kernel P2P stores;
     # nccl = row slabs + padded all_gather + placement
-    xmode = os.environ.get("SFB_BENCH_EXCHANGE", "cols")
-    ranges = shard_rows(pipe.col_costs if xmode.startswith("cols") else pipe.row_costs, pipe.ell_of_row, world)
+    # packed (default) = column shards of the l <= L blocks in upper-packed storage + in-place NCCL all-gather of the
+    # packed slabs (half the matrix bytes) + local unpack/mirror pass
+    # pull (default) = packed slabs left in place in peer-mapped buffers, the expansion kernel pulls every column from
+    # its owner over NVLink (exchange fused into the kernel)
+    xmode = os.environ.get("SFB_BENCH_EXCHANGE", "pull")
+    if xmode in ("packed", "pull"):
+        off = pipe.packed_offsets()
+        ranges = shard_rows(pipe.col_costs_upper, pipe.ell_of_row, world)
+    else:
+        ranges = shard_rows(pipe.col_costs if xmode.startswith("cols") else pipe.row_costs, pipe.ell_of_row, world)
     lo, hi = ranges[rank]
     # N = 1: the matrix stays in a device buffer; N > 1: every rank holds the full matrix, rows stored into all
     # copies by the block kernel itself (all-gather fused into the epilogue over NVLink peer memory)
     slab = torch.empty((pipe.nout, hi - lo), dtype=torch.float64, device="cuda") if world == 1 else None
     pm = PeerMatrix(pipe.nout) if (world > 1 and xmode in ("cols_dma", "dma", "stores")) else None
-    full_t = torch.empty((pipe.nout, pipe.nout), dtype=torch.float64, device="cuda") if (world > 1 and xmode == "cols") else None
+    full_t = torch.empty((pipe.nout, pipe.nout), dtype=torch.float64, device="cuda") if (world > 1 and xmode in ("cols", "packed", "pull")) else None
+    packed_t = torch.empty(int(off[-1]), dtype=torch.float64, device="cuda") if (world > 1 and xmode == "packed") else None
+    from sfb_b200.device import PeerBuffer, stream_barrier
+    pb = PeerBuffer(int(off[-1])) if (world > 1 and xmode == "pull") else None
 
     fused = xmode in ("dma", "stores")
-    from sfb_b200.device import allgather_col_slabs
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    from sfb_b200.device import allgather_col_slabs, allgather_packed_slabs
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
     if world > 1 and not fused:
         from sfb_b200.device import gather_row_slabs
         slab = torch.empty((pipe.nout, hi - lo), dtype=torch.float64, device="cuda")
@@ -245,7 +258,22 @@ def run_b200(args):
         evs[0].record()
         pipe.calc_wr_lm_sharded(d_win)
         evs[1].record()
-        if world > 1 and xmode == "cols":
+        if world > 1 and xmode == "pull":
+            if hi > lo:
+                pipe.power_win_mix_upper_packed(lo, hi, pb.tensor)
+            evs[3].record()
+            stream_barrier(pipe)
+            evs[4].record()
+            out = pipe.unpack_mirror_pull(pb, ranges, full_t)
+            stream_barrier(pipe)
+        elif world > 1 and xmode == "packed":
+            if hi > lo:
+                pipe.power_win_mix_upper_packed(lo, hi, packed_t)
+            evs[3].record()
+            allgather_packed_slabs(packed_t, [(int(off[l]), int(off[h])) for l, h in ranges])
+            evs[4].record()
+            out = pipe.unpack_mirror(packed_t, full_t)
+        elif world > 1 and xmode == "cols":
             if hi > lo:
                 pipe.power_win_mix_cols(lo, hi, out=full_t[lo:hi])
             allgather_col_slabs(full_t, ranges)
@@ -283,6 +311,8 @@ def run_b200(args):
     barrier()
     tim = _lib.timings()
     stage_ms = {"stage1": [], "wl": [], "what": [], "block": [], "fill": [], "stage1_incl_gather": [], "stage23_incl_exchange": []}
+    if world > 1 and xmode in ("packed", "pull"):
+        stage_ms.update({"exchange": [], "unpack": []})
     launches_per_step = 0
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -301,6 +331,9 @@ def run_b200(args):
         torch.cuda.synchronize()
         stage_ms["stage1_incl_gather"].append(evs[0].elapsed_time(evs[1]))
         stage_ms["stage23_incl_exchange"].append(evs[1].elapsed_time(evs[2]))
+        if world > 1 and xmode in ("packed", "pull"):
+            stage_ms["exchange"].append(evs[3].elapsed_time(evs[4]))
+            stage_ms["unpack"].append(evs[4].elapsed_time(evs[2]))
         launches_per_step = int(tim["launches"])
     ev1.record()
     barrier()
@@ -438,10 +471,13 @@ def run_b200(args):
             "config": dict(wl.describe(), l2="working set (win 0.4 GB + ring buffers 0.3 GB + M %.1f GB) exceeds the "
                                              "126 MB L2, no explicit flush" % (8e-9 * n * n),
                            parallelism=f"sharded x{world}" + (" (stage 1 shell-sharded + NCCL all-gather of W_lm(r); "
-                                                                   "M sharded by columns (L,N,N') = contiguous "
-                                                                   "slabs written in place, then an uneven in-place "
-                                                                   "NCCL all-gather (grouped send/recv) over NVLink; "
-                                                                   f"exchange={xmode})"
+                                                                   "M sharded by columns (L,N,N'): each rank forms the "
+                                                                   "l<=L blocks of its columns in upper-packed storage "
+                                                                   "(half the matrix bytes); pull: the unpack+mirror "
+                                                                   "kernel reads every column from its owner's peer-"
+                                                                   "mapped buffer over NVLink (exchange fused into the "
+                                                                   "kernel); packed: in-place NCCL all-gather of the "
+                                                                   f"slabs first; exchange={xmode})"
                                                                    if world > 1 else "")),
             "roofline": roofline, "per_rank": per_rank, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
@@ -450,15 +486,35 @@ def run_b200(args):
     if world > 1:
         if pm is not None:
             pm.close()
+        if pb is not None:
+            pb.close()
         dist.destroy_process_group()
 
 
 def main():
     args = parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_b200(args)
+    # stdout carries exactly ONE JSON line: anything a library prints there meanwhile (NCCL's version banner, ...)
+    # is sent to stderr by pointing fd 1 at fd 2 until the result is ready
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    out = io.StringIO()
+    try:
+        with contextlib.redirect_stdout(out):
+            if args.impl == "reference":
+                run_reference(args)
+            else:
+                run_b200(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+    lines = [ln for ln in out.getvalue().splitlines() if ln.startswith("{")]
+    rest = [ln for ln in out.getvalue().splitlines() if not ln.startswith("{")]
+    if rest:
+        print("\n".join(rest), file=sys.stderr)
+    if lines:
+        print(lines[-1], flush=True)
 
 
 if __name__ == "__main__":

@@ -156,6 +156,29 @@ int32_t sfb_power_win_mix_block_dev(sfb_cmix_plan* plan, const double* d_alm1, c
 int32_t sfb_cmix_row_costs(const sfb_cmix_plan* plan, double* cost, int64_t n);
 int32_t sfb_cmix_col_costs(const sfb_cmix_plan* plan, double* cost, int64_t n);
 
+/* Multi-GPU exchange format (auto-correlation, lnn sorted by l, nr <= 64): "upper-packed" storage keeps, for output
+ * column j, only the rows of the blocks with l <= l(j), i.e. rows [0, rend(j)), contiguously at element offset
+ * offsets[j] (offsets[nout] = total length).  A rank forms the blocks with l <= L of its column range
+ * [col_lo,col_hi) -- a contiguous slab [offsets[col_lo], offsets[col_hi]) of the packed buffer -- the slabs are
+ * all-gathered in place (half the bytes of the full matrix), and sfb_cmix_unpack_mirror_dev expands the packed buffer
+ * into the full column-major matrix: M[r,j] = P[offsets[j]+r], and below the block diagonal M[j,r] = M[r,j] f_r/f_j,
+ * f = (div2Lp1 ? 1 : 2l+1)(interchange_NN ? 1 : 1+[n != n']): the un-symmetrised kernel of src/windows.jl:613-627 is
+ * symmetric under (l,n,n') <-> (L,N,N') (derivations/sfb.tex:516-517; the reference's own to-do, src/windows.jl:22-33). */
+int32_t sfb_cmix_packed_offsets(const sfb_cmix_plan* plan, int64_t* offsets, int64_t n_plus_1);
+int32_t sfb_cmix_col_costs_upper(const sfb_cmix_plan* plan, double* cost, int64_t n);
+int32_t sfb_power_win_mix_upper_packed_dev(sfb_cmix_plan* plan, const double* d_alm, int32_t div2Lp1,
+                                           int32_t interchange_NN, int64_t col_lo, int64_t col_hi, double* d_packed,
+                                           void* stream);
+int32_t sfb_cmix_unpack_mirror_dev(sfb_cmix_plan* plan, const double* d_packed, int32_t div2Lp1, int32_t interchange_NN,
+                                   double* d_M, int64_t ldM, void* stream);
+/* Fused exchange: packed_of_rank[g] is rank g's packed buffer (sfb_ipc_alloc / sfb_ipc_open, own buffer included), rank g
+ * owning the columns [col_bounds[g], col_bounds[g+1]).  The kernel pulls every column from its owner over NVLink while
+ * writing the local full matrix, so no separate all-gather of M runs.  Callers must order it after every rank's
+ * sfb_power_win_mix_upper_packed_dev (a stream-ordered barrier, e.g. a 1-element NCCL all-reduce).            */
+int32_t sfb_cmix_unpack_mirror_peers_dev(sfb_cmix_plan* plan, const double* const* packed_of_rank,
+                                         const int64_t* col_bounds, int32_t nranks, int32_t div2Lp1,
+                                         int32_t interchange_NN, double* d_M, int64_t ldM, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

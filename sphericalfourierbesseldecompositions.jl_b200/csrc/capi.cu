@@ -636,6 +636,67 @@ int32_t sfb_memcpy_dev(void* dst, const void* src, int64_t bytes, void* stream) 
     return 0;
 }
 
+int32_t sfb_power_win_mix_upper_packed_dev(sfb_cmix_plan* plan, const double* d_alm, int32_t div2Lp1,
+                                           int32_t interchange_NN, int64_t col_lo, int64_t col_hi, double* d_packed,
+                                           void* stream) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    auto* p = reinterpret_cast<CmixPlan*>(plan);
+    SFB_REQUIRE(p && d_alm && d_packed, "null pointer");
+    const double t0 = g_times[6];
+    SFB_TRY(cmix_run(p, d_alm, d_alm, div2Lp1, interchange_NN, 0, p->nout, col_lo, col_hi, d_packed, p->nout,
+                     (cudaStream_t)stream, nullptr, 0, false, false, true));
+    record_cmix_times(p);
+    g_times[6] = t0 + p->launches;
+    return 0;
+}
+int32_t sfb_cmix_unpack_mirror_dev(sfb_cmix_plan* plan, const double* d_packed, int32_t div2Lp1, int32_t interchange_NN,
+                                   double* d_M, int64_t ldM, void* stream) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    auto* p = reinterpret_cast<CmixPlan*>(plan);
+    const double* bases[1] = {d_packed};
+    SFB_TRY(cmix_unpack_mirror(p, bases, nullptr, 1, div2Lp1, interchange_NN, d_M, ldM, (cudaStream_t)stream));
+    g_times[6] += 1;
+    return 0;
+}
+int32_t sfb_cmix_unpack_mirror_peers_dev(sfb_cmix_plan* plan, const double* const* packed_of_rank,
+                                         const int64_t* col_bounds, int32_t nranks, int32_t div2Lp1,
+                                         int32_t interchange_NN, double* d_M, int64_t ldM, void* stream) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    auto* p = reinterpret_cast<CmixPlan*>(plan);
+    SFB_REQUIRE(col_bounds, "null pointer");
+    SFB_TRY(cmix_unpack_mirror(p, packed_of_rank, col_bounds, nranks, div2Lp1, interchange_NN, d_M, ldM,
+                               (cudaStream_t)stream));
+    g_times[6] += 1;
+    return 0;
+}
+int32_t sfb_cmix_packed_offsets(const sfb_cmix_plan* plan, int64_t* offsets, int64_t n_plus_1) {
+    const auto* p = reinterpret_cast<const CmixPlan*>(plan);
+    SFB_REQUIRE(p && offsets && n_plus_1 == p->nout + 1, "sfb_cmix_packed_offsets: bad arguments");
+    SFB_REQUIRE(p->ell_sorted && (int64_t)p->h_colbase.size() == p->nout + 1,
+                "sfb_cmix_packed_offsets: upper-packed storage needs an lnn table sorted by l");
+    for (int64_t i = 0; i <= p->nout; ++i) offsets[i] = p->h_colbase[i];
+    return 0;
+}
+// cost of each output column when only the blocks with l <= L are formed (upper-packed / mirror mode)
+int32_t sfb_cmix_col_costs_upper(const sfb_cmix_plan* plan, double* cost, int64_t n) {
+    const auto* p = reinterpret_cast<const CmixPlan*>(plan);
+    SFB_REQUIRE(p && cost && n == p->nout, "sfb_cmix_col_costs_upper: bad arguments");
+    for (int L = 0; L <= p->lmax; ++L) {
+        const int cols = p->ell_ptr[L + 1] - p->ell_ptr[L];
+        if (!cols) continue;
+        const double b = p->a_of_ell[L];
+        double c = 0;
+        for (int l = 0; l <= L; ++l) {
+            if (p->ell_ptr[l + 1] == p->ell_ptr[l]) continue;
+            const double ap = 8.0 * ((p->a_of_ell[l] + 7) / 8);
+            c += 2.0 * ap * p->nrp * p->nrp * b + 2.0 * ap * ap * p->nrp * b * (b + 1) / 2 +
+                 2.0 * p->nrp * p->nrp * (l + 1);
+        }
+        for (int s = p->ell_ptr[L]; s < p->ell_ptr[L + 1]; ++s) cost[p->h_row_out[s]] = c / cols;
+    }
+    return 0;
+}
+
 // cost of each output COLUMN (L,N,N'): the block (l,L) costs the same whichever way it is assigned, so the
 // column cost is the transpose of the row model
 int32_t sfb_cmix_col_costs(const sfb_cmix_plan* plan, double* cost, int64_t n) {

@@ -623,6 +623,15 @@ int cmix_plan_create(CmixPlan** out, const int64_t* lnn, int64_t lnnsize, int64_
     rc = rc ? rc : up(p->d_nl_L, nl_L);
     rc = rc ? rc : up(p->d_nl_N, nl_N);
     rc = rc ? rc : up(p->d_es, es);
+    if (p->ell_sorted) {  // upper-packed storage: column j keeps rows [0, rend(j)), rend = end of j's own l-block
+        std::vector<int64_t> lend(lmax + 1, 0);
+        for (int64_t o = 0; o < p->nout; ++o) lend[es[o] & 0x3fffffff] = o + 1;
+        p->h_colbase.assign(p->nout + 1, 0);
+        // column lengths rounded up to 4 doubles: every column starts 32-byte aligned (16-byte loads in the unpack kernel)
+        for (int64_t o = 0; o < p->nout; ++o)
+            p->h_colbase[o + 1] = p->h_colbase[o] + round_up(lend[es[o] & 0x3fffffff], 4);
+        rc = rc ? rc : up(p->d_colbase, p->h_colbase);
+    }
     rc = rc ? rc : p->d_row_out.alloc(nrows);
     rc = rc ? rc : p->d_ell_list.alloc(lmax + 1);
     rc = rc ? rc : p->d_w2.alloc((size_t)(lmax + 1) * (lmax + 1) * (lmax + 1));
@@ -650,7 +659,7 @@ void cmix_plan_destroy(CmixPlan* p) { delete p; }
 
 int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp1, int interchange, int64_t row_lo,
              int64_t row_hi, int64_t col_lo, int64_t col_hi, double* d_M, int64_t ldM, cudaStream_t stream,
-             double* const* peers, int npeers, bool reuse_wl, bool mirror) {
+             double* const* peers, int npeers, bool reuse_wl, bool mirror, bool upper_packed) {
     SFB_REQUIRE(p && d_alm1 && d_alm2 && d_M, "cmix_run: null pointer");
     SFB_REQUIRE(npeers >= 0 && npeers <= 7, "cmix_run: at most 7 peers");
     SFB_REQUIRE(0 <= row_lo && row_lo <= row_hi && row_hi <= p->nout, "cmix_run: bad row range");
@@ -670,6 +679,12 @@ int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp
     // register-Z kernel (cmix_regz.cu) for the auto-correlation path with nr <= 64; in mirror mode it forms the L >= l
     // blocks only and cmix_mirror_fill writes the blocks below the block diagonal afterwards
     const bool regz = cmix_regz_eligible(p, sym, npeers);
+    if (upper_packed) {
+        SFB_REQUIRE(regz && p->ell_sorted && !mirror && row_lo == 0 && row_hi == p->nout,
+                    "cmix_run: upper-packed output needs the auto-correlation path with nr <= 64, an l-sorted lnn table "
+                    "and the full row range");
+    }
+    const bool upper = mirror || upper_packed;  // only the blocks with L >= l are formed
     cudaEvent_t ev[4];
     for (auto& e : ev) SFB_CUDA_OK(cudaEventCreate(&e));
 
@@ -762,7 +777,7 @@ int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp
         SFB_CUDA_OK(cudaMemcpyAsync(p->d_what_ells.p, wells.data(), wells.size() * sizeof(int), cudaMemcpyHostToDevice,
                                     stream));
         what_build_kernel<<<dim3(ngroups, (unsigned)wells.size()), 256, kWhatGroup * (lmax + 1) * sizeof(double), stream>>>(
-            p->d_W.p, p->d_w2.p, p->d_What.p, p->d_what_ells.p, ell0, lmax, nrp, Llo, Lhi, mirror ? 1 : 0);
+            p->d_W.p, p->d_w2.p, p->d_What.p, p->d_what_ells.p, ell0, lmax, nrp, Llo, Lhi, upper ? 1 : 0);
         SFB_CUDA_OK(cudaGetLastError());
         p->launches++;
         SFB_CUDA_OK(cudaEventRecord(e1, stream));
@@ -771,14 +786,14 @@ int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp
         if (regz) {
             std::vector<int> blocks;
             for (int l : wells)
-                for (int L = mirror ? l : 0; L <= lmax; ++L) {
+                for (int L = upper ? l : 0; L <= lmax; ++L) {
                     if (!L_used[L] || p->a_of_ell[L] == 0) continue;
                     const int desc[8] = {l, L, p->a_of_ell[l], p->a_of_ell[L], p->ell_ptr[l],
                                          p->ell_ptr[l + 1] - p->ell_ptr[l], (l - ell0) * (lmax + 1) + L, 0};
                     blocks.insert(blocks.end(), desc, desc + 8);
                 }
-            SFB_TRY(cmix_regz_run(p, blocks, p->d_What.p, div2Lp1, interchange, col_lo, col_hi, d_M, ldM, stream, &flops,
-                                  &p->launches));
+            SFB_TRY(cmix_regz_run(p, blocks, p->d_What.p, div2Lp1, interchange, col_lo, col_hi, d_M, ldM,
+                                  upper_packed ? p->d_colbase.p + col_lo : nullptr, stream, &flops, &p->launches));
         }
         for (int AT = regz ? 0 : p->amax_tiles; AT >= 1; --AT) {
             std::vector<int> ells;

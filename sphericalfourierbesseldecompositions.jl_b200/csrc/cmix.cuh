@@ -41,6 +41,8 @@ struct CmixPlan {
     DevBuf<int> d_what_ells;          // l-blocks whose Ŵ is built for the current row shard
     DevBuf<int> d_es;                 // per output index: l | [n≠n'] << 30 (mirror fill)
     bool ell_sorted = false;          // l non-decreasing in output order
+    std::vector<long long> h_colbase; // upper-packed storage: element offset of column j (nout + 1 entries), ell_sorted only
+    DevBuf<long long> d_colbase;
     DevBuf<int> d_regz_blocks;        // per-launch block descriptors of the register-Z kernel (cmix_regz.cu)
     size_t what_budget_bytes = size_t(2) << 30;
 
@@ -63,17 +65,25 @@ void cmix_plan_destroy(CmixPlan* p);
 // mirror = true (auto-correlation only): d_M is the base of the FULL matrix; for the l-blocks of the row range only
 // the blocks with L >= l are formed and every tile also fills the mirrored block, using
 //   M[(L,N,N'),(l,n,n')] = c_l (A + [n≠n'] B),  M[(l,n,n'),(L,N,N')] = c_L (A + [N≠N'] B)   (same A, B).
+// upper_packed = true (auto-correlation, register-Z kernel, l-sorted table): only the blocks with l <= L of the column
+// range [col_lo, col_hi) are formed and written in upper-packed storage (column j at d_M + colbase[j], rows
+// [0, rend(j))); d_M is the base of the whole packed buffer.  cmix_unpack_mirror expands it.
 // `peers` (optional): up to 7 more device pointers (peer-mapped, same offset/ldM semantics as d_M); every element
 // is also stored there, which fuses the all-gather of row shards into the kernel epilogue.
 int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp1, int interchange,
              int64_t row_lo, int64_t row_hi, int64_t col_lo, int64_t col_hi, double* d_M, int64_t ldM,
              cudaStream_t stream, double* const* peers = nullptr, int npeers = 0, bool reuse_wl = false,
-             bool mirror = false);
+             bool mirror = false, bool upper_packed = false);
 // Register-resident-Z block kernel (cmix_regz.cu): auto-correlation, nr <= 64, no peer stores.
 bool cmix_regz_eligible(const CmixPlan* p, bool sym, int npeers);
 int cmix_regz_run(CmixPlan* p, const std::vector<int>& blocks, const double* d_What, int div2Lp1, int interchange,
-                  int64_t col_lo, int64_t col_hi, double* d_M, int64_t ldM, cudaStream_t stream, double* flops,
-                  int* launches);
+                  int64_t col_lo, int64_t col_hi, double* d_M, int64_t ldM, const long long* d_colbase,
+                  cudaStream_t stream, double* flops, int* launches);
+// upper-packed storage -> full column-major matrix (direct copy of the l <= L blocks + mirror image below them)
+// bases[g] = packed buffer of rank g (peer-mapped; nranks = 1: the local buffer), rank g owning the columns
+// [col_bounds[g], col_bounds[g+1]) (col_bounds may be null for nranks = 1)
+int cmix_unpack_mirror(CmixPlan* p, const double* const* bases, const int64_t* col_bounds, int nranks, int div2Lp1,
+                       int interchange, double* d_M, int64_t ldM, cudaStream_t stream);
 int cmix_mirror_fill(CmixPlan* p, int64_t c0, int64_t c1, int div2Lp1, int interchange, double* d_M, int64_t ldM,
                      cudaStream_t stream);
 // l-block aligned row ranges of roughly equal cost for the mirrored, pipelined host path

@@ -35,6 +35,7 @@ struct RegzArgs {
     const int* pairidx;    // [L][nmax][nmax] -> output column or -1
     double* M;
     long long ldM;
+    const long long* colbase;  // optional: element offset of output column c (relative to col_lo) instead of c * ldM
     int nmax, nrp;
     int col_lo, col_hi;
     int div2Lp1, interchange;
@@ -200,7 +201,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) cmix_regz_kernel(RegzArgs p) {
                     *reinterpret_cast<double2*>(Tw + (i * 8 + g) * TLD + j * 8 + 2 * t) =
                         make_double2(acc[i][j][0], acc[i][j][1]);
             __syncwarp();
-            const size_t coff = (size_t)col * p.ldM;
+            const size_t coff = p.colbase ? (size_t)p.colbase[col] : (size_t)col * p.ldM;
             const bool offdiag = (N2 != N);
             // eight rows per lane per iteration: all table and tile loads of an iteration are independent
             for (int idx0 = lane; idx0 < nrows; idx0 += 32 * kRegzU) {
@@ -307,6 +308,128 @@ int cmix_mirror_fill(CmixPlan* p, int64_t c0, int64_t c1, int div2Lp1, int inter
     return 0;
 }
 
+// =============================================================================================
+// Upper-packed storage (multi-GPU exchange format): output column j keeps only the rows of the blocks with
+// l <= l(j), i.e. rows [0, rend(j)), at element offset colbase[j]; a rank's column range is one contiguous slab
+// (half the bytes of the full matrix cross NVLink).  cmix_unpack_mirror_kernel expands it into the full
+// column-major matrix: M[r, j] = P[colbase[j] + r] for r < rend(j), and below the block diagonal
+// M[j, r] = M[r, j] · f_r / f_j for l(r) < l(j)  (same identity as cmix_mirror_fill_kernel).
+// With several ranks the packed buffer of the column's OWNER is read directly (peer-mapped memory, NVLink loads): the
+// all-gather of the packed slabs is fused into this kernel and overlaps its HBM writes.
+struct PackedSrc {
+    const double* base[8];  // packed buffer of rank g (own buffer included), peer-mapped
+    int col_start[9];       // rank g owns the columns [col_start[g], col_start[g+1])
+    int nranks;
+};
+
+template <bool VEC>
+__global__ void __launch_bounds__(256) cmix_unpack_mirror_kernel(PackedSrc src,
+                                                                 const long long* __restrict__ colbase,
+                                                                 double* __restrict__ M, long long ld, int n,
+                                                                 const int* __restrict__ es, int div2Lp1,
+                                                                 int interchange) {
+    __shared__ double tile[kFillT][kFillT + 1];
+    __shared__ int esr[kFillT], esc[kFillT];
+    __shared__ const double* cptr[kFillT];
+    const int jb = blockIdx.x * kFillT, rb = blockIdx.y * kFillT;
+    const int x = threadIdx.x & 31, y0 = threadIdx.x >> 5;
+    if (threadIdx.x < kFillT) esr[threadIdx.x] = (rb + threadIdx.x < n) ? es[rb + threadIdx.x] : -1;
+    else if (threadIdx.x < 2 * kFillT) {
+        const int j = jb + threadIdx.x - kFillT;
+        esc[threadIdx.x - kFillT] = (j < n) ? es[j] : -1;
+        int g = 0;
+        while (g + 1 < src.nranks && j >= src.col_start[g + 1]) ++g;
+        cptr[threadIdx.x - kFillT] = src.base[g] + ((j < n) ? colbase[j] : 0);
+    }
+    __syncthreads();
+    {   // l is sorted: a tile whose smallest row l exceeds its largest column l holds no source element
+        const int jlast = min(kFillT, n - jb) - 1;
+        if ((esr[0] & 0x3fffffff) > (esc[jlast] & 0x3fffffff)) return;
+    }
+    // source elements (rows rb+2x, rb+2x+1, column jb+y): direct write, and into tile[y][.] for the mirror image.
+    // 16-byte accesses (columns start on even offsets in packed storage, VEC: ld even and M 16-byte aligned); all
+    // eight loads of a thread are issued before the first store (they may cross NVLink: keep them in flight).
+    constexpr int NK = kFillT / 8;
+    const int x2 = 2 * x;
+    const int er0 = esr[x2], er1 = esr[x2 + 1];
+    double2 v[NK];
+    unsigned ok0 = 0, ok1 = 0;
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+        const int y = y0 + 8 * k;
+        const int ec = esc[y];
+        const bool a0 = (er0 >= 0 && ec >= 0 && (er0 & 0x3fffffff) <= (ec & 0x3fffffff));
+        const bool a1 = (er1 >= 0 && ec >= 0 && (er1 & 0x3fffffff) <= (ec & 0x3fffffff));
+        v[k] = make_double2(0.0, 0.0);
+        if (a0) v[k] = *reinterpret_cast<const double2*>(cptr[y] + rb + x2);   // row rb+2x+1 < padded rend(j)
+        ok0 |= (a0 ? 1u : 0u) << k;
+        ok1 |= (a1 ? 1u : 0u) << k;   // l sorted: a1 implies a0
+    }
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+        const int y = y0 + 8 * k;
+        double* dst = M + (size_t)(jb + y) * ld + rb + x2;
+        if ((ok1 >> k) & 1u) {
+            if (VEC) *reinterpret_cast<double2*>(dst) = v[k];
+            else { dst[0] = v[k].x; dst[1] = v[k].y; }
+            tile[y][x2] = v[k].x;
+            tile[y][x2 + 1] = v[k].y;
+        } else if ((ok0 >> k) & 1u) {
+            dst[0] = v[k].x;
+            tile[y][x2] = v[k].x;
+        }
+    }
+    __syncthreads();
+    // mirror image: destination (rows jb+2x, jb+2x+1, column rb+y) = tile[.][y] f_r / f_j  for l(r) < l(j)
+    const int ej0 = esc[x2], ej1 = esc[x2 + 1];
+    const int lj0 = ej0 & 0x3fffffff, lj1 = ej1 & 0x3fffffff;
+    const double ifj0 = 1.0 / ((div2Lp1 ? 1.0 : 2.0 * lj0 + 1.0) * ((!interchange && (ej0 >> 30)) ? 2.0 : 1.0));
+    const double ifj1 = 1.0 / ((div2Lp1 ? 1.0 : 2.0 * lj1 + 1.0) * ((!interchange && (ej1 >> 30)) ? 2.0 : 1.0));
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+        const int y = y0 + 8 * k;
+        const int e2 = esr[y];
+        if (e2 < 0) continue;
+        const int lr = e2 & 0x3fffffff;
+        const double fr = (div2Lp1 ? 1.0 : 2.0 * lr + 1.0) * ((!interchange && (e2 >> 30)) ? 2.0 : 1.0);
+        const bool b0 = (ej0 >= 0 && lr < lj0), b1 = (ej1 >= 0 && lr < lj1);
+        double* dst = M + (size_t)(rb + y) * ld + jb + x2;
+        if (b0 && b1) {
+            const double w0 = tile[x2][y] * (fr * ifj0), w1 = tile[x2 + 1][y] * (fr * ifj1);
+            if (VEC) *reinterpret_cast<double2*>(dst) = make_double2(w0, w1);
+            else { dst[0] = w0; dst[1] = w1; }
+        } else if (b0) {
+            dst[0] = tile[x2][y] * (fr * ifj0);
+        } else if (b1) {
+            dst[1] = tile[x2 + 1][y] * (fr * ifj1);
+        }
+    }
+}
+
+int cmix_unpack_mirror(CmixPlan* p, const double* const* bases, const int64_t* col_bounds, int nranks, int div2Lp1,
+                       int interchange, double* d_M, int64_t ldM, cudaStream_t stream) {
+    SFB_REQUIRE(p && bases && d_M && nranks >= 1 && nranks <= 8, "cmix_unpack_mirror: bad arguments");
+    PackedSrc src;
+    for (int g = 0; g < 8; ++g) src.base[g] = (g < nranks) ? bases[g] : nullptr;
+    for (int g = 0; g <= 8; ++g) src.col_start[g] = (int)((g <= nranks && col_bounds) ? col_bounds[std::min(g, nranks)] : p->nout);
+    if (!col_bounds) src.col_start[0] = 0;
+    src.nranks = nranks;
+    for (int g = 0; g < nranks; ++g) SFB_REQUIRE(bases[g], "cmix_unpack_mirror: null packed buffer");
+    SFB_REQUIRE(p->ell_sorted, "cmix_unpack_mirror: the lnn table must be sorted by l");
+    SFB_REQUIRE(ldM >= p->nout, "cmix_unpack_mirror: ldM smaller than the matrix");
+    const int n = (int)p->nout;
+    dim3 grid((unsigned)ceil_div(n, kFillT), (unsigned)ceil_div(n, kFillT));
+    const bool vec = (ldM % 2 == 0) && (reinterpret_cast<uintptr_t>(d_M) % 16 == 0);
+    if (vec)
+        cmix_unpack_mirror_kernel<true><<<grid, 256, 0, stream>>>(src, p->d_colbase.p, d_M, ldM, n, p->d_es.p, div2Lp1,
+                                                                  interchange);
+    else
+        cmix_unpack_mirror_kernel<false><<<grid, 256, 0, stream>>>(src, p->d_colbase.p, d_M, ldM, n, p->d_es.p, div2Lp1,
+                                                                   interchange);
+    SFB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 template <int AT, int NT, int NW>
 static size_t regz_smem_bytes(int nmax, int max_rows) {
     constexpr int AP = AT * 8, K = NT * 8, S = K + 8;
@@ -346,8 +469,8 @@ bool cmix_regz_eligible(const CmixPlan* p, bool sym, int npeers) {
 // Launch the register-Z kernel over the listed (row-ell, col-ell) blocks of one Ŵ chunk.
 // `blocks` holds 8 ints per block (see RegzArgs); they are grouped by the row side's tile count here.
 int cmix_regz_run(CmixPlan* p, const std::vector<int>& blocks, const double* d_What, int div2Lp1, int interchange,
-                  int64_t col_lo, int64_t col_hi, double* d_M, int64_t ldM, cudaStream_t stream, double* flops,
-                  int* launches) {
+                  int64_t col_lo, int64_t col_hi, double* d_M, int64_t ldM, const long long* d_colbase,
+                  cudaStream_t stream, double* flops, int* launches) {
     const int nb = (int)(blocks.size() / 8);
     if (nb == 0) return 0;
     const int NT = (p->nrp <= 32) ? 4 : 8;
@@ -378,6 +501,7 @@ int cmix_regz_run(CmixPlan* p, const std::vector<int>& blocks, const double* d_W
     args.pairidx = p->d_pairidx.p;
     args.M = d_M;
     args.ldM = ldM;
+    args.colbase = d_colbase;
     args.nmax = p->nmax;
     args.nrp = p->nrp;
     args.col_lo = (int)col_lo;

@@ -237,6 +237,80 @@ class DevicePipeline:
             allgather_col_slabs(full, ranges, group)
         return full, ranges
 
+    # ---- upper-packed exchange (default multi-GPU path) -----------------------------------------------
+    def packed_offsets(self):
+        """Element offset of every output column in upper-packed storage (nout + 1 entries, host int64)."""
+        if getattr(self, "_packed_off", None) is None:
+            off = np.zeros(self.nout + 1, dtype=np.int64)
+            _lib.check(self.lib.sfb_cmix_packed_offsets(self._cmix, off.ctypes.data_as(C.c_void_p), self.nout + 1))
+            self._packed_off = off
+            cu = np.zeros(self.nout)
+            _lib.check(self.lib.sfb_cmix_col_costs_upper(self._cmix, _lib.ptr(cu), self.nout))
+            self.col_costs_upper = cu
+        return self._packed_off
+
+    def power_win_mix_upper_packed(self, lo, hi, packed, div2Lp1=False, interchange_NN=False):
+        """Blocks with l <= L of the columns [lo, hi), written into `packed` (the whole upper-packed buffer)."""
+        _lib.check(self.lib.sfb_power_win_mix_upper_packed_dev(self._cmix, self.alm.data_ptr(), int(div2Lp1),
+                                                               int(interchange_NN), lo, hi, packed.data_ptr(),
+                                                               self._stream()))
+        return packed
+
+    def unpack_mirror(self, packed, full=None, div2Lp1=False, interchange_NN=False):
+        torch = _torch()
+        if full is None:
+            full = torch.empty((self.nout, self.nout), dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.sfb_cmix_unpack_mirror_dev(self._cmix, packed.data_ptr(), int(div2Lp1), int(interchange_NN),
+                                                       full.data_ptr(), self.nout, self._stream()))
+        return full
+
+    def unpack_mirror_pull(self, peer_packed, ranges, full=None, div2Lp1=False, interchange_NN=False):
+        """Fused exchange + expansion: every column of the packed matrix is read from its owner's buffer over NVLink
+        (peer-mapped memory) while the local full matrix is written.  The caller orders this after all ranks' block
+        kernels (`stream_barrier`)."""
+        torch = _torch()
+        if full is None:
+            full = torch.empty((self.nout, self.nout), dtype=torch.float64, device=self.device)
+        pb = peer_packed
+        bases = (C.c_void_p * pb.world)(*pb.rank_ptrs)
+        bounds = np.asarray([r[0] for r in ranges] + [ranges[-1][1]], dtype=np.int64)
+        _lib.check(self.lib.sfb_cmix_unpack_mirror_peers_dev(self._cmix, bases, bounds.ctypes.data_as(C.c_void_p), pb.world,
+                                                             int(div2Lp1), int(interchange_NN), full.data_ptr(),
+                                                             self.nout, self._stream()))
+        return full
+
+    def power_win_mix_allgather_packed(self, d_win, full=None, packed=None, group=None, div2Lp1=False,
+                                       interchange_NN=False, peer_packed=None):
+        """Multi-GPU path for the auto-correlation matrix: stage 1 shell-sharded; stage 2+3 sharded over the column
+        index (L,N,N') forming only the blocks with l <= L, written in upper-packed storage (half the bytes of the
+        matrix); then every rank expands the packed matrix into the full one (direct half + mirror image).
+        With `peer_packed` (a PeerBuffer of packed_offsets()[-1] doubles) the exchange is fused into the expansion
+        kernel, which pulls each column from its owner over NVLink; otherwise the packed slabs are all-gathered in
+        place with NCCL first.  Returns (full, ranges); `full` holds Mᵀ in C order."""
+        torch = _torch()
+        import torch.distributed as dist
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        off = self.packed_offsets()
+        if peer_packed is not None:
+            packed = peer_packed.tensor
+        elif packed is None:
+            packed = torch.empty(int(off[-1]), dtype=torch.float64, device=self.device)
+        self.calc_wr_lm_sharded(d_win, group)
+        ranges = shard_rows(self.col_costs_upper, self.ell_of_row, world)
+        lo, hi = ranges[rank]
+        if hi > lo:
+            self.power_win_mix_upper_packed(lo, hi, packed, div2Lp1=div2Lp1, interchange_NN=interchange_NN)
+        if peer_packed is not None and world > 1:
+            stream_barrier(self, group)      # every rank's slab is complete before anyone pulls it
+            full = self.unpack_mirror_pull(peer_packed, ranges, full, div2Lp1=div2Lp1, interchange_NN=interchange_NN)
+            stream_barrier(self, group)      # ... and stays untouched until every rank has pulled it
+            return full, ranges
+        if world > 1:
+            allgather_packed_slabs(packed, [(int(off[l]), int(off[h])) for l, h in ranges], group)
+        full = self.unpack_mirror(packed, full, div2Lp1=div2Lp1, interchange_NN=interchange_NN)
+        return full, ranges
+
     def power_win_mix_sharded(self, d_win, group=None, gather=True, **kw):
         """Row-sharded coupling matrix over the ranks of `group`; with gather=True every rank returns the
         full matrix as a (nout, nout) tensor holding Mᵀ in C order (= M in Julia's column-major order)."""
@@ -272,11 +346,84 @@ def allgather_col_slabs(full, ranges, group=None):
         w.wait()
 
 
+def stream_barrier(pipe, group=None):
+    """Stream-ordered cross-rank barrier (a one-element NCCL all-reduce on the current stream, no host sync)."""
+    import torch.distributed as dist
+    if getattr(pipe, "_bar", None) is None:
+        pipe._bar = _torch().zeros(1, dtype=_torch().float32, device=pipe.device)
+    dist.all_reduce(pipe._bar, group=group)
+
+
+def allgather_packed_slabs(packed, spans, group=None):
+    """In-place uneven all-gather of the 1-D packed buffer: rank g owns packed[spans[g][0]:spans[g][1]]."""
+    import torch.distributed as dist
+    rank = dist.get_rank(group)
+    lo, hi = spans[rank]
+    ops = []
+    for g, (l, h) in enumerate(spans):
+        if g == rank or h <= l:
+            continue
+        if hi > lo:
+            ops.append(dist.P2POp(dist.isend, packed[lo:hi], g, group))
+        ops.append(dist.P2POp(dist.irecv, packed[l:h], g, group))
+    if not ops:
+        return
+    for w in dist.batch_isend_irecv(ops):
+        w.wait()
+
+
 class _DevArray:
     """__cuda_array_interface__ holder so torch can view a library-owned device buffer without a copy."""
 
     def __init__(self, ptr, shape):
         self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+
+class PeerBuffer:
+    """A device buffer of `nelem` doubles on every rank, IPC-mapped into all peers of the node: rank_ptrs[g] is the
+    address of rank g's buffer in THIS process (own buffer included)."""
+
+    def __init__(self, nelem, group=None):
+        torch = _torch()
+        import torch.distributed as dist
+        self.lib = _lib.load()
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if self.world > 8:
+            raise ValueError("PeerBuffer supports at most 8 GPUs of one node")
+        self.ptr = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        _lib.check(self.lib.sfb_ipc_alloc(C.byref(self.ptr), 8 * int(nelem), handle))
+        handles = [bytes(handle.raw)]
+        if self.world > 1:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle.raw), group=group)
+        self.rank_ptrs, self._opened = [], []
+        for g, h in enumerate(handles):
+            if g == self.rank:
+                self.rank_ptrs.append(self.ptr.value)
+                continue
+            q = C.c_void_p()
+            _lib.check(self.lib.sfb_ipc_open(C.create_string_buffer(h, 64), C.byref(q)))
+            self._opened.append(q)
+            self.rank_ptrs.append(q.value)
+        self.tensor = torch.as_tensor(_DevArray(self.ptr.value, (int(nelem),)),
+                                      device=torch.device("cuda", torch.cuda.current_device()))
+
+    def close(self):
+        import torch.distributed as dist
+        if self.ptr:
+            _torch().cuda.synchronize()
+            if self.world > 1:
+                dist.barrier(self.group)
+            for q in self._opened:
+                self.lib.sfb_ipc_close(q)
+            if self.world > 1:
+                dist.barrier(self.group)
+            self.lib.sfb_ipc_free(self.ptr)
+            self.ptr = C.c_void_p()
+            self._opened = []
 
 
 class PeerMatrix:

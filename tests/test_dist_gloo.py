@@ -34,6 +34,17 @@ def _worker(rank, world, port, ret):
     fullc[clo:chi] = torch.from_numpy(np.ascontiguousarray(M.T[clo:chi]))
     allgather_col_slabs(fullc, cr)
     ok = ok and np.array_equal(fullc.numpy().T, M)
+    # upper-packed slabs: column j keeps rows [0, rend(j)); uneven in-place all-gather of the 1-D buffer
+    from sfb_b200.device import allgather_packed_slabs
+    first = np.concatenate([[0], np.cumsum(np.bincount(ell))])
+    rend = first[ell + 1]
+    off = np.concatenate([[0], np.cumsum(rend)])
+    packed = torch.zeros(int(off[-1]), dtype=torch.float64)
+    for j in range(clo, chi):
+        packed[off[j]:off[j + 1]] = torch.from_numpy(M[:rend[j], j].copy())
+    allgather_packed_slabs(packed, [(int(off[l]), int(off[h])) for l, h in cr])
+    ref = np.concatenate([M[:rend[j], j] for j in range(n)])
+    ok = ok and np.array_equal(packed.numpy(), ref)
     out = torch.tensor([1.0 if ok else 0.0])
     dist.all_reduce(out, op=dist.ReduceOp.MIN)
     if rank == 0:

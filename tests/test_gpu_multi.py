@@ -39,6 +39,15 @@ def _worker(rank, world, port, ret):
     ok = rel(pipe.alm, alm_single) < 1e-13 and rel(full, single) < 1e-13
     ag, _ = pipe.power_win_mix_allgather(d_win)
     ok = ok and rel(ag, single) < 1e-13
+    pk, _ = pipe.power_win_mix_allgather_packed(d_win)      # default path: upper-packed slabs + unpack/mirror
+    ok = ok and rel(pk, single) < 1e-13
+    from sfb_b200.device import PeerBuffer
+    pb = PeerBuffer(int(pipe.packed_offsets()[-1]))
+    for kw in (dict(), dict(div2Lp1=True, interchange_NN=True)):
+        pl, _ = pipe.power_win_mix_allgather_packed(d_win, peer_packed=pb, **kw)   # exchange fused into the expansion
+        ref = pipe.power_win_mix_rows(0, pipe.nout, **kw)
+        ok = ok and rel(pl, ref) < 1e-13
+    pb.close()
     from sfb_b200.device import PeerMatrix
     pm = PeerMatrix(pipe.nout)
     for mode in ("cols", "dma", "stores"):

@@ -209,4 +209,16 @@ def test_device_pipeline_row_shards():
     assert relerr(np.concatenate(cparts, axis=1), M) < 1e-13
     wc = pipe.wr_lm_complex().cpu().numpy().T
     assert relerr(wc, sfb.calc_Wr_lm(win, 2 * a.lmax, a.nside)) < 1e-13
+    # upper-packed exchange format: three column shards into one packed buffer, then unpack + mirror
+    off = pipe.packed_offsets()
+    assert off[0] == 0 and off[-1] < pipe.nout ** 2 and np.all(np.diff(off) > 0)
+    ur = shard_rows(pipe.col_costs_upper, pipe.ell_of_row, 3)
+    for kw in (dict(), dict(div2Lp1=True), dict(interchange_NN=True)):
+        packed = torch.full((int(off[-1]),), float("nan"), dtype=torch.float64, device="cuda")
+        for lo, hi in ur:
+            pipe.power_win_mix_upper_packed(lo, hi, packed, **kw)
+        got = pipe.unpack_mirror(packed, **kw).cpu().numpy().T
+        ref = pipe.power_win_mix_rows(0, pipe.nout, **kw).cpu().numpy().T
+        assert np.isfinite(got).all()
+        assert relerr(got, ref) < 1e-13
     pipe.close()
