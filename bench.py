@@ -234,7 +234,7 @@ def run_b200(args):
     xmode = os.environ.get("SFB_BENCH_EXCHANGE", "pull")
     if xmode in ("packed", "pull"):
         off = pipe.packed_offsets()
-        ranges = shard_rows(pipe.col_costs_upper, pipe.ell_of_row, world)
+        ranges = pipe.packed_shard_ranges(world)
     else:
         ranges = shard_rows(pipe.col_costs if xmode.startswith("cols") else pipe.row_costs, pipe.ell_of_row, world)
     lo, hi = ranges[rank]

@@ -173,11 +173,13 @@ int32_t sfb_cmix_unpack_mirror_dev(sfb_cmix_plan* plan, const double* d_packed, 
                                    double* d_M, int64_t ldM, void* stream);
 /* Fused exchange: packed_of_rank[g] is rank g's packed buffer (sfb_ipc_alloc / sfb_ipc_open, own buffer included), rank g
  * owning the columns [col_bounds[g], col_bounds[g+1]).  The kernel pulls every column from its owner over NVLink while
- * writing the local full matrix, so no separate all-gather of M runs.  Callers must order it after every rank's
+ * writing the local full matrix, so no separate all-gather of M runs; rank my_rank starts with the columns of rank
+ * my_rank+1 and proceeds cyclically, so the readers never gang up on one owner.  Callers must order it after every rank's
  * sfb_power_win_mix_upper_packed_dev (a stream-ordered barrier, e.g. a 1-element NCCL all-reduce).            */
 int32_t sfb_cmix_unpack_mirror_peers_dev(sfb_cmix_plan* plan, const double* const* packed_of_rank,
-                                         const int64_t* col_bounds, int32_t nranks, int32_t div2Lp1,
-                                         int32_t interchange_NN, double* d_M, int64_t ldM, void* stream);
+                                         const int64_t* col_bounds, int32_t nranks, int32_t my_rank,
+                                         int32_t div2Lp1, int32_t interchange_NN, double* d_M, int64_t ldM,
+                                         void* stream);
 
 #ifdef __cplusplus
 }

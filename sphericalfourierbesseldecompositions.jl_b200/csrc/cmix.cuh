@@ -43,6 +43,8 @@ struct CmixPlan {
     bool ell_sorted = false;          // l non-decreasing in output order
     std::vector<long long> h_colbase; // upper-packed storage: element offset of column j (nout + 1 entries), ell_sorted only
     DevBuf<long long> d_colbase;
+    DevBuf<int> d_jt_order;           // column-tile visiting order of the fused pull (cmix_unpack_mirror)
+    std::vector<int> h_jt_key;        // (column bounds, nranks, rank) the order was built for
     DevBuf<int> d_regz_blocks;        // per-launch block descriptors of the register-Z kernel (cmix_regz.cu)
     size_t what_budget_bytes = size_t(2) << 30;
 
@@ -82,8 +84,8 @@ int cmix_regz_run(CmixPlan* p, const std::vector<int>& blocks, const double* d_W
 // upper-packed storage -> full column-major matrix (direct copy of the l <= L blocks + mirror image below them)
 // bases[g] = packed buffer of rank g (peer-mapped; nranks = 1: the local buffer), rank g owning the columns
 // [col_bounds[g], col_bounds[g+1]) (col_bounds may be null for nranks = 1)
-int cmix_unpack_mirror(CmixPlan* p, const double* const* bases, const int64_t* col_bounds, int nranks, int div2Lp1,
-                       int interchange, double* d_M, int64_t ldM, cudaStream_t stream);
+int cmix_unpack_mirror(CmixPlan* p, const double* const* bases, const int64_t* col_bounds, int nranks, int my_rank,
+                       int div2Lp1, int interchange, double* d_M, int64_t ldM, cudaStream_t stream);
 int cmix_mirror_fill(CmixPlan* p, int64_t c0, int64_t c1, int div2Lp1, int interchange, double* d_M, int64_t ldM,
                      cudaStream_t stream);
 // l-block aligned row ranges of roughly equal cost for the mirrored, pipelined host path

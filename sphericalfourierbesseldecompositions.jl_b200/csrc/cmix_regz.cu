@@ -320,6 +320,9 @@ struct PackedSrc {
     const double* base[8];  // packed buffer of rank g (own buffer included), peer-mapped
     int col_start[9];       // rank g owns the columns [col_start[g], col_start[g+1])
     int nranks;
+    const int* jt_order;    // column-tile visiting order (null: natural).  Every rank starts with a different owner's
+                            // columns and proceeds cyclically, so that at any time the readers pull from different
+                            // GPUs (no NVLink egress hot spot); its own (local) tiles are interleaved evenly
 };
 
 template <bool VEC>
@@ -331,7 +334,11 @@ __global__ void __launch_bounds__(256) cmix_unpack_mirror_kernel(PackedSrc src,
     __shared__ double tile[kFillT][kFillT + 1];
     __shared__ int esr[kFillT], esc[kFillT];
     __shared__ const double* cptr[kFillT];
-    const int jb = blockIdx.x * kFillT, rb = blockIdx.y * kFillT;
+    // row tiles fastest: one wave of CTAs works on a few column tiles, i.e. on ONE owner's columns
+    const int nt = (n + kFillT - 1) / kFillT;
+    const int jq = (int)(blockIdx.x / nt), rt = (int)(blockIdx.x % nt);
+    const int jt = src.jt_order ? src.jt_order[jq] : jq;
+    const int jb = jt * kFillT, rb = rt * kFillT;
     const int x = threadIdx.x & 31, y0 = threadIdx.x >> 5;
     if (threadIdx.x < kFillT) esr[threadIdx.x] = (rb + threadIdx.x < n) ? es[rb + threadIdx.x] : -1;
     else if (threadIdx.x < 2 * kFillT) {
@@ -406,19 +413,48 @@ __global__ void __launch_bounds__(256) cmix_unpack_mirror_kernel(PackedSrc src,
     }
 }
 
-int cmix_unpack_mirror(CmixPlan* p, const double* const* bases, const int64_t* col_bounds, int nranks, int div2Lp1,
-                       int interchange, double* d_M, int64_t ldM, cudaStream_t stream) {
+int cmix_unpack_mirror(CmixPlan* p, const double* const* bases, const int64_t* col_bounds, int nranks, int my_rank,
+                       int div2Lp1, int interchange, double* d_M, int64_t ldM, cudaStream_t stream) {
     SFB_REQUIRE(p && bases && d_M && nranks >= 1 && nranks <= 8, "cmix_unpack_mirror: bad arguments");
     PackedSrc src;
     for (int g = 0; g < 8; ++g) src.base[g] = (g < nranks) ? bases[g] : nullptr;
     for (int g = 0; g <= 8; ++g) src.col_start[g] = (int)((g <= nranks && col_bounds) ? col_bounds[std::min(g, nranks)] : p->nout);
     if (!col_bounds) src.col_start[0] = 0;
     src.nranks = nranks;
+    src.jt_order = nullptr;
+    const int ntile = (int)ceil_div(p->nout, kFillT);
+    if (nranks > 1 && my_rank >= 0 && my_rank < nranks) {
+        std::vector<int> key(src.col_start, src.col_start + 9);
+        key.push_back(nranks);
+        key.push_back(my_rank);
+        if (key != p->h_jt_key) {
+            // a tile belongs to the owner of its first column
+            std::vector<int> remote, local, order;
+            const int t0 = (int)ceil_div(src.col_start[(my_rank + 1) % nranks], kFillT);
+            for (int q = 0; q < ntile; ++q) {
+                const int jt = (t0 + q) % ntile;
+                const int j = jt * kFillT;
+                (j >= src.col_start[my_rank] && j < src.col_start[my_rank + 1] ? local : remote).push_back(jt);
+            }
+            size_t il = 0, ir = 0;
+            for (int q = 0; q < ntile; ++q) {
+                const bool take_local = ((q + 1) * local.size()) / ntile > (q * local.size()) / ntile;
+                if ((take_local && il < local.size()) || ir >= remote.size()) order.push_back(local[il++]);
+                else order.push_back(remote[ir++]);
+            }
+            SFB_TRY(p->d_jt_order.alloc(ntile));
+            SFB_CUDA_OK(cudaMemcpyAsync(p->d_jt_order.p, order.data(), ntile * sizeof(int), cudaMemcpyHostToDevice, stream));
+            SFB_CUDA_OK(cudaStreamSynchronize(stream));
+            p->h_jt_key = key;
+        }
+        src.jt_order = p->d_jt_order.p;
+    }
     for (int g = 0; g < nranks; ++g) SFB_REQUIRE(bases[g], "cmix_unpack_mirror: null packed buffer");
     SFB_REQUIRE(p->ell_sorted, "cmix_unpack_mirror: the lnn table must be sorted by l");
     SFB_REQUIRE(ldM >= p->nout, "cmix_unpack_mirror: ldM smaller than the matrix");
     const int n = (int)p->nout;
-    dim3 grid((unsigned)ceil_div(n, kFillT), (unsigned)ceil_div(n, kFillT));
+    const unsigned nt = (unsigned)ceil_div(n, kFillT);
+    dim3 grid(nt * nt);
     const bool vec = (ldM % 2 == 0) && (reinterpret_cast<uintptr_t>(d_M) % 16 == 0);
     if (vec)
         cmix_unpack_mirror_kernel<true><<<grid, 256, 0, stream>>>(src, p->d_colbase.p, d_M, ldM, n, p->d_es.p, div2Lp1,

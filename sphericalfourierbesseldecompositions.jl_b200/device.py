@@ -249,6 +249,18 @@ class DevicePipeline:
             self.col_costs_upper = cu
         return self._packed_off
 
+    def packed_shard_ranges(self, world, balance=None):
+        """Column ranges (L-block aligned) of the upper-packed path.  Every rank's time is its own compute plus serving
+        its slab to the world-1 readers, so the split balances  flops / (29 TFLOP/s) + (world-1) bytes / (700 GB/s)
+        (rates measured at cfg4: register-Z kernel, NVLink peer loads); balance="cost" uses the flop model alone."""
+        import os
+        off = self.packed_offsets()
+        balance = balance or os.environ.get("SFB_SHARD_BALANCE", "mixed")
+        w = self.col_costs_upper / 29e12
+        if balance == "mixed" and world > 1:
+            w = w + (world - 1) * 8.0 * np.diff(off) / 700e9
+        return shard_rows(w, self.ell_of_row, world)
+
     def power_win_mix_upper_packed(self, lo, hi, packed, div2Lp1=False, interchange_NN=False):
         """Blocks with l <= L of the columns [lo, hi), written into `packed` (the whole upper-packed buffer)."""
         _lib.check(self.lib.sfb_power_win_mix_upper_packed_dev(self._cmix, self.alm.data_ptr(), int(div2Lp1),
@@ -275,7 +287,7 @@ class DevicePipeline:
         bases = (C.c_void_p * pb.world)(*pb.rank_ptrs)
         bounds = np.asarray([r[0] for r in ranges] + [ranges[-1][1]], dtype=np.int64)
         _lib.check(self.lib.sfb_cmix_unpack_mirror_peers_dev(self._cmix, bases, bounds.ctypes.data_as(C.c_void_p), pb.world,
-                                                             int(div2Lp1), int(interchange_NN), full.data_ptr(),
+                                                             pb.rank, int(div2Lp1), int(interchange_NN), full.data_ptr(),
                                                              self.nout, self._stream()))
         return full
 
@@ -297,7 +309,7 @@ class DevicePipeline:
         elif packed is None:
             packed = torch.empty(int(off[-1]), dtype=torch.float64, device=self.device)
         self.calc_wr_lm_sharded(d_win, group)
-        ranges = shard_rows(self.col_costs_upper, self.ell_of_row, world)
+        ranges = self.packed_shard_ranges(world)
         lo, hi = ranges[rank]
         if hi > lo:
             self.power_win_mix_upper_packed(lo, hi, packed, div2Lp1=div2Lp1, interchange_NN=interchange_NN)

@@ -212,7 +212,7 @@ def test_device_pipeline_row_shards():
     # upper-packed exchange format: three column shards into one packed buffer, then unpack + mirror
     off = pipe.packed_offsets()
     assert off[0] == 0 and off[-1] < pipe.nout ** 2 and np.all(np.diff(off) > 0)
-    ur = shard_rows(pipe.col_costs_upper, pipe.ell_of_row, 3)
+    ur = pipe.packed_shard_ranges(3)
     for kw in (dict(), dict(div2Lp1=True), dict(interchange_NN=True)):
         packed = torch.full((int(off[-1]),), float("nan"), dtype=torch.float64, device="cuda")
         for lo, hi in ur:
