@@ -239,6 +239,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) cmix_regz_kernel(RegzArgs p) {
 // above the diagonal can be skipped without looking at the table.
 constexpr int kFillT = 64;  // tile edge: 16 independent 8-byte loads in flight per thread
 
+template <bool VEC>
 __global__ void __launch_bounds__(256) cmix_mirror_fill_kernel(double* __restrict__ M, long long ld, int n, int c0,
                                                                int c1, int rbase, const int* __restrict__ es,
                                                                int div2Lp1, int interchange, int sorted) {
@@ -258,40 +259,59 @@ __global__ void __launch_bounds__(256) cmix_mirror_fill_kernel(double* __restric
         lcmin = esc[0] & 0x3fffffff;
         if (lrmax <= lcmin) return;
     }
-    // source element (row cb+xx, column rb+y) -> tile[y][xx]
+    // source elements (rows cb+2x, cb+2x+1, column rb+y) -> tile[y][.]; 16-byte accesses when VEC (ld, c0 even and M
+    // 16-byte aligned).  l is non-decreasing along rows and columns, which orders the two predicates of a pair.
+    constexpr int NK = kFillT / 8;
+    const int x2 = 2 * x;
+    const int ec0 = esc[x2], ec1 = esc[x2 + 1];
+    const int lc0 = ec0 & 0x3fffffff, lc1 = ec1 & 0x3fffffff;
     bool any = false;
 #pragma unroll
-    for (int kx = 0; kx < kFillT / 32; ++kx) {
-        const int xx = x + 32 * kx;
-        const int ec = esc[xx];
-#pragma unroll
-        for (int k = 0; k < kFillT / 8; ++k) {
-            const int y = y0 + 8 * k;
-            const int er = esr[y];
-            const bool need = (ec >= 0 && er >= 0 && (er & 0x3fffffff) > (ec & 0x3fffffff));
-            if (need) tile[y][xx] = M[(size_t)(rb + y) * ld + cb + xx];
-            any = any || need;
+    for (int k = 0; k < NK; ++k) {
+        const int y = y0 + 8 * k;
+        const int er = esr[y];
+        const int lr = er & 0x3fffffff;
+        const bool n0 = (er >= 0 && ec0 >= 0 && lr > lc0), n1 = (er >= 0 && ec1 >= 0 && lr > lc1);
+        const double* srcp = M + (size_t)(rb + y) * ld + cb + x2;
+        if (n0 && n1) {
+            if (VEC) {
+                const double2 v = *reinterpret_cast<const double2*>(srcp);
+                tile[y][x2] = v.x;
+                tile[y][x2 + 1] = v.y;
+            } else {
+                tile[y][x2] = srcp[0];
+                tile[y][x2 + 1] = srcp[1];
+            }
+        } else if (n0) {
+            tile[y][x2] = srcp[0];
+        } else if (n1) {
+            tile[y][x2 + 1] = srcp[1];
         }
+        any = any || n0 || n1;
     }
     if (!__syncthreads_or(any)) return;
-    // destination element (row rb+xx, column cb+y) = tile[xx][y]
+    // destination elements (rows rb+2x, rb+2x+1, column cb+y) = tile[.][y] f_c / f_r
+    const int er0 = esr[x2], er1 = esr[x2 + 1];
+    const int lr0 = er0 & 0x3fffffff, lr1 = er1 & 0x3fffffff;
+    const double ifr0 = 1.0 / ((div2Lp1 ? 1.0 : 2.0 * lr0 + 1.0) * ((!interchange && (er0 >> 30)) ? 2.0 : 1.0));
+    const double ifr1 = 1.0 / ((div2Lp1 ? 1.0 : 2.0 * lr1 + 1.0) * ((!interchange && (er1 >> 30)) ? 2.0 : 1.0));
 #pragma unroll
-    for (int kx = 0; kx < kFillT / 32; ++kx) {
-        const int xx = x + 32 * kx;
-        const int er = esr[xx];
-        if (er < 0) continue;
-        const int lr = er & 0x3fffffff;
-        const double fr = (div2Lp1 ? 1.0 : 2.0 * lr + 1.0) * ((!interchange && (er >> 30)) ? 2.0 : 1.0);
-        const double ifr = 1.0 / fr;
-#pragma unroll
-        for (int k = 0; k < kFillT / 8; ++k) {
-            const int y = y0 + 8 * k;
-            const int e2 = esc[y];
-            if (e2 < 0) continue;
-            const int lc = e2 & 0x3fffffff;
-            if (lr <= lc) continue;
-            const double fc = (div2Lp1 ? 1.0 : 2.0 * lc + 1.0) * ((!interchange && (e2 >> 30)) ? 2.0 : 1.0);
-            M[(size_t)(cb + y) * ld + rb + xx] = tile[xx][y] * (fc * ifr);
+    for (int k = 0; k < NK; ++k) {
+        const int y = y0 + 8 * k;
+        const int e2 = esc[y];
+        if (e2 < 0) continue;
+        const int lc = e2 & 0x3fffffff;
+        const double fc = (div2Lp1 ? 1.0 : 2.0 * lc + 1.0) * ((!interchange && (e2 >> 30)) ? 2.0 : 1.0);
+        const bool d0 = (er0 >= 0 && lr0 > lc), d1 = (er1 >= 0 && lr1 > lc);
+        double* dst = M + (size_t)(cb + y) * ld + rb + x2;
+        if (d0 && d1) {
+            const double w0 = tile[x2][y] * (fc * ifr0), w1 = tile[x2 + 1][y] * (fc * ifr1);
+            if (VEC) *reinterpret_cast<double2*>(dst) = make_double2(w0, w1);
+            else { dst[0] = w0; dst[1] = w1; }
+        } else if (d0) {
+            dst[0] = tile[x2][y] * (fc * ifr0);
+        } else if (d1) {
+            dst[1] = tile[x2 + 1][y] * (fc * ifr1);
         }
     }
 }
@@ -302,8 +322,13 @@ int cmix_mirror_fill(CmixPlan* p, int64_t c0, int64_t c1, int div2Lp1, int inter
     const int n = (int)p->nout;
     const int rbase = p->ell_sorted ? (int)(c0 / kFillT) * kFillT : 0;
     dim3 grid((unsigned)ceil_div(c1 - c0, kFillT), (unsigned)ceil_div(n - rbase, kFillT));
-    cmix_mirror_fill_kernel<<<grid, 256, 0, stream>>>(d_M, ldM, n, (int)c0, (int)c1, rbase, p->d_es.p, div2Lp1,
-                                                      interchange, p->ell_sorted ? 1 : 0);
+    const bool vec = p->ell_sorted && (ldM % 2 == 0) && (c0 % 2 == 0) && (reinterpret_cast<uintptr_t>(d_M) % 16 == 0);
+    if (vec)
+        cmix_mirror_fill_kernel<true><<<grid, 256, 0, stream>>>(d_M, ldM, n, (int)c0, (int)c1, rbase, p->d_es.p, div2Lp1,
+                                                                interchange, 1);
+    else
+        cmix_mirror_fill_kernel<false><<<grid, 256, 0, stream>>>(d_M, ldM, n, (int)c0, (int)c1, rbase, p->d_es.p,
+                                                                 div2Lp1, interchange, p->ell_sorted ? 1 : 0);
     SFB_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -119,6 +119,32 @@ def test_cmix_from_wrlm_matches_oracle(kw):
     assert relerr(got, ref) < RTOL
 
 
+# every tile class of the block kernels: nmax_l = 5 / 12 / 20 / 26 / 32 (1..4 row tiles of 8), 24 / 40 / 64 shells
+# (register-Z kernel with 4 or 8 radial tiles) and 72 shells (shared-memory-Z kernel), dense lnn tables
+@pytest.mark.parametrize("nmax,lmax,nr", [(5, 3, 24), (12, 3, 40), (20, 2, 64), (26, 2, 40), (32, 1, 64), (26, 1, 72)])
+@pytest.mark.parametrize("kw", [dict(), dict(div2Lp1=True, interchange_NN=True)])
+def test_cmix_tile_classes(nmax, lmax, nr, kw):
+    import warnings
+    from oracle import cref
+    sfb, oa, a, owm, wm, oc, c, rng = _setup(nmax=nmax, lmax=lmax, nr=nr, dnmax=None)
+    assert max(oa.nmax_l) == nmax
+    LMAX = 2 * oa.lmax
+    lmsize = (LMAX + 1) * (LMAX + 2) // 2
+    W = rng.standard_normal((nr, lmsize)) + 1j * rng.standard_normal((nr, lmsize))   # m-fast W_lm(r), any values
+    for l in range(LMAX + 1):
+        W[:, l * (l + 1) // 2] = W[:, l * (l + 1) // 2].real       # m = 0 coefficients of a real map are real
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        G = ow.rsdrgnlr(oa, owm)
+        got = sfb.power_win_mix_from_wrlm(W, None, wm, c, layout=1, **kw)
+    Wc = cref.calc_wrl_wrl(W, W, LMAX)
+    n = oc.lnn.shape[1]
+    ref = cref.calc_cmix_rows(oc.lnn, np.arange(1, n + 1), G, Wc, div2Lp1=kw.get("div2Lp1", False),
+                              interchange=kw.get("interchange_NN", False))
+    assert got.shape == (n, n)
+    assert relerr(got, ref) < RTOL
+
+
 @pytest.mark.parametrize("interchange", [False, True])
 def test_cmix_two_windows(interchange):
     sfb, oa, a, owm, wm, oc, c, rng = _setup(nmax=3, lmax=4, nr=37, dnmax=None)
