@@ -93,6 +93,15 @@ int32_t sfb_power_win_mix_binned(const double* win1, int64_t nr, int64_t npix_in
                                  const int64_t* v_rowval, const double* v_nzval, int64_t LNN2, int32_t div2Lp1,
                                  int32_t interchange_NN, double* N_out);
 
+/* win_lnn(win, wmodes, cmodes) (src/windows.jl:382-391, calc_intr_gg_fn :394-418): the shot-noise
+ * window W_lnn' = sum_r r^2 dr g_nl(r) g_n'l(r) Wr_00(r)/sqrt(4 pi), with Wr_00 = calc_Wr_lm(win, 2 lmax, nside)[:,1]
+ * ("need to be consistent", :386).  G = rsdrgnlr as for power_win_mix; Wlnn_out has lnnsize entries.  A negative
+ * Wr_00 is an error, as the reference takes its square root (:400).                                              */
+int32_t sfb_win_lnn(const double* win, int64_t nr, int64_t npix_in, int64_t ld_win, int64_t nside, const double* G,
+                    int64_t nmax, int64_t lmax, const int64_t* lnn, int64_t lnnsize, double* Wlnn_out);
+/* device-resident form: d_alm = planar W_lm(r) of sfb_calc_wr_lm_dev, d_Wlnn = nout doubles */
+int32_t sfb_win_lnn_dev(sfb_cmix_plan* plan, const double* d_alm, double* d_Wlnn, void* stream);
+
 /* separable window: power_win_mix(win1::SeparableArray, ..., w̃, v, ...)  src/windows.jl:809-814, 942-990
  *   (calc_angular_mixing_matrix :866-878, calc_radial_mixing :924-938, calc_cmixii_separable :651-679)
  *   phi : nr Float64, mask : npix_in Float64; binning arguments as above (NULL colptr = I)         */

@@ -50,6 +50,22 @@ function calc_Wr_lm(win::SeparableArray, LMAX::Integer, Wnside::Integer; niter=3
     return SeparableArray(win.phi, wlm, name1=:phi, name2=:wlm)
 end
 
+############################## win_lnn ##############################
+
+# src/windows.jl:382-391 (with calc_intr_gg_fn :394-418): shot-noise window from Wr_00 of the same stage 1
+function win_lnn(win::AbstractMatrix{Float64}, wmodes::ConfigurationSpaceModes, cmodes::ClnnModes)
+    win = win isa Matrix{Float64} ? win : Matrix{Float64}(win)
+    amodes = cmodes.amodes
+    G = rsdrgnlr(amodes, wmodes)
+    lnn = cmodes.lnn
+    nr, npix = size(win)
+    Wlnn = Vector{Float64}(undef, getlnnsize(cmodes))
+    GC.@preserve win G lnn Wlnn check(ccall((:sfb_win_lnn, libsfb), Int32,
+        (Ptr{Float64}, Int64, Int64, Int64, Int64, Ptr{Float64}, Int64, Int64, Ptr{Int64}, Int64, Ptr{Float64}),
+        win, nr, npix, stride(win, 2), amodes.nside, G, amodes.nmax, amodes.lmax, lnn, size(lnn, 2), Wlnn))
+    return Wlnn
+end
+
 ############################## power_win_mix ##############################
 
 power_win_mix(win, wmodes::ConfigurationSpaceModes, cmodes::ClnnModes; kwargs...) =

@@ -285,6 +285,25 @@ def power_win_mix(win1, win2, wmodes, cmodes, div2Lp1=False, interchange=False, 
 # ----------------------------------------------------------------------------
 # separable pieces
 
+def win_lnn(win, wmodes, cmodes):
+    """src/windows.jl:382-391 + calc_intr_gg_fn :394-418 (derivative=0).  nodes = r, weights = Δr (:568); the spline
+    through (r, Wr_00/√4π) evaluated at its own knots returns the knot values, so fn = Wr_00/√4π.  Literal operation
+    order: gnlr *= nodes √weights √fn, then the dot product per (l,n,n')."""
+    amodes = cmodes.amodes
+    Wr_00 = np.real(calc_Wr_lm(win, 2 * amodes.lmax, amodes.nside)[:, 0])
+    r, dr = window_r(wmodes)
+    fn = Wr_00 / math.sqrt(4 * math.pi)
+    if np.any(fn < 0):
+        raise ValueError("DomainError: sqrt of a negative Wr_00")
+    gnlr = precompute_gnlr(amodes, wmodes) * (r * math.sqrt(dr) * np.sqrt(fn))[:, None, None]
+    lnn = cmodes.lnn
+    out = np.empty(lnn.shape[1])
+    for i in range(lnn.shape[1]):
+        l, n, n_ = lnn[:, i]
+        out[i] = gnlr[:, n - 1, l] @ gnlr[:, n_ - 1, l]
+    return out
+
+
 def calc_angular_mixing_matrix(lmax, w1lm, w2lm):
     """src/windows.jl:866-878 (m-major alm of length lmsize(2 lmax))."""
     Wl = hp.alm2cl(w1lm, w2lm, 2 * lmax)

@@ -16,11 +16,11 @@ from .modes import (AnlmModes, ClnnBinnedModes, ClnnModes, bandpower_binning_wei
                     getlmsize, getlnn, getlnnsize, getnlm, getnlmsize)
 from .separable import SeparableArray
 from .windows import (ConfigurationSpaceModes, calc_Wr_lm, check_nsamp, optimize_Wr_lm_layout, power_win_mix,
-                      power_win_mix_from_wrlm, precompute_gnlr, rsdrgnlr, window_r)
+                      power_win_mix_from_wrlm, precompute_gnlr, rsdrgnlr, win_lnn, window_r)
 
 __all__ = [
     "AnlmModes", "ClnnModes", "ClnnBinnedModes", "bandpower_binning_weights", "estimate_nside", "getidx", "getlkk",
     "getlmsize", "getlnn", "getlnnsize", "getnlm", "getnlmsize", "SeparableArray", "ConfigurationSpaceModes",
     "calc_Wr_lm", "check_nsamp", "optimize_Wr_lm_layout", "power_win_mix", "power_win_mix_from_wrlm",
-    "precompute_gnlr", "rsdrgnlr", "window_r",
+    "precompute_gnlr", "rsdrgnlr", "win_lnn", "window_r",
 ]

@@ -405,6 +405,37 @@ int32_t sfb_power_win_mix_binned(const double* win1, int64_t nr, int64_t npix_in
     return 0;
 }
 
+int32_t sfb_win_lnn(const double* win, int64_t nr, int64_t npix_in, int64_t ld_win, int64_t nside, const double* G,
+                    int64_t nmax, int64_t lmax, const int64_t* lnn, int64_t lnnsize, double* Wlnn_out) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    SFB_REQUIRE(win && Wlnn_out, "null pointer");
+    PlanGuard pg;
+    SFB_TRY(get_cmix_plan(&pg.p, lnn, lnnsize, 1, G, nr, nmax, lmax));
+    DevBuf<double>&a1 = g_ws.alm1, &a2 = g_ws.alm2;
+    bool same = true;
+    SFB_TRY(windows_to_alm(win, nullptr, nr, npix_in, ld_win, nside, 2 * lmax, a1, a2, &same));
+    // Wr_00 / √(4π) enters under a square root in the reference (src/windows.jl:400): negative values throw there
+    std::vector<double> w00((size_t)nr);
+    SFB_CUDA_OK(cudaMemcpy(w00.data(), a1.p, (size_t)nr * sizeof(double), cudaMemcpyDeviceToHost));
+    for (double v : w00) {
+        if (!(v >= 0.0)) {
+            set_error("DomainError: sqrt of a negative Wr_00 in win_lnn (src/windows.jl:400)");
+            return 4;
+        }
+    }
+    DevBuf<double> d_out;
+    SFB_TRY(d_out.alloc((size_t)pg.p->nout));
+    SFB_TRY(win_lnn_run(pg.p, a1.p, d_out.p, 0));
+    g_times[6] += 1;
+    SFB_TRY(check_finite(d_out.p, (size_t)pg.p->nout, "Wlnn"));
+    SFB_CUDA_OK(cudaMemcpy(Wlnn_out, d_out.p, (size_t)pg.p->nout * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+int32_t sfb_win_lnn_dev(sfb_cmix_plan* plan, const double* d_alm, double* d_Wlnn, void* stream) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    return win_lnn_run(reinterpret_cast<CmixPlan*>(plan), d_alm, d_Wlnn, (cudaStream_t)stream);
+}
+
 int32_t sfb_power_win_mix_separable(const double* phi, const double* mask, int64_t nr, int64_t npix_in,
                                     int64_t nside, const double* G, int64_t nmax, int64_t lmax,
                                     const int64_t* lnn, int64_t lnnsize, const int64_t* wt_colptr,

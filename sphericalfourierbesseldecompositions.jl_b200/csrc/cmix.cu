@@ -623,6 +623,12 @@ int cmix_plan_create(CmixPlan** out, const int64_t* lnn, int64_t lnnsize, int64_
     rc = rc ? rc : up(p->d_nl_L, nl_L);
     rc = rc ? rc : up(p->d_nl_N, nl_N);
     rc = rc ? rc : up(p->d_es, es);
+    {   // output index -> CSR slot (n, n' of the row)
+        std::vector<int> slot_of_out((size_t)p->nout, 0);
+        for (size_t sl = 0; sl < p->h_row_out.size(); ++sl)
+            if (p->h_row_out[sl] >= 0) slot_of_out[p->h_row_out[sl]] = (int)sl;
+        rc = rc ? rc : up(p->d_slot_of_out, slot_of_out);
+    }
     if (p->ell_sorted) {  // upper-packed storage: column j keeps rows [0, rend(j)), rend = end of j's own l-block
         std::vector<int64_t> lend(lmax + 1, 0);
         for (int64_t o = 0; o < p->nout; ++o) lend[es[o] & 0x3fffffff] = o + 1;
@@ -957,6 +963,34 @@ std::vector<std::pair<int64_t, int64_t>> cmix_row_chunks_mirror(const CmixPlan* 
     }
     if (start < p->nout) out.emplace_back(start, p->nout);
     return out;
+}
+
+// =============================================================================================
+// win_lnn (src/windows.jl:382-418): W_lnn' = Σ_r [r √Δr g_nl(r)] [r √Δr g_n'l(r)] W_00(r)/√(4π), one warp per (l,n,n').
+// W_00(r) is the (l,m) = (0,0) coefficient of stage 1: the first re-plane of the planar alm buffer.
+__global__ void __launch_bounds__(256) win_lnn_kernel(const double* __restrict__ G, const double* __restrict__ alm,
+                                                      const int* __restrict__ es, const int* __restrict__ slot_of_out,
+                                                      const int* __restrict__ row_n, const int* __restrict__ row_n2,
+                                                      int nmax, int nrp, int nout, double* __restrict__ out) {
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i >= nout) return;
+    const int l = es[i] & 0x3fffffff, s = slot_of_out[i];
+    const double* g1 = G + ((size_t)l * nmax + row_n[s]) * nrp;
+    const double* g2 = G + ((size_t)l * nmax + row_n2[s]) * nrp;
+    double acc = 0.0;
+    for (int r = lane; r < nrp; r += 32) acc = fma(g1[r] * g2[r], alm[r], acc);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) out[i] = acc * 0.28209479177387814;  // 1/√(4π)
+}
+
+int win_lnn_run(CmixPlan* p, const double* d_alm, double* d_out, cudaStream_t stream) {
+    SFB_REQUIRE(p && d_alm && d_out, "win_lnn: null pointer");
+    const int n = (int)p->nout;
+    win_lnn_kernel<<<(unsigned)ceil_div((int64_t)n * 32, 256), 256, 0, stream>>>(
+        p->d_G.p, d_alm, p->d_es.p, p->d_slot_of_out.p, p->d_row_n.p, p->d_row_n2.p, p->nmax, p->nrp, n, d_out);
+    SFB_CUDA_OK(cudaGetLastError());
+    return 0;
 }
 
 // =============================================================================================

@@ -6,6 +6,7 @@
 //   calc_cmixlnnLNN!    src/windows.jl:613-627   -> what_build_kernel + cmix_block_kernel
 //   calc_cmix           src/windows.jl:700-746   -> cmix_block_kernel epilogue (N<->N' partner, flags)
 //   _power_win_mix      src/windows.jl:825-862   -> csr/csc products in binned.cu
+//   win_lnn             src/windows.jl:382-418   -> win_lnn_kernel
 #pragma once
 #include "common.cuh"
 #include <utility>
@@ -39,6 +40,7 @@ struct CmixPlan {
     DevBuf<int> d_ell_list;           // per-launch list of ells
     DevBuf<int> d_chunks;             // per-launch (L, N0, N1) chunk lists
     DevBuf<int> d_what_ells;          // l-blocks whose Ŵ is built for the current row shard
+    DevBuf<int> d_slot_of_out;        // output index -> CSR slot
     DevBuf<int> d_es;                 // per output index: l | [n≠n'] << 30 (mirror fill)
     bool ell_sorted = false;          // l non-decreasing in output order
     std::vector<long long> h_colbase; // upper-packed storage: element offset of column j (nout + 1 entries), ell_sorted only
@@ -92,6 +94,9 @@ int cmix_mirror_fill(CmixPlan* p, int64_t c0, int64_t c1, int div2Lp1, int inter
 std::vector<std::pair<int64_t, int64_t>> cmix_row_chunks_mirror(const CmixPlan* p, int k);
 // column ranges of roughly equal cost (L-block aligned) for pipelining compute with the D2H of finished slabs
 std::vector<std::pair<int64_t, int64_t>> cmix_col_chunks(const CmixPlan* p, int k);
+
+// win_lnn (src/windows.jl:382-418) from the planar alm of stage 1: out[i] = Σ_r G_ln G_ln' W_00(r)/√(4π), nout values
+int win_lnn_run(CmixPlan* p, const double* d_alm, double* d_out, cudaStream_t stream);
 
 // Host complex (nr x lmsize, column-major, interleaved) -> device planar alm; layout 0 = m-major, 1 = m-fast.
 int alm_from_host(const double* h_wrlm, int64_t nr, int lmax2, int layout, DevBuf<double>& d_alm, int nrp,

@@ -248,6 +248,23 @@ def _power_win_mix_binned(win1, win2, wt, v, wmodes, bcmodes, div2Lp1, interchan
     return N
 
 
+def win_lnn(win, wmodes, cmodes):
+    """win_lnn(win, wmodes, cmodes) (src/windows.jl:382-391): shot-noise window W_lnn' from Wr_00(r) of the same
+    calc_Wr_lm the coupling matrix uses.  Returns a vector of lnnsize values."""
+    lib = _lib.load()
+    amodes, G, lnn = _mode_tables(cmodes, wmodes)
+    if isinstance(win, SeparableArray):
+        win = np.outer(win.phi, win.mask)
+    w = _as_julia_matrix(win)
+    nr, npix = w.shape
+    if nr != wmodes.nr:
+        raise ValueError("window has %d shells, wmodes.nr = %d" % (nr, wmodes.nr))
+    out = np.empty(lnn.shape[1], dtype=np.float64)
+    _lib.check(lib.sfb_win_lnn(_lib.ptr(w), nr, npix, w.strides[1] // 8, amodes.nside, _lib.ptr(G), amodes.nmax,
+                               amodes.lmax, _lib.ptr(lnn), lnn.shape[1], _lib.ptr(out)))
+    return out
+
+
 def power_win_mix_from_wrlm(W1r_lm, W2r_lm, wmodes, cmodes, layout=LAYOUT_MMAJOR, div2Lp1=False, interchange_NN=False,
                             lnn_min=1):
     """calc_Wrl_Wrl + calc_cmix from precomputed W_lm(r) (src/windows.jl:796-801): the stage-2/3 entry point."""

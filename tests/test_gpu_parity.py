@@ -172,6 +172,24 @@ def test_power_win_mix_end_to_end_kmax():
     assert np.abs(K - K.T).max() / np.abs(K).max() < 1e-11   # symmetry identity, SURVEY §8c.5
 
 
+def test_win_lnn_matches_oracle():
+    # win_lnn (src/windows.jl:382-418) on the Wr_00 of the same stage 1
+    from sfb_b200 import _lib
+    sfb, oa, a, owm, wm, oc, c, rng = _setup(kmax=0.03, nr=40, dnmax=None)
+    win, _, _ = _random_window(rng, owm, smooth=False)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        got = sfb.win_lnn(win, wm, c)
+    ref = ow.win_lnn(win, owm, oc)
+    assert got.shape == ref.shape == (oc.lnn.shape[1],)
+    assert relerr(got, ref) < RTOL
+    with pytest.raises(_lib.SFBError, match="DomainError"):      # sqrt of a negative Wr_00 throws in the reference
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            sfb.win_lnn(-win, wm, c)
+
+
 def test_no_window_is_identity():
     # test/test_windows.jl:181-213: full sky => M ≈ I, atol 1e-3
     sfb, oa, a, owm, wm, oc, c, rng = _setup(nmax=3, lmax=5, nr=1000)

@@ -127,3 +127,27 @@ def test_analytic_ell0_expmrr0():
     M0[np.ix_(idx0, idx0)] = T1
     assert relerr(M, M0) < 1.1e-6
     assert relerr(M[np.ix_(idx0, idx0)], T1) < 2e-6
+
+
+def test_win_lnn_analytic_ell0_expmrr0():
+    # test/test_windows.jl:259-297: win_lnn's l=0 entries equal the analytic W0nn for phi = exp(-r/r0), rmin=0 (rtol 1e-6)
+    a = om.AnlmModes(0.01, 0.0, 1000.0)
+    wm = ow.ConfigurationSpaceModes(0.0, 1000.0, 2032, a.nside)
+    c = om.ClnnModes(a)
+    win = ow.make_window(wm, "radial_expmrr0", "fullsky")
+    wlnn = ow.win_lnn(win.dense() if hasattr(win, "dense") else win, wm, c)
+    W0 = _W0nn_expmrr0(wm, a)
+    got = np.zeros_like(W0)
+    for i in np.flatnonzero(c.lnn[0] == 0):      # get_0nn, src/utils.jl:44-54
+        n1, n2 = c.lnn[1, i], c.lnn[2, i]
+        got[n1 - 1, n2 - 1] = got[n2 - 1, n1 - 1] = wlnn[i]
+    assert relerr(got, W0) < 1e-6
+
+
+def test_win_lnn_full_sky_is_identity():
+    # Wr_00 = sqrt(4 pi) for the full sky, so W_lnn' = sum_r r^2 dr g_nl g_n'l = delta_nn' (test/test_gnl.jl:27-41)
+    a = om.AnlmModes(3, 4, 500.0, 1000.0)
+    wm = ow.ConfigurationSpaceModes(500.0, 1000.0, 1000, a.nside)
+    c = om.ClnnModes(a)
+    wlnn = ow.win_lnn(np.ones((wm.nr, wm.npix)), wm, c)
+    assert np.allclose(wlnn, (c.lnn[1] == c.lnn[2]).astype(float), atol=1e-5)
