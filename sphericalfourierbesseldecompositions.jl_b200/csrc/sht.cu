@@ -861,9 +861,14 @@ __global__ void __launch_bounds__(kT) legendre_analysis_kernel(const double* __r
 
 // G_m(ring)[c] = Σ_l λ_lm(θ) a_lm[c]: north = E + O, south = E - O    CTA = (m, 64 north rings, BW columns)
 template <int NI>
-__global__ void __launch_bounds__(kT) legendre_synthesis_kernel(const double* __restrict__ alm,
+__global__ void __launch_bounds__(kT, 2) legendre_synthesis_kernel(const double* __restrict__ alm,
                                                                 const double* __restrict__ lam, int nrings, int nhalf,
-                                                                int lmax, int nrp, double* __restrict__ G) {
+                                                                int lmax, int nrp, double* __restrict__ G,
+                                                                double* __restrict__ F2,
+                                                                const int* __restrict__ nphi_tab) {
+    // F2 (optional): rings with nφ > 2 lmax have no aliases, their re-analysed Fourier coefficients are F'_m = nφ G_m
+    // (imaginary part of m = 0 dropped; see ring_alias_kernel), so they are written there directly and the alias pass
+    // only visits the short polar rings.
     constexpr int BW = ColTile<NI>::BW, LD = ColTile<NI>::LD;
     __shared__ double Ls[32 * kLdB];  // [l (16 even-parity, 16 odd-parity)][ring]
     __shared__ double Bs[32 * LD];
@@ -913,22 +918,26 @@ __global__ void __launch_bounds__(kT) legendre_synthesis_kernel(const double* __
         warp_gemm_ts<2, NI>(accO, Ls + 16 * kLdB + wm * 16, kLdB, Bs + 16 * LD + wn * 8 * NI, LD, 16);
         __syncthreads();
     }
-    double* Gm = G + (size_t)m * nrings * ncol;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
         const int k = k0 + wm * 16 + i * 8 + g;
         if (k >= nhalf) continue;
+        const int nph = F2 ? nphi_tab[k] : 0;
+        const bool direct = nph > 2 * lmax;
+        const double sc = direct ? (double)nph : 1.0;
+        double* Gm = (direct ? F2 : G) + (size_t)m * nrings * ncol;
         double* dn = Gm + (size_t)k * ncol + c0;
         double* ds = Gm + (size_t)(nrings - 1 - k) * ncol + c0;
 #pragma unroll
         for (int j = 0; j < NI; ++j) {
             const int col = wn * 8 * NI + j * 8 + 2 * t;
             if (c0 + col < ncol) {
-                dn[col] = accE[i][j][0] + accO[i][j][0];
-                dn[col + 1] = accE[i][j][1] + accO[i][j][1];
+                const double z = (direct && m == 0 && c0 + col >= nrp) ? 0.0 : sc;  // nrp is even: col, col+1 same plane
+                dn[col] = z * (accE[i][j][0] + accO[i][j][0]);
+                dn[col + 1] = z * (accE[i][j][1] + accO[i][j][1]);
                 if (k != nhalf - 1) {
-                    ds[col] = accE[i][j][0] - accO[i][j][0];
-                    ds[col + 1] = accE[i][j][1] - accO[i][j][1];
+                    ds[col] = z * (accE[i][j][0] - accO[i][j][0]);
+                    ds[col + 1] = z * (accE[i][j][1] - accO[i][j][1]);
                 }
             }
         }
@@ -948,6 +957,7 @@ __global__ void ring_alias_kernel(const double* __restrict__ G, double* __restri
                                   const int* __restrict__ shift_tab, int nrings, int lmax, int nrp) {
     const int ring = blockIdx.x, m = blockIdx.y;
     const int n = nphi_tab[ring];
+    if (n > 2 * lmax) return;  // alias free: F' = nφ G was written by legendre_synthesis_kernel
     const double sig = shift_tab[ring] ? -1.0 : 1.0;
     const size_t stride_m = (size_t)nrings * 2 * nrp;
     const double* g = G + (size_t)ring * 2 * nrp;
@@ -1202,15 +1212,19 @@ int sht_map2alm(ShtPlan* p, const double* d_win, int64_t ldw, int niter, double*
     RingTabs rt{p->d_nphi.p, p->d_start.p, p->d_shift.p, p->d_twoff.p, p->d_tw.p};
     const double w = 4.0 * 3.14159265358979323846 / (double)p->npix;
     const bool pixel_iter = getenv("SFB_SHT_PIXEL_ITER") != nullptr;  // cross-check: refine through pixel space
-    auto legendre_synthesis = [&]() -> int {
+    auto legendre_synthesis = [&](bool ring_iter) -> int {
+        double* f2 = ring_iter ? p->d_F2.p : nullptr;
         const int nil = pick_ni(2 * p->nrp);
         dim3 gs(p->lmax + 1, (unsigned)ceil_div(p->nhalf, 64), (unsigned)ceil_div(2 * p->nrp, 16 * nil));
         if (nil == 4)
-            legendre_synthesis_kernel<4><<<gs, kT, 0, st>>>(d_alm, p->d_lam.p, p->nrings, p->nhalf, p->lmax, p->nrp, p->d_FG.p);
+            legendre_synthesis_kernel<4><<<gs, kT, 0, st>>>(d_alm, p->d_lam.p, p->nrings, p->nhalf, p->lmax, p->nrp, p->d_FG.p,
+                                                            f2, p->d_nphi.p);
         else if (nil == 2)
-            legendre_synthesis_kernel<2><<<gs, kT, 0, st>>>(d_alm, p->d_lam.p, p->nrings, p->nhalf, p->lmax, p->nrp, p->d_FG.p);
+            legendre_synthesis_kernel<2><<<gs, kT, 0, st>>>(d_alm, p->d_lam.p, p->nrings, p->nhalf, p->lmax, p->nrp, p->d_FG.p,
+                                                            f2, p->d_nphi.p);
         else
-            legendre_synthesis_kernel<1><<<gs, kT, 0, st>>>(d_alm, p->d_lam.p, p->nrings, p->nhalf, p->lmax, p->nrp, p->d_FG.p);
+            legendre_synthesis_kernel<1><<<gs, kT, 0, st>>>(d_alm, p->d_lam.p, p->nrings, p->nhalf, p->lmax, p->nrp, p->d_FG.p,
+                                                            f2, p->d_nphi.p);
         SFB_CUDA_OK(cudaGetLastError());
         p->launches += 1;
         return 0;
@@ -1224,7 +1238,7 @@ int sht_map2alm(ShtPlan* p, const double* d_win, int64_t ldw, int niter, double*
         SFB_TRY(run_legendre_analysis(p, p->d_FG.p, w, 0, nullptr, p->d_a0.p, st));
         SFB_CUDA_OK(cudaMemcpyAsync(d_alm, p->d_a0.p, nalm * sizeof(double), cudaMemcpyDeviceToDevice, st));
         for (int it = 0; it < niter; ++it) {
-            SFB_TRY(legendre_synthesis());
+            SFB_TRY(legendre_synthesis(true));
             ring_alias_kernel<<<dim3(p->nrings, p->lmax + 1), 64, 0, st>>>(p->d_FG.p, p->d_F2.p, p->d_nphi.p, p->d_shift.p,
                                                                           p->nrings, p->lmax, p->nrp);
             SFB_CUDA_OK(cudaGetLastError());
@@ -1235,7 +1249,7 @@ int sht_map2alm(ShtPlan* p, const double* d_win, int64_t ldw, int niter, double*
     SFB_TRY(run_analysis(p, map, ldm, 0, d_alm, st));
     if (niter > 0) SFB_TRY(p->d_resid.alloc((size_t)p->npix * p->nrp));
     for (int it = 0; it < niter; ++it) {
-        SFB_TRY(legendre_synthesis());
+        SFB_TRY(legendre_synthesis(false));
         if (p->ntiles > 0) {
             dim3 gr(p->ntiles, (unsigned)ceil_div(p->nrp, 64));
             ring_synthesis_kernel<<<gr, kT, 0, st>>>(p->d_FG.p, rt, p->d_tile_ring.p, p->d_tile_j0.p, p->nrings,
