@@ -56,8 +56,9 @@ __global__ void w3j000sq_table_kernel(double* __restrict__ w2, int lmax) {
 // W[L1][i][j] = Σ_{M>=0} (2-δ_M0) Re(W1[i,L1M] conj W2[j,L1M])      (src/windows.jl:682-696)
 __global__ void __launch_bounds__(256) wl_build_kernel(const double* __restrict__ alm1, const double* __restrict__ alm2,
                                                        double* __restrict__ W, int LMAX, int nrp) {
-    // each thread owns a 4 x 4 block of (i, j): 16 loads feed 32 FMAs per M
-    const int L1 = blockIdx.x;
+    // each thread owns a 4 x 4 block of (i, j): 16 loads feed 32 FMAs per M; the M loop is unrolled so that several
+    // M's loads are in flight (the longest CTA, L1 = LMAX, is the critical path: heaviest L1 first)
+    const int L1 = LMAX - blockIdx.x;
     const int nb = nrp / 4;  // nrp is a multiple of 8
     for (int blk = threadIdx.x; blk < nb * nb; blk += blockDim.x) {
         const int i0 = (blk / nb) * 4, j0 = (blk % nb) * 4;
@@ -66,6 +67,7 @@ __global__ void __launch_bounds__(256) wl_build_kernel(const double* __restrict_
         for (int a = 0; a < 4; ++a)
 #pragma unroll
             for (int b = 0; b < 4; ++b) s[a][b] = 0.0;
+#pragma unroll 4
         for (int M = 0; M <= L1; ++M) {
             const size_t lm = (size_t)L1 + ((size_t)M * (2 * LMAX + 1 - M)) / 2;
             const double* a1 = alm1 + lm * 2 * nrp;
