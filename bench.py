@@ -397,7 +397,8 @@ def run_b200(args):
                         "hbm_peak_gbs": peaks.get("hbm_gbs"),
                         "frac": (8.0 * n * n / (fill_ms * 1e-3) / 1e9 / peaks["hbm_gbs"])
                         if (fill_ms > 0 and peaks.get("hbm_gbs")) else None,
-                        "traffic": traffic.get("cmix_mirror_fill_kernel", {}).get("traffic_bytes") if world == 1 else None},
+                        "traffic": (sum(v["traffic_bytes"] for k, v in traffic.items()
+                                        if k.startswith("cmix_mirror_fill_kernel")) or None) if world == 1 else None},
         "stage1": {"ms": stage1_ms, "alg_tflops": wl.flops_alg_stage1() / (stage1_ms * 1e-3) / 1e12,
                    "alg_gbs": wl.bytes_alg_stage1() / (stage1_ms * 1e-3) / 1e9,
                    "hbm_peak_gbs": peaks.get("hbm_gbs"), "hbm_frac": (wl.bytes_alg_stage1() / (stage1_ms * 1e-3) / 1e9 /
