@@ -173,6 +173,92 @@ __global__ void __launch_bounds__(256) what_build_kernel(const double* __restric
 }
 
 // =============================================================================================
+// Ŵ on the FP64 tensor cores: for one ℓ the L1 sum is the banded GEMM  Ŵ_ℓ[L][e] = Σ_{L1} A_ℓ[L][L1] · W[L1][e],
+// A_ℓ[L][L1] = (ℓ L L1;000)² (zero outside the triangle and for the wrong parity), e = (r, r') flattened.
+// CTA = (ℓ, 32 L's of one parity = 4 DMMA row tiles, 256 e's: 4 warps x 64, three CTAs per SM); every W element fetched from L2 feeds 32 L's (the FMA
+// kernel above: 8), and the contraction runs over the union of the 32 triangles only, in steps of four L1 of the right
+// parity.  A lives in shared memory (row stride ≡ 4 mod 16: conflict-free fragment loads), B fragments come straight
+// from L2 with the next k-step's eight loads in flight.
+constexpr int kWhatRows = 32;   // L values (same parity) per CTA
+__global__ void __launch_bounds__(128, 3) what_build_dmma_kernel(const double* __restrict__ W, const double* __restrict__ w2,
+                                                              double* __restrict__ What, const int* __restrict__ ells,
+                                                              int ell0, int lmax, int nrp, int Llo, int Lhi, int mirror,
+                                                              int SW) {
+    extern __shared__ double wsm[];  // [kWhatRows][SW], column h <-> L1 = par + 2h
+    const int ell = ells[blockIdx.y];
+    const int gi = blockIdx.x, p = gi & 1, base = (gi >> 1) * (2 * kWhatRows) + p;
+    const int last = base + 2 * (kWhatRows - 1);
+    if (base > Lhi || last < Llo || base > lmax) return;
+    if (mirror && last < ell) return;  // only L >= l blocks are formed
+    const int par = (ell + p) & 1;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    for (int x = tid; x < kWhatRows * SW; x += blockDim.x) wsm[x] = 0.0;
+    __syncthreads();
+    int L1lo = 1 << 30, L1hi = -1;
+    for (int q = 0; q < kWhatRows; ++q) {
+        const int L = base + 2 * q;
+        if (L > lmax) break;
+        if ((mirror && L < ell) || L < Llo || L > Lhi) continue;   // rows nobody reads stay zero
+        const int lo = min(ell, L), d = abs(ell - L);
+        L1lo = min(L1lo, d);
+        L1hi = max(L1hi, ell + L);
+        const double* src = w2 + ((size_t)ell * (lmax + 1) + L) * (lmax + 1);
+        for (int k = tid; k <= lo; k += blockDim.x) wsm[q * SW + ((d + 2 * k - par) >> 1)] = src[k];
+    }
+    __syncthreads();
+    if (L1hi < 0) return;
+    const int n2 = nrp * nrp;
+    const int e0 = (blockIdx.z * 4 + warp) * 64;
+    if (e0 >= n2) return;
+    const int hlo = (L1lo - par) >> 1, hhi = (L1hi - par) >> 1;
+    const int nks = (hhi - hlo + 4) / 4;   // k-steps of four L1 values (h, h+1, h+2, h+3)
+    // row tiles that hold at least one wanted L
+    bool live[4];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+        const int Lf = base + 2 * (mt * 8), Ll = min(base + 2 * (mt * 8 + 7), lmax - ((lmax - base) & 1));
+        live[mt] = (Lf <= lmax) && !(mirror && Ll < ell) && !(Ll < Llo || Lf > Lhi);
+    }
+    double acc[4][8][2];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[mt][j][0] = acc[mt][j][1] = 0.0;
+    const double* Wb = W + e0 + g;
+    auto loadB = [&](int ks, double (&b)[8]) {
+        const int L1 = par + 2 * (hlo + 4 * ks + t);
+        const bool ok = (L1 <= 2 * lmax);
+        const double* src = Wb + (size_t)(ok ? L1 : 0) * n2;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) b[j] = ok ? __ldg(src + 8 * j) : 0.0;
+    };
+    double bcur[8], bnxt[8];
+    loadB(0, bcur);
+    for (int ks = 0; ks < nks; ++ks) {
+        if (ks + 1 < nks) loadB(ks + 1, bnxt);
+        const double* arow = wsm + g * SW + hlo + 4 * ks + t;
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+            if (!live[mt]) continue;
+            const double a = arow[mt * 8 * SW];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dmma884(acc[mt][j], a, bcur[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bcur[j] = bnxt[j];
+    }
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+        if (!live[mt]) continue;
+        const int L = base + 2 * (mt * 8 + g);
+        if (L > lmax) continue;
+        double* dst = What + ((size_t)(ell - ell0) * (lmax + 1) + L) * n2 + e0 + 2 * t;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) *reinterpret_cast<double2*>(dst + 8 * j) = make_double2(acc[mt][j][0], acc[mt][j][1]);
+    }
+}
+
+// =============================================================================================
 // Coupling-matrix block kernel.  One CTA = (ℓ, L, chunk of N values [N0,N1)), 8 warps:
 //   Z_N[n][r']   = Σ_r  G_ℓn[r] G_LN[r] Ŵ_ℓL[r][r']   for every N of the chunk     (DMMA, kept in shared memory)
 //   T_N,N'[n][n'] = Σ_r' Z_N[n][r'] G_LN'[r'] G_ℓn'[r']  for N' >= N               (DMMA, a × a × nr tiles; the
@@ -784,8 +870,21 @@ int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp
         SFB_TRY(p->d_what_ells.alloc(lmax + 1));
         SFB_CUDA_OK(cudaMemcpyAsync(p->d_what_ells.p, wells.data(), wells.size() * sizeof(int), cudaMemcpyHostToDevice,
                                     stream));
-        what_build_kernel<<<dim3(ngroups, (unsigned)wells.size()), 256, kWhatGroup * (lmax + 1) * sizeof(double), stream>>>(
-            p->d_W.p, p->d_w2.p, p->d_What.p, p->d_what_ells.p, ell0, lmax, nrp, Llo, Lhi, upper ? 1 : 0);
+        if (getenv("SFB_WHAT_FMA") == nullptr && (nrp * nrp) % 64 == 0) {
+            const int SW = (int)round_up(lmax + 4, 16) + 4;   // >= lmax + 4 columns, ≡ 4 (mod 16)
+            const size_t wsm_bytes = (size_t)kWhatRows * SW * sizeof(double);
+            SFB_REQUIRE(wsm_bytes <= 200 * 1024, "what_build: lmax too large for the shared-memory 3j tile");
+            SFB_CUDA_OK(cudaFuncSetAttribute(what_build_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)wsm_bytes));
+            const int ng32 = 2 * (int)ceil_div(lmax + 1, 2 * kWhatRows);
+            what_build_dmma_kernel<<<dim3(ng32, (unsigned)wells.size(), (unsigned)ceil_div(nrp * nrp, 256)), 128, wsm_bytes,
+                                     stream>>>(p->d_W.p, p->d_w2.p, p->d_What.p, p->d_what_ells.p, ell0, lmax, nrp, Llo,
+                                               Lhi, upper ? 1 : 0, SW);
+        } else {
+            what_build_kernel<<<dim3(ngroups, (unsigned)wells.size()), 256, kWhatGroup * (lmax + 1) * sizeof(double),
+                                stream>>>(p->d_W.p, p->d_w2.p, p->d_What.p, p->d_what_ells.p, ell0, lmax, nrp, Llo, Lhi,
+                                          upper ? 1 : 0);
+        }
         SFB_CUDA_OK(cudaGetLastError());
         p->launches++;
         SFB_CUDA_OK(cudaEventRecord(e1, stream));
