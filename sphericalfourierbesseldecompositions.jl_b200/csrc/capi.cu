@@ -30,6 +30,9 @@ struct Trace {
 
 static std::mutex g_mutex;  // one call at a time (the Julia side calls from one task and blocks)
 static double g_times[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+// plans whose last (device-resident, asynchronous) run has unread timing events: resolved by sfb_get_timings
+static ShtPlan* g_pend_sht = nullptr;
+static CmixPlan* g_pend_cmix = nullptr;
 
 // ---- cached stage-1 plan (tables depend only on nside/lmax/nr) ----
 static ShtPlan* g_sht = nullptr;
@@ -115,6 +118,17 @@ static void record_cmix_times(const CmixPlan* p) {
     g_times[5] = p->flops_executed;
     g_times[6] += p->launches;
 }
+
+// Device-resident entry points: run without a host sync and leave the timing events to sfb_get_timings.
+static bool async_enabled() { return getenv("SFB_SYNC_TIMINGS") == nullptr; }   // SFB_SYNC_TIMINGS=1: sync per call
+#define SFB_CMIX_RUN_ASYNC(plan_, call_)            \
+    do {                                            \
+        (plan_)->async_times = async_enabled();     \
+        const int rc__ = (call_);                   \
+        (plan_)->async_times = false;               \
+        if (rc__ != 0) return rc__;                 \
+        g_pend_cmix = (plan_);                      \
+    } while (0)
 
 // Device workspace reused across host-pointer calls (cudaMalloc / cudaFree of multi-GB buffers is slow).
 struct Workspace {
@@ -296,7 +310,20 @@ int32_t sfb_set_device(int32_t device) {
 }
 
 int32_t sfb_get_timings(double* out, int32_t n) {
+    std::lock_guard<std::mutex> lk(g_mutex);
     SFB_REQUIRE(out && n >= 0, "bad arguments");
+    if (g_pend_sht) {
+        SFB_TRY(sht_resolve_times(g_pend_sht));
+        g_times[0] = g_pend_sht->t_total;
+        g_pend_sht = nullptr;
+    }
+    if (g_pend_cmix) {
+        SFB_TRY(cmix_resolve_times(g_pend_cmix));
+        const double launches = g_times[6];
+        record_cmix_times(g_pend_cmix);
+        g_times[6] = launches;
+        g_pend_cmix = nullptr;
+    }
     for (int i = 0; i < n && i < 8; ++i) out[i] = g_times[i];
     return 0;
 }
@@ -506,6 +533,7 @@ int32_t sfb_sht_plan_create(sfb_sht_plan** plan, int64_t nside_in, int64_t nside
 }
 int32_t sfb_sht_plan_destroy(sfb_sht_plan* plan) {
     std::lock_guard<std::mutex> lk(g_mutex);
+    if (g_pend_sht == reinterpret_cast<ShtPlan*>(plan)) g_pend_sht = nullptr;
     sht_plan_destroy(reinterpret_cast<ShtPlan*>(plan));
     return 0;
 }
@@ -517,8 +545,12 @@ int32_t sfb_calc_wr_lm_dev(sfb_sht_plan* plan, const double* d_win, int64_t ld_w
                            void* stream) {
     std::lock_guard<std::mutex> lk(g_mutex);
     auto* p = reinterpret_cast<ShtPlan*>(plan);
-    SFB_TRY(sht_map2alm(p, d_win, ld_win, (int)niter, d_alm, (cudaStream_t)stream));
-    g_times[0] = p->t_total;
+    SFB_REQUIRE(p, "null plan");
+    p->async_times = async_enabled();   // no host sync: the caller can enqueue stage 2+3 behind stage 1
+    const int rc = sht_map2alm(p, d_win, ld_win, (int)niter, d_alm, (cudaStream_t)stream);
+    p->async_times = false;
+    SFB_TRY(rc);
+    g_pend_sht = p;
     g_times[6] = p->launches;
     return 0;
 }
@@ -535,6 +567,7 @@ int32_t sfb_cmix_plan_create(sfb_cmix_plan** plan, const int64_t* lnn, int64_t l
 }
 int32_t sfb_cmix_plan_destroy(sfb_cmix_plan* plan) {
     std::lock_guard<std::mutex> lk(g_mutex);
+    if (g_pend_cmix == reinterpret_cast<CmixPlan*>(plan)) g_pend_cmix = nullptr;
     cmix_plan_destroy(reinterpret_cast<CmixPlan*>(plan));
     return 0;
 }
@@ -543,11 +576,11 @@ int32_t sfb_power_win_mix_dev(sfb_cmix_plan* plan, const double* d_alm1, const d
                               void* stream) {
     std::lock_guard<std::mutex> lk(g_mutex);
     auto* p = reinterpret_cast<CmixPlan*>(plan);
+    SFB_REQUIRE(p, "null plan");
     const double t0 = g_times[6];
     const bool mirror = (d_alm1 == d_alm2) && row_lo == 0 && row_hi == p->nout && ldM >= p->nout && mirror_enabled();
-    SFB_TRY(cmix_run(p, d_alm1, d_alm2, div2Lp1, interchange_NN, row_lo, row_hi, 0, p->nout, d_M, ldM,
-                     (cudaStream_t)stream, nullptr, 0, false, mirror));
-    record_cmix_times(p);
+    SFB_CMIX_RUN_ASYNC(p, cmix_run(p, d_alm1, d_alm2, div2Lp1, interchange_NN, row_lo, row_hi, 0, p->nout, d_M, ldM,
+                                   (cudaStream_t)stream, nullptr, 0, false, mirror));
     g_times[6] = t0 + p->launches;
     return 0;
 }
@@ -556,10 +589,10 @@ int32_t sfb_power_win_mix_block_dev(sfb_cmix_plan* plan, const double* d_alm1, c
                                     int64_t col_hi, double* d_M, int64_t ldM, void* stream) {
     std::lock_guard<std::mutex> lk(g_mutex);
     auto* p = reinterpret_cast<CmixPlan*>(plan);
+    SFB_REQUIRE(p, "null plan");
     const double t0 = g_times[6];
-    SFB_TRY(cmix_run(p, d_alm1, d_alm2, div2Lp1, interchange_NN, row_lo, row_hi, col_lo, col_hi, d_M, ldM,
-                     (cudaStream_t)stream));
-    record_cmix_times(p);
+    SFB_CMIX_RUN_ASYNC(p, cmix_run(p, d_alm1, d_alm2, div2Lp1, interchange_NN, row_lo, row_hi, col_lo, col_hi, d_M, ldM,
+                                   (cudaStream_t)stream));
     g_times[6] = t0 + p->launches;
     return 0;
 }
@@ -577,9 +610,8 @@ int32_t sfb_power_win_mix_dev_peers(sfb_cmix_plan* plan, const double* d_alm1, c
         peers[i] = peer_M_full[i] + row_lo;
     }
     const double t0 = g_times[6];
-    SFB_TRY(cmix_run(p, d_alm1, d_alm2, div2Lp1, interchange_NN, row_lo, row_hi, 0, p->nout, d_M_full + row_lo, ldM,
-                     (cudaStream_t)stream, peers, npeers));
-    record_cmix_times(p);
+    SFB_CMIX_RUN_ASYNC(p, cmix_run(p, d_alm1, d_alm2, div2Lp1, interchange_NN, row_lo, row_hi, 0, p->nout,
+                                   d_M_full + row_lo, ldM, (cudaStream_t)stream, peers, npeers));
     g_times[6] = t0 + p->launches;
     return 0;
 }
@@ -674,9 +706,8 @@ int32_t sfb_power_win_mix_upper_packed_dev(sfb_cmix_plan* plan, const double* d_
     auto* p = reinterpret_cast<CmixPlan*>(plan);
     SFB_REQUIRE(p && d_alm && d_packed, "null pointer");
     const double t0 = g_times[6];
-    SFB_TRY(cmix_run(p, d_alm, d_alm, div2Lp1, interchange_NN, 0, p->nout, col_lo, col_hi, d_packed, p->nout,
-                     (cudaStream_t)stream, nullptr, 0, false, false, true));
-    record_cmix_times(p);
+    SFB_CMIX_RUN_ASYNC(p, cmix_run(p, d_alm, d_alm, div2Lp1, interchange_NN, 0, p->nout, col_lo, col_hi, d_packed, p->nout,
+                                   (cudaStream_t)stream, nullptr, 0, false, false, true));
     g_times[6] = t0 + p->launches;
     return 0;
 }

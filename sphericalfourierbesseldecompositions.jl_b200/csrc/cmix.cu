@@ -175,11 +175,12 @@ __global__ void __launch_bounds__(256) what_build_kernel(const double* __restric
 // =============================================================================================
 // Ŵ on the FP64 tensor cores: for one ℓ the L1 sum is the banded GEMM  Ŵ_ℓ[L][e] = Σ_{L1} A_ℓ[L][L1] · W[L1][e],
 // A_ℓ[L][L1] = (ℓ L L1;000)² (zero outside the triangle and for the wrong parity), e = (r, r') flattened.
-// CTA = (ℓ, 32 L's of one parity = 4 DMMA row tiles, 256 e's: 4 warps x 64, three CTAs per SM); every W element fetched from L2 feeds 32 L's (the FMA
+// CTA = (ℓ, 32 L's of one parity = 4 DMMA row tiles, 1024 e's: 4 warps x 4 tiles of 64, three CTAs per SM); every W element fetched from L2 feeds 32 L's (the FMA
 // kernel above: 8), and the contraction runs over the union of the 32 triangles only, in steps of four L1 of the right
 // parity.  A lives in shared memory (row stride ≡ 4 mod 16: conflict-free fragment loads), B fragments come straight
 // from L2 with the next k-step's eight loads in flight.
 constexpr int kWhatRows = 32;   // L values (same parity) per CTA
+constexpr int kWhatEPW = 4;     // 64-wide e tiles per warp
 __global__ void __launch_bounds__(128, 3) what_build_dmma_kernel(const double* __restrict__ W, const double* __restrict__ w2,
                                                               double* __restrict__ What, const int* __restrict__ ells,
                                                               int ell0, int lmax, int nrp, int Llo, int Lhi, int mirror,
@@ -208,8 +209,6 @@ __global__ void __launch_bounds__(128, 3) what_build_dmma_kernel(const double* _
     __syncthreads();
     if (L1hi < 0) return;
     const int n2 = nrp * nrp;
-    const int e0 = (blockIdx.z * 4 + warp) * 64;
-    if (e0 >= n2) return;
     const int hlo = (L1lo - par) >> 1, hhi = (L1hi - par) >> 1;
     const int nks = (hhi - hlo + 4) / 4;   // k-steps of four L1 values (h, h+1, h+2, h+3)
     // row tiles that hold at least one wanted L
@@ -219,42 +218,48 @@ __global__ void __launch_bounds__(128, 3) what_build_dmma_kernel(const double* _
         const int Lf = base + 2 * (mt * 8), Ll = min(base + 2 * (mt * 8 + 7), lmax - ((lmax - base) & 1));
         live[mt] = (Lf <= lmax) && !(mirror && Ll < ell) && !(Ll < Llo || Lf > Lhi);
     }
-    double acc[4][8][2];
+    // each warp sweeps kWhatEPW column tiles of 64 e's: the 3j tile in shared memory is built once per 1024 e's
+    for (int ep = 0; ep < kWhatEPW; ++ep) {
+        const int e0 = ((blockIdx.z * 4 + warp) * kWhatEPW + ep) * 64;
+        if (e0 >= n2) break;
+        double acc[4][8][2];
 #pragma unroll
-    for (int mt = 0; mt < 4; ++mt)
+        for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[mt][j][0] = acc[mt][j][1] = 0.0;
-    const double* Wb = W + e0 + g;
-    auto loadB = [&](int ks, double (&b)[8]) {
-        const int L1 = par + 2 * (hlo + 4 * ks + t);
-        const bool ok = (L1 <= 2 * lmax);
-        const double* src = Wb + (size_t)(ok ? L1 : 0) * n2;
+            for (int j = 0; j < 8; ++j) acc[mt][j][0] = acc[mt][j][1] = 0.0;
+        const double* Wb = W + e0 + g;
+        auto loadB = [&](int ks, double (&b)[8]) {
+            const int L1 = par + 2 * (hlo + 4 * ks + t);
+            const bool ok = (L1 <= 2 * lmax);
+            const double* src = Wb + (size_t)(ok ? L1 : 0) * n2;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) b[j] = ok ? __ldg(src + 8 * j) : 0.0;
-    };
-    double bcur[8], bnxt[8];
-    loadB(0, bcur);
-    for (int ks = 0; ks < nks; ++ks) {
-        if (ks + 1 < nks) loadB(ks + 1, bnxt);
-        const double* arow = wsm + g * SW + hlo + 4 * ks + t;
+            for (int j = 0; j < 8; ++j) b[j] = ok ? __ldg(src + 8 * j) : 0.0;
+        };
+        double bcur[8], bnxt[8];
+        loadB(0, bcur);
+        for (int ks = 0; ks < nks; ++ks) {
+            if (ks + 1 < nks) loadB(ks + 1, bnxt);
+            const double* arow = wsm + g * SW + hlo + 4 * ks + t;
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt) {
+                if (!live[mt]) continue;
+                const double a = arow[mt * 8 * SW];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dmma884(acc[mt][j], a, bcur[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bcur[j] = bnxt[j];
+        }
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt) {
             if (!live[mt]) continue;
-            const double a = arow[mt * 8 * SW];
+            const int L = base + 2 * (mt * 8 + g);
+            if (L > lmax) continue;
+            double* dst = What + ((size_t)(ell - ell0) * (lmax + 1) + L) * n2 + e0 + 2 * t;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) dmma884(acc[mt][j], a, bcur[j]);
+            for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<double2*>(dst + 8 * j) = make_double2(acc[mt][j][0], acc[mt][j][1]);
         }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) bcur[j] = bnxt[j];
-    }
-#pragma unroll
-    for (int mt = 0; mt < 4; ++mt) {
-        if (!live[mt]) continue;
-        const int L = base + 2 * (mt * 8 + g);
-        if (L > lmax) continue;
-        double* dst = What + ((size_t)(ell - ell0) * (lmax + 1) + L) * n2 + e0 + 2 * t;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) *reinterpret_cast<double2*>(dst + 8 * j) = make_double2(acc[mt][j][0], acc[mt][j][1]);
     }
 }
 
@@ -749,7 +754,12 @@ int cmix_plan_create(CmixPlan** out, const int64_t* lnn, int64_t lnnsize, int64_
     return 0;
 }
 
-void cmix_plan_destroy(CmixPlan* p) { delete p; }
+void cmix_plan_destroy(CmixPlan* p) {
+    if (p) {
+        for (auto& e : p->pend_ev) cudaEventDestroy(e);
+    }
+    delete p;
+}
 
 int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp1, int interchange, int64_t row_lo,
              int64_t row_hi, int64_t col_lo, int64_t col_hi, double* d_M, int64_t ldM, cudaStream_t stream,
@@ -779,8 +789,10 @@ int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp
                     "and the full row range");
     }
     const bool upper = mirror || upper_packed;  // only the blocks with L >= l are formed
+    if (p->pending) SFB_TRY(cmix_resolve_times(p));   // a previous asynchronous run nobody asked the times of
     cudaEvent_t ev[4];
     for (auto& e : ev) SFB_CUDA_OK(cudaEventCreate(&e));
+    std::vector<cudaEvent_t> chunk_ev;
 
     // rows of the shard -> output row index relative to row_lo, -1 elsewhere; ells touched by the shard
     std::vector<int> row_out(p->h_row_out.size());
@@ -849,7 +861,6 @@ int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp
     args.mirror = mirror ? 1 : 0;
     args.dbg = getenv("SFB_CMIX_DBG") ? atoi(getenv("SFB_CMIX_DBG")) : 0;
 
-    float t_what = 0.f, t_block = 0.f;
     double flops = 0.0;
     const int ngroups = 2 * (int)ceil_div(lmax + 1, 2 * kWhatGroup);
     std::vector<int> ell_list_all;  // device ell_list is filled per launch at distinct offsets
@@ -877,7 +888,7 @@ int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp
             SFB_CUDA_OK(cudaFuncSetAttribute(what_build_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)wsm_bytes));
             const int ng32 = 2 * (int)ceil_div(lmax + 1, 2 * kWhatRows);
-            what_build_dmma_kernel<<<dim3(ng32, (unsigned)wells.size(), (unsigned)ceil_div(nrp * nrp, 256)), 128, wsm_bytes,
+            what_build_dmma_kernel<<<dim3(ng32, (unsigned)wells.size(), (unsigned)ceil_div(nrp * nrp, 256 * kWhatEPW)), 128, wsm_bytes,
                                      stream>>>(p->d_W.p, p->d_w2.p, p->d_What.p, p->d_what_ells.p, ell0, lmax, nrp, Llo,
                                                Lhi, upper ? 1 : 0, SW);
         } else {
@@ -952,15 +963,9 @@ int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp
                 }
         }
         SFB_CUDA_OK(cudaEventRecord(e2, stream));
-        SFB_CUDA_OK(cudaEventSynchronize(e2));
-        float a_ms = 0, b_ms = 0;
-        cudaEventElapsedTime(&a_ms, e0, e1);
-        cudaEventElapsedTime(&b_ms, e1, e2);
-        t_what += a_ms;
-        t_block += b_ms;
-        cudaEventDestroy(e0);
-        cudaEventDestroy(e1);
-        cudaEventDestroy(e2);
+        chunk_ev.push_back(e0);
+        chunk_ev.push_back(e1);
+        chunk_ev.push_back(e2);
     }
     p->t_fill = 0;
     if (regz && mirror) {
@@ -969,16 +974,58 @@ int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp
         p->launches++;
         SFB_CUDA_OK(cudaEventRecord(ev[3], stream));
     }
+    p->flops_executed = flops;
+    p->pend_ev.clear();
+    p->pend_ev.push_back(ev[0]);
+    p->pend_ev.push_back(ev[1]);
+    p->pend_ev.insert(p->pend_ev.end(), chunk_ev.begin(), chunk_ev.end());
+    p->pend_ev.push_back(ev[2]);
+    p->pend_ev.push_back(ev[3]);
+    p->pend_fill = regz && mirror;
+    p->pending = true;
+    if (p->async_times) return 0;
+    SFB_TRY(cmix_resolve_times(p));
     SFB_CUDA_OK(cudaStreamSynchronize(stream));
-    if (regz && mirror) {
-        cudaEventElapsedTime(&p->t_fill, ev[2], ev[3]);
-        t_block += p->t_fill;
+    return 0;
+}
+
+// Wait for the last run's events and fill t_wl / t_what / t_block (incl. t_fill) / t_fill.
+int cmix_resolve_times(CmixPlan* p) {
+    if (!p || !p->pending) return 0;
+    auto& ev = p->pend_ev;
+    const size_t n = ev.size();
+    float t_what = 0.f, t_block = 0.f;
+    p->t_fill = 0.f;
+    int rc = 0;
+    if (n >= 4) {
+        const size_t nch = (n - 4) / 3;   // (begin, Ŵ end, blocks end) per l-chunk, after the two W_L1 events
+        const size_t last = p->pend_fill ? n - 1 : (nch ? 2 + 3 * (nch - 1) + 2 : 1);
+        if (cudaEventSynchronize(ev[last]) != cudaSuccess) rc = 1;
+        if (!rc) {
+            cudaEventElapsedTime(&p->t_wl, ev[0], ev[1]);
+            for (size_t i = 0; i < nch; ++i) {
+                const size_t c = 2 + 3 * i;
+                float a_ms = 0, b_ms = 0;
+                cudaEventElapsedTime(&a_ms, ev[c], ev[c + 1]);
+                cudaEventElapsedTime(&b_ms, ev[c + 1], ev[c + 2]);
+                t_what += a_ms;
+                t_block += b_ms;
+            }
+            if (p->pend_fill) {
+                cudaEventElapsedTime(&p->t_fill, ev[n - 2], ev[n - 1]);
+                t_block += p->t_fill;
+            }
+        }
     }
-    cudaEventElapsedTime(&p->t_wl, ev[0], ev[1]);
+    for (auto& e : ev) cudaEventDestroy(e);
+    ev.clear();
+    p->pending = false;
     p->t_what = t_what;
     p->t_block = t_block;
-    p->flops_executed = flops;
-    for (auto& e : ev) cudaEventDestroy(e);
+    if (rc) {
+        set_error("cmix_resolve_times: event synchronisation failed");
+        return 1;
+    }
     return 0;
 }
 

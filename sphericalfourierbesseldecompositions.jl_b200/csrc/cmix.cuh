@@ -54,6 +54,10 @@ struct CmixPlan {
     float t_wl = 0, t_fill = 0, t_what = 0, t_block = 0;  // t_block includes t_fill
     double flops_executed = 0;
     int launches = 0;
+    // async_times: cmix_run records its timing events and returns without a host sync; cmix_resolve_times fills t_*.
+    // pend_ev = [wl begin, wl end, (chunk begin, Ŵ end, blocks end)*, fill begin, fill end]
+    bool async_times = false, pending = false, pend_fill = false;
+    std::vector<cudaEvent_t> pend_ev;
 };
 
 // Build the plan from the caller's tables (host pointers).
@@ -62,6 +66,7 @@ struct CmixPlan {
 int cmix_plan_create(CmixPlan** out, const int64_t* lnn, int64_t lnnsize, int64_t lnn_min, const double* G,
                      int64_t nr, int64_t nmax, int64_t lmax);
 void cmix_plan_destroy(CmixPlan* p);
+int cmix_resolve_times(CmixPlan* p);
 
 // alm layout (device): planar [lm (m-major, lmax2 = 2*lmax)][comp (re,im)][nrp], padded shells zero.
 // Writes the block rows [row_lo,row_hi) x columns [col_lo,col_hi) (0-based, of the nout x nout matrix) into d_M

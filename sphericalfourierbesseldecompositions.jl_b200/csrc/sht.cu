@@ -1122,7 +1122,13 @@ int sht_plan_create(ShtPlan** out, int64_t nside_in, int64_t nside_out, int64_t 
     return 0;
 }
 
-void sht_plan_destroy(ShtPlan* p) { delete p; }
+void sht_plan_destroy(ShtPlan* p) {
+    if (p && p->pending) {
+        cudaEventDestroy(p->tev0);
+        cudaEventDestroy(p->tev1);
+    }
+    delete p;
+}
 
 // map -> ring-Fourier coefficients F (d_FG)
 static int run_ring_analysis(ShtPlan* p, const double* map, int64_t ldw, cudaStream_t st) {
@@ -1294,10 +1300,24 @@ int sht_map2alm(ShtPlan* p, const double* d_win, int64_t ldw, int niter, double*
     }
     }
     SFB_CUDA_OK(cudaEventRecord(e1, st));
-    SFB_CUDA_OK(cudaEventSynchronize(e1));
-    cudaEventElapsedTime(&p->t_total, e0, e1);
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
+    if (p->pending) {
+        cudaEventDestroy(p->tev0);
+        cudaEventDestroy(p->tev1);
+    }
+    p->tev0 = e0;
+    p->tev1 = e1;
+    p->pending = true;
+    return p->async_times ? 0 : sht_resolve_times(p);
+}
+
+int sht_resolve_times(ShtPlan* p) {
+    if (!p || !p->pending) return 0;
+    SFB_CUDA_OK(cudaEventSynchronize(p->tev1));
+    cudaEventElapsedTime(&p->t_total, p->tev0, p->tev1);
+    cudaEventDestroy(p->tev0);
+    cudaEventDestroy(p->tev1);
+    p->tev0 = p->tev1 = nullptr;
+    p->pending = false;
     return 0;
 }
 

@@ -35,6 +35,10 @@ struct ShtPlan {
 
     float t_total = 0;
     int launches = 0;
+    // async_times: sht_map2alm only records its two timing events and returns without a host sync; t_total is filled by
+    // sht_resolve_times (the device-resident API uses this so that the host can enqueue stage 2+3 behind stage 1)
+    bool async_times = false, pending = false;
+    cudaEvent_t tev0 = nullptr, tev1 = nullptr;
 };
 
 int sht_plan_create(ShtPlan** out, int64_t nside_in, int64_t nside_out, int64_t lmax, int64_t nr);
@@ -42,6 +46,7 @@ void sht_plan_destroy(ShtPlan* p);
 
 // d_win: [pixel][shell], pixel stride ldw (>= nr).  d_alm: planar [lm (m-major)][re,im][nrp].
 int sht_map2alm(ShtPlan* p, const double* d_win, int64_t ldw, int niter, double* d_alm, cudaStream_t stream);
+int sht_resolve_times(ShtPlan* p);
 // planar -> ComplexF64 nr x lmsize (device), layout 0 = m-major, 1 = m-fast
 int sht_alm_to_complex(const ShtPlan* p, const double* d_alm, int layout, double* d_out, cudaStream_t stream);
 
