@@ -304,6 +304,116 @@ def win_lnn(win, wmodes, cmodes):
     return out
 
 
+# ----------------------------------------------------------------------------
+# calc_wmix and the brute-force coupling matrix from it (src/windows.jl:273-364, 367-378, 434-525): an independent
+# route to M through general-m Gaunt sums, which the reference's own test pins against power_win_mix(win, ...) at
+# rtol 1e-10 (test/test_windows.jl:403-409).  SURVEY §8f row 1 / §8c identity 3.
+
+def calc_gaunts_L(l, lp, m, mp):
+    """src/windows.jl:449-464: gaunt[L] = (l l' L; m m' -m-m') (l l' L; 0 0 0) sqrt((2L+1)(2l+1)(2l'+1)/4π), L = Lmin.."""
+    from .wigner import wigner3j_family
+    Lmin, w3j = wigner3j_family(l, lp, m, mp)
+    Lmin0, w000 = wigner3j_family(l, lp, 0, 0)
+    L = Lmin + np.arange(w3j.size)
+    return w3j * np.sqrt((2 * L + 1) * (2 * l + 1) * (2 * lp + 1) / (4 * math.pi)) * w000[L - Lmin0], L
+
+
+def calc_wmix_ii(l, m, lp, mp, gg1, Wr_lm, LMAX):
+    """src/windows.jl:273-294 (Wr_lm in HEALPix m-major column order, LMcalcStruct(LMAX))."""
+    M = m - mp
+    gaunt, L = calc_gaunts_L(l, lp, -m, mp)
+    aM = abs(M)
+    w_ang = 0.0 + 0.0j
+    for j in range(L.size):
+        LM = int(L[j]) + (aM * (2 * LMAX + 1 - aM)) // 2     # 0-based LMcalcStruct index, src/LMcalcStructs.jl:13-18
+        w_ang += gaunt[j] * (gg1 @ Wr_lm[:, LM])
+    if M < 0:
+        w_ang = (-1) ** M * np.conj(w_ang)
+    return (-1) ** m * w_ang
+
+
+def calc_wmix(win, wmodes, amodes, neg_m=False):
+    """src/windows.jl:299-364: W_{nlm}^{n'l'm'} for m, m' >= 0 (or m -> -m with neg_m), nlmsize x nlmsize ComplexF64."""
+    nlmsize = om.getnlmsize(amodes)
+    LMAX = 2 * amodes.lmax
+    Wr_lm = calc_Wr_lm(win, LMAX, amodes.nside)
+    G = rsdrgnlr(amodes, wmodes)
+    wmix = np.full((nlmsize, nlmsize), np.nan + 0j)
+    nl = [(n, l) for n in range(1, amodes.nmax + 1) for l in range(int(amodes.lmax_n[n - 1]) + 1)]
+    for (n, l) in nl:
+        ibase = om.getidx_nlm(amodes, n, l, 0) - 1
+        for (n_, l_) in nl:
+            ibase_ = om.getidx_nlm(amodes, n_, l_, 0) - 1
+            gg1 = G[:, n - 1, l] * G[:, n_ - 1, l_]
+            for m in range(l + 1):
+                for m_ in range(l_ + 1):
+                    wmix[ibase + m, ibase_ + m_] = calc_wmix_ii(l, -m if neg_m else m, l_, m_, gg1, Wr_lm, LMAX)
+    return wmix
+
+
+def get_wmix(w, w_, nl, m, NL, M):
+    """src/windows.jl:367-378 (nl, NL: 0-based indices of the m = 0 entries)."""
+    if m >= 0:
+        if M >= 0:
+            return w[nl + m, NL + M]
+        return (-1) ** (m + M) * np.conj(w_[nl + m, NL - M])
+    if M >= 0:
+        return w_[nl - m, NL + M]
+    return (-1) ** (m - M) * np.conj(w[nl - m, NL - M])
+
+
+def power_win_mix_ii(lnn, LNN, wmix, wmix_negm, amodes):
+    """src/windows.jl:467-509."""
+    l, n, n_ = lnn
+    L, N, N_ = LNN
+    j0 = om.getidx_nlm(amodes, n, l, 0) - 1
+    j_0 = om.getidx_nlm(amodes, n_, l, 0) - 1
+    J0 = om.getidx_nlm(amodes, N, L, 0) - 1
+    J_0 = om.getidx_nlm(amodes, N_, L, 0) - 1
+    mix = 0.0
+    for m in range(l + 1):
+        for M in range(L + 1):
+            mix += np.real(wmix[j0 + m, J0 + M] * np.conj(wmix[j_0 + m, J_0 + M]))
+            for (sm, sM, cond) in ((-1, 1, m > 0), (1, -1, M > 0), (-1, -1, m > 0 and M > 0)):
+                if cond:
+                    w1 = get_wmix(wmix, wmix_negm, j0, sm * m, J0, sM * M)
+                    w2 = get_wmix(wmix, wmix_negm, j_0, sm * m, J_0, sM * M)
+                    mix += np.real(w1 * np.conj(w2))
+    return mix / (2 * l + 1)
+
+
+def power_win_mix_from_wmix(wmix, wmix_negm, cmodes):
+    """power_win_mix(wmix, wmix_negm, cmodes), src/windows.jl:512-525."""
+    amodes = cmodes.amodes
+    n = cmodes.lnn.shape[1]
+    out = np.empty((n, n))
+    for ip in range(n):
+        L, N, N_ = (int(x) for x in cmodes.lnn[:, ip])
+        for i in range(n):
+            l, a, b = (int(x) for x in cmodes.lnn[:, i])
+            v = power_win_mix_ii((l, a, b), (L, N, N_), wmix, wmix_negm, amodes)
+            if N != N_:
+                v += power_win_mix_ii((l, a, b), (L, N_, N), wmix, wmix_negm, amodes)
+            out[i, ip] = v
+    return out
+
+
+def sum_m_lmeqLM(A, cmodes):
+    """src/theory.jl:86-118: (1/(2l+1)) Σ_m Re A[(n1,l,m),(n2,l,m)], symmetrised in (n1, n2), per (l,n1,n2) of cmodes."""
+    amodes = cmodes.amodes
+    out = np.empty(cmodes.lnn.shape[1])
+    for i in range(out.size):
+        l, n1, n2 = (int(x) for x in cmodes.lnn[:, i])
+        acc = 0.0
+        for (a, b) in ((n1, n2), (n2, n1)):
+            ia = om.getidx_nlm(amodes, a, l, 0) - 1
+            ib = om.getidx_nlm(amodes, b, l, 0) - 1
+            cl = np.real(A[ia, ib]) + 2 * sum(np.real(A[ia + m, ib + m]) for m in range(1, l + 1))
+            acc += cl / (2 * l + 1)
+        out[i] = acc / 2
+    return out
+
+
 def calc_angular_mixing_matrix(lmax, w1lm, w2lm):
     """src/windows.jl:866-878 (m-major alm of length lmsize(2 lmax))."""
     Wl = hp.alm2cl(w1lm, w2lm, 2 * lmax)

@@ -151,3 +151,40 @@ def test_win_lnn_full_sky_is_identity():
     c = om.ClnnModes(a)
     wlnn = ow.win_lnn(np.ones((wm.nr, wm.npix)), wm, c)
     assert np.allclose(wlnn, (c.lnn[1] == c.lnn[2]).astype(float), atol=1e-5)
+
+
+def test_wigner3j_families_vs_sympy():
+    # general-m families (WignerFamilies semantics, src/windows.jl:434-445) against exact sympy values
+    from sympy.physics.wigner import wigner_3j
+    from oracle.wigner import wigner3j_family
+    for (j2, j3, m2, m3) in [(2, 3, 1, -2), (5, 5, 0, 0), (5, 5, -5, 5), (4, 4, 2, -2), (10, 7, -3, 5), (0, 0, 0, 0),
+                             (1, 1, 0, 0), (6, 2, -6, 2), (12, 12, 0, 0), (3, 0, 1, 0), (9, 14, 4, -11)]:
+        jmin, f = wigner3j_family(j2, j3, m2, m3)
+        assert jmin == max(abs(j2 - j3), abs(m2 + m3)) and f.size == j2 + j3 - jmin + 1
+        for k, v in enumerate(f):
+            assert abs(v - float(wigner_3j(jmin + k, j2, j3, -m2 - m3, m2, m3))) < 1e-14
+    assert wigner3j_family(2, 3, 3, 0)[1].size == 0
+
+
+def test_M_equals_brute_force_from_wmix():
+    # test/test_windows.jl:363-409: M from calc_wmix (general-m Gaunt sums, explicit m-sums, src/windows.jl:273-364,
+    # 467-525) equals power_win_mix(win, wmodes, cmodes) at rtol 1e-10 -- an independent route to the coupling matrix
+    a = om.AnlmModes(2, 5, 500.0, 1000.0)
+    wm = ow.ConfigurationSpaceModes(500.0, 1000.0, 100, a.nside)
+    c = om.ClnnModes(a, dnmax=1)
+    rng = np.random.default_rng(3)
+    mask = rng.random(wm.npix)
+    mask[: wm.npix // 2] *= 0.5
+    win = np.outer(np.exp(-(wm.r / (0.55 * wm.rmax)) ** 2), mask)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        wmix = ow.calc_wmix(win, wm, a)
+        wmix_negm = ow.calc_wmix(win, wm, a, neg_m=True)
+        M = ow.power_win_mix_from_wmix(wmix, wmix_negm, c)
+        M1 = ow.power_win_mix(win, win, wm, c)
+        wlnn = ow.win_lnn(win, wm, c)
+    assert np.isfinite(wmix).all()
+    assert relerr(M, M1) < 1e-10
+    # W_lnn' = (1/(2l+1)) Σ_m W_{nlm}^{n'lm} (test/test_windows.jl:250,254: rtol 1e-3 there; exact here up to rounding)
+    assert relerr(ow.sum_m_lmeqLM(wmix, c), wlnn) < 1e-10
