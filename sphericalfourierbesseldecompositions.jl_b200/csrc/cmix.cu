@@ -779,6 +779,10 @@ int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp
         SFB_REQUIRE(sym && npeers == 0 && col_lo == 0 && col_hi == p->nout && ldM >= p->nout,
                     "cmix_run: mirror mode needs the auto-correlation path and the full matrix");
     }
+    // mirror mode relies on the l-blocks being contiguous and ordered (every table ClnnModes builds is); for any other
+    // table all blocks are formed directly.  With the full row and column range the two modes address d_M identically.
+    if (mirror && !p->ell_sorted && row_lo == 0 && row_hi == p->nout) mirror = false;
+    SFB_REQUIRE(!mirror || p->ell_sorted, "cmix_run: mirror mode needs an lnn table sorted by l");
     const int lmax = p->lmax, nrp = p->nrp;
     // register-Z kernel (cmix_regz.cu) for the auto-correlation path with nr <= 64; in mirror mode it forms the L >= l
     // blocks only and cmix_mirror_fill writes the blocks below the block diagonal afterwards
