@@ -454,9 +454,52 @@ def run_b200(args):
                                      "formed on the device, only N = w̃Mv returns to the host"}
         except Exception as exc:  # noqa: BLE001
             e2e["binned"] = {"error": str(exc)}
-    elif world > 1:
+    elif world > 1 and not args.no_e2e:
+        # N > 1: every rank uploads the shells it transforms from pinned host memory, the sharded step runs, and rank 0
+        # reads the assembled matrix back into pinned host memory (what a user of the one-process-per-GPU pipeline
+        # does to obtain M on the host).  Falls back to a note if anything in this leg fails.
         e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
                "note": "e2e is measured at N=1 through the host C ABI; multi-GPU runs keep shards device-resident"}
+        from sfb_b200.device import shard_shells
+        s_lo, s_hi = shard_shells(wl.nr, world)[rank]
+        ok, host_shard, host_out, err = 1.0, None, None, ""
+        try:    # the only steps that can fail on one rank alone: host allocations
+            host_shard = torch.empty((d_win.shape[0], max(1, s_hi - s_lo)), dtype=torch.float64).pin_memory()
+            if s_hi > s_lo:
+                host_shard.copy_(d_win[:, s_lo:s_hi].cpu())
+            host_out = torch.empty((n, n), dtype=torch.float64).pin_memory() if rank == 0 else None
+        except Exception as exc:  # noqa: BLE001
+            ok, err = 0.0, str(exc)
+        flag = torch.tensor([ok], device="cuda", dtype=torch.float64)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)     # every rank takes the same branch: no collective can hang
+        if float(flag.item()) == 1.0:
+            def e2e_step():
+                if s_hi > s_lo:
+                    d_win[:, s_lo:s_hi].copy_(host_shard, non_blocking=True)
+                out = step()
+                if rank == 0:
+                    host_out.copy_(out, non_blocking=True)
+                torch.cuda.synchronize()
+
+            e2e_step()
+            barrier()
+            t0 = time.perf_counter()
+            k = max(1, min(args.steps, 3))
+            for _ in range(k):
+                e2e_step()
+            barrier()
+            dt = torch.tensor([(time.perf_counter() - t0) / k], device="cuda", dtype=torch.float64)
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            dt = float(dt.item())
+            e2e = {"value": n * n / dt, "unit": UNIT, "h2d_bytes_per_step": int(win.nbytes),
+                   "d2h_bytes_per_step": int(8 * n * n), "ms_per_step": dt * 1e3,
+                   "api": "DevicePipeline (one process per GPU): pinned host shells in on every rank, sharded step, "
+                          "assembled matrix out to pinned host memory on rank 0"}
+        elif err:
+            e2e["error"] = err
+    elif world > 1:
+        e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
+               "note": "--no-e2e"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
