@@ -31,7 +31,8 @@ def build():
     M = ow.power_win_mix(win, win, wm, c)
     Md = ow.power_win_mix(win, win, wm, c, div2Lp1=True, interchange=True, lnn_min=7)
     wt, v = om.bandpower_binning_weights(c, dl=3)
-    return dict(kmax=0.022, nr=20, win_nside=8, win=win, lnn=c.lnn, nmax_l=a.nmax_l, knl=a.knl, Wr_lm=Wr_lm, M=M,
+    Wlnn = ow.win_lnn(win, wm, c)
+    return dict(Wlnn=Wlnn, kmax=0.022, nr=20, win_nside=8, win=win, lnn=c.lnn, nmax_l=a.nmax_l, knl=a.knl, Wr_lm=Wr_lm, M=M,
                 M_div_interchange_min7=Md, N_binned_dl3=wt @ M @ v)
 
 

@@ -26,6 +26,7 @@ def test_oracle_reproduces_golden(gold):
     assert relerr(W, gold["Wr_lm"][:3]) < 1e-13
     M = ow.power_win_mix(gold["win"], gold["win"], wm, c)
     assert relerr(M, gold["M"]) < 1e-12
+    assert relerr(ow.win_lnn(gold["win"], wm, c), gold["Wlnn"]) < 1e-12
 
 
 @pytest.mark.gpu
@@ -47,3 +48,4 @@ def test_cuda_reproduces_golden(gold):
         wt, v = sfb.bandpower_binning_weights(c, dl=3)
         N = sfb.power_win_mix(win, wt, v, wm, sfb.ClnnBinnedModes(wt, v, c))
         assert relerr(N, gold["N_binned_dl3"]) < 1e-10
+        assert relerr(sfb.win_lnn(win, wm, c), gold["Wlnn"]) < 1e-10
