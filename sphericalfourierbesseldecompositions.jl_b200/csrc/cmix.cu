@@ -794,9 +794,6 @@ int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp
     }
     const bool upper = mirror || upper_packed;  // only the blocks with L >= l are formed
     if (p->pending) SFB_TRY(cmix_resolve_times(p));   // a previous asynchronous run nobody asked the times of
-    cudaEvent_t ev[4];
-    for (auto& e : ev) SFB_CUDA_OK(cudaEventCreate(&e));
-    std::vector<cudaEvent_t> chunk_ev;
 
     // rows of the shard -> output row index relative to row_lo, -1 elsewhere; ells touched by the shard
     std::vector<int> row_out(p->h_row_out.size());
@@ -823,6 +820,9 @@ int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp
             }
         }
     if (Lhi < 0) return 0;
+    cudaEvent_t ev[4];
+    for (auto& e : ev) SFB_CUDA_OK(cudaEventCreate(&e));
+    std::vector<cudaEvent_t> chunk_ev;
 
     // ---- W_{L1} ----
     SFB_CUDA_OK(cudaEventRecord(ev[0], stream));
