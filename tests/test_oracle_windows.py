@@ -188,3 +188,26 @@ def test_M_equals_brute_force_from_wmix():
     assert relerr(M, M1) < 1e-10
     # W_lnn' = (1/(2l+1)) Σ_m W_{nlm}^{n'lm} (test/test_windows.jl:250,254: rtol 1e-3 there; exact here up to rounding)
     assert relerr(ow.sum_m_lmeqLM(wmix, c), wlnn) < 1e-10
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(div2Lp1=True), dict(interchange=True), dict(div2Lp1=True, interchange=True)])
+def test_upper_blocks_determine_the_matrix(small, kw):
+    # The algebra behind cmix_mirror_fill_kernel / cmix_unpack_mirror_kernel (csrc/cmix_regz.cu): the blocks with
+    # l(i) <= l(i') determine the rest through M[i',i] = M[i,i'] f_i / f_i',
+    # f = (div2Lp1 ? 1 : 2l+1) (interchange_NN' ? 1 : 1 + [n != n'])   (derivations/sfb.tex:516-517)
+    a, wm, c, win = small
+    M = ow.power_win_mix(win.dense(), win.dense(), wm, c, **kw)
+    ell, n1, n2 = c.lnn
+    f = np.ones(ell.size) * (1.0 if kw.get("div2Lp1") else (2.0 * ell + 1.0))
+    f = f * (1.0 if kw.get("interchange") else (1.0 + (n1 != n2)))
+    # upper-packed storage: column j keeps rows [0, rend(j)), rend = end of j's own l-block
+    first = np.concatenate([[0], np.cumsum(np.bincount(ell))])
+    rend = first[ell + 1]
+    packed = [M[:rend[j], j].copy() for j in range(M.shape[0])]
+    R = np.full_like(M, np.nan)
+    for j, col in enumerate(packed):
+        R[:rend[j], j] = col                                       # direct half
+        lower = ell[:rend[j]] < ell[j]
+        R[j, :rend[j]][lower] = col[lower] * f[:rend[j]][lower] / f[j]   # mirror image below the block diagonal
+    assert np.isfinite(R).all()
+    assert relerr(R, M) < 1e-12
