@@ -211,3 +211,21 @@ def test_upper_blocks_determine_the_matrix(small, kw):
         R[j, :rend[j]][lower] = col[lower] * f[:rend[j]][lower] / f[j]   # mirror image below the block diagonal
     assert np.isfinite(R).all()
     assert relerr(R, M) < 1e-12
+
+
+def test_wmix_full_sky_is_identity():
+    # full sky: W_{nlm}^{n'l'm'} = δ (test/test_window_chains.jl:405-415 pins δ_{ll'}δ_{mm'} at atol 1e-6; the radial part
+    # is the g_nl orthonormality of test/test_gnl.jl:27-41), for m >= 0 and for the neg_m table
+    a = om.AnlmModes(2, 4, 500.0, 1000.0)
+    wm = ow.ConfigurationSpaceModes(500.0, 1000.0, 1000, a.nside)
+    win = np.ones((wm.nr, wm.npix))
+    w = ow.calc_wmix(win, wm, a)
+    assert np.allclose(w, np.eye(w.shape[0]), atol=1e-5)
+    wn = ow.calc_wmix(win, wm, a, neg_m=True)
+    # neg_m: entry (n,l,-m ; n',l',m') -- only m = m' = 0 survives on the diagonal
+    n = w.shape[0]
+    expect = np.zeros((n, n))
+    for i in range(1, n + 1):
+        if om.getnlm(a, i)[2] == 0:
+            expect[i - 1, i - 1] = 1.0
+    assert np.allclose(wn, expect, atol=1e-5)
