@@ -111,3 +111,76 @@ def test_fft_sht_equals_exact_sum(ns, lmax):
     assert np.linalg.norm(a.synthesis(x) - b.synthesis(x)) / np.linalg.norm(m) < 1e-13
     with pytest.raises(ValueError):
         hp.SHT(ns, 4 * ns + 1)
+
+
+def test_belt_rings_reduce_to_gram_matrices():
+    # Design check for DESIGN §9.2: on alias-free rings (nφ > 2 lmax) the composition analysis∘synthesis is the
+    # data-independent, m-block-diagonal operator K_m[l][l'] = w nφ Σ_rings λ_lm(θ) λ_l'm(θ) (even and odd l decouple).
+    import math
+    from oracle import healpix as ohp
+    from oracle.sht_fft import FastSHT
+    nside, lmax = 8, 12
+    sht = FastSHT(nside, lmax)
+    info = sht.info
+    belt = np.flatnonzero(info.nphi > 2 * lmax)
+    assert belt.size >= 2 * nside + 1                      # at least the whole equatorial belt
+    rng = np.random.default_rng(4)
+    nlm = ohp.getlmsize(lmax)
+    alm = rng.standard_normal((1, nlm)) + 1j * rng.standard_normal((1, nlm))
+    for l in range(lmax + 1):
+        alm[0, ohp.lm_index_mmajor(lmax, l, 0)] = alm[0, ohp.lm_index_mmajor(lmax, l, 0)].real   # real map
+    m_syn = sht.synthesis(alm)
+    keep = np.zeros(sht.npix, dtype=bool)
+    for ring in belt:
+        keep[info.start[ring]:info.start[ring] + info.nphi[ring]] = True
+    ref = sht.adjoint_synthesis(np.where(keep, m_syn, 0.0))          # A(belt part of S(alm))
+    w = 4 * math.pi / sht.npix
+    nh = sht.nhalf
+    got = np.zeros_like(ref)
+    north = np.flatnonzero(info.nphi[:nh] > 2 * lmax)                 # belt rings of the northern half incl. equator
+    mult = np.where(north == nh - 1, 1.0, 2.0)                        # N/S pairs count twice, the equator once
+    nphi = info.nphi[north].astype(float)
+    for m in range(lmax + 1):
+        i0 = ohp.lm_index_mmajor(lmax, m, m)
+        sl = slice(i0, i0 + lmax + 1 - m)
+        lam = sht.lam[sl][:, north]                                   # [l, ring]
+        odd = sht.parity[sl]
+        K = w * (lam * (nphi * mult)[None, :]) @ lam.T                # [l, l']
+        K[np.ix_(~odd, odd)] = 0.0                                    # opposite parities cancel between N and S
+        K[np.ix_(odd, ~odd)] = 0.0
+        got[0, sl] = K @ alm[0, sl]
+    assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 1e-12
+
+
+def test_alias_operator_class_sum_form():
+    # Design check for DESIGN §9.1: the ring alias operator of ring_alias_kernel (csrc/sht.cu) in O(lmax) per ring.
+    # F'_m = nφ σ^q [ (P[ρ][0] + σ P[ρ][1]) + σ^{[ρ≠0]} conj(P[(nφ-ρ) mod nφ][0] + σ P[.][1]) ],  ρ = m mod nφ, q = m div nφ,
+    # P[ρ][par] = Σ_{m' ≡ ρ, (m' div nφ) ≡ par} c_{m'} G_{m'},  c_0 = 1/2.
+    rng = np.random.default_rng(0)
+    lmax = 37
+    for n, shift in [(4, 0), (4, 1), (8, 0), (12, 1), (20, 0), (36, 1), (40, 0), (76, 1)]:
+        G = rng.standard_normal(lmax + 1) + 1j * rng.standard_normal(lmax + 1)
+        sig = -1.0 if shift else 1.0
+        F = np.zeros(lmax + 1, complex)                       # the kernel's double loop
+        for m in range(lmax + 1):
+            re = im = 0.0
+            for mp in range(m % n, lmax + 1, n):
+                s = (sig if ((mp - m) // n) & 1 else 1.0) * (0.5 if mp == 0 else 1.0)
+                re += s * G[mp].real
+                im += s * G[mp].imag
+            for mp in range((n - m % n) % n, lmax + 1, n):
+                s = (sig if ((mp + m) // n) & 1 else 1.0) * (0.5 if mp == 0 else 1.0)
+                re += s * G[mp].real
+                im -= s * G[mp].imag
+            F[m] = n * (re + 1j * im)
+        P = np.zeros((n, 2), complex)
+        for mp in range(lmax + 1):
+            P[mp % n, (mp // n) & 1] += (0.5 if mp == 0 else 1.0) * G[mp]
+        F2 = np.zeros(lmax + 1, complex)
+        for m in range(lmax + 1):
+            rho, q = m % n, m // n
+            plus = P[rho, 0] + sig * P[rho, 1]
+            rp = (n - rho) % n
+            minus = np.conj(P[rp, 0] + sig * P[rp, 1]) * (sig if rho != 0 else 1.0)
+            F2[m] = n * (sig ** q) * (plus + minus)
+        assert np.abs(F - F2).max() < 1e-13
