@@ -71,8 +71,9 @@ def gen_mask(nside, fsky):
 
 def make_window(wmodes, *features):
     """Subset of make_window (…Decompositions.jl:300-494): :fullsky, :ang_75/half/quarter/
-    eighth/sixteenth, :radial, :radial_expmrr0, :separable, :dense; renormalised to
-    max 1 after every feature like the reference (:467-475)."""
+    eighth/sixteenth, :radial, :radial_expmrr0, :separable, :dense, :rotate (:277-299,
+    378-382; oracle/rotate.py); renormalised to max 1 after every feature like the
+    reference (:467-475)."""
     r = wmodes.r
     win = np.ones((wmodes.nr, wmodes.npix))
     fsky = {"ang_75": 0.75, "ang_half": 0.5, "ang_quarter": 0.25, "ang_eighth": 0.125,
@@ -81,7 +82,8 @@ def make_window(wmodes, *features):
     def normalise(w):
         if isinstance(w, SeparableArray):
             w.mask = w.mask / w.mask.max()
-            w.phi = w.phi / (w.phi.max() * w.mask.max())
+            # maximum(win.phi * win.mask') = the largest of the four extreme products
+            w.phi = w.phi / max(a * b for a in (w.phi.max(), w.phi.min()) for b in (w.mask.max(), w.mask.min()))
         else:
             w /= w.max()
         return w
@@ -109,6 +111,13 @@ def make_window(wmodes, *features):
                 win = win * phi[:, None]
         elif feat == "separable":
             win = SeparableArray(win.mean(axis=1), win.mean(axis=0))
+        elif feat == "rotate":
+            from . import rotate as rot
+            ang = (rot.ROTATE_ALPHA, rot.ROTATE_BETA, rot.ROTATE_GAMMA)
+            if isinstance(win, SeparableArray):
+                win.mask = rot.rotate_euler(win.mask, *ang)
+            else:
+                win = np.stack([rot.rotate_euler(win[i], *ang) for i in range(win.shape[0])])
         elif feat == "dense":
             win = win.dense() if isinstance(win, SeparableArray) else np.array(win)
         else:
@@ -332,14 +341,17 @@ def calc_wmix_ii(l, m, lp, mp, gg1, Wr_lm, LMAX):
     return (-1) ** m * w_ang
 
 
-def calc_wmix(win, wmodes, amodes, neg_m=False):
-    """src/windows.jl:299-364: W_{nlm}^{n'l'm'} for m, m' >= 0 (or m -> -m with neg_m), nlmsize x nlmsize ComplexF64."""
+def calc_wmix(win, wmodes, amodes, neg_m=False, only_nl=None):
+    """src/windows.jl:299-364: W_{nlm}^{n'l'm'} for m, m' >= 0 (or m -> -m with neg_m), nlmsize x nlmsize ComplexF64.
+    `only_nl` (test aid, not in the reference): restrict both loops to the listed (n,l); other entries stay NaN."""
     nlmsize = om.getnlmsize(amodes)
     LMAX = 2 * amodes.lmax
     Wr_lm = calc_Wr_lm(win, LMAX, amodes.nside)
     G = rsdrgnlr(amodes, wmodes)
     wmix = np.full((nlmsize, nlmsize), np.nan + 0j)
     nl = [(n, l) for n in range(1, amodes.nmax + 1) for l in range(int(amodes.lmax_n[n - 1]) + 1)]
+    if only_nl is not None:
+        nl = [x for x in nl if x in set(only_nl)]
     for (n, l) in nl:
         ibase = om.getidx_nlm(amodes, n, l, 0) - 1
         for (n_, l_) in nl:
