@@ -21,10 +21,15 @@ function check(status::Integer)
     error(msg)                      # ErrorException, like error()/@assert in the reference
 end
 
-# r .* √Δr .* precompute_gnlr(amodes, wmodes)   (src/windows.jl:799) — stays in Julia (input of the path)
+# r .* √Δr .* precompute_gnlr(amodes, wmodes)   (src/windows.jl:799) — stays in Julia (input of the path).
+# precompute_gnlr allocates `fill(NaN, nr, size(amodes.basisfunctions.knl)...)` (src/windows.jl:551); for
+# AnlmModes(kmax, rmin, rmax) that knl table is the UNTRIMMED one (SphericalBesselGNLs.jl:313-316), larger than
+# amodes.nmax x (amodes.lmax+1) (src/modes.jl:144,156).  The C ABI indexes G[r + nr*(n + nmax*l)] with
+# nmax = amodes.nmax, so the table is trimmed to exactly nr x amodes.nmax x (amodes.lmax+1) here.
 function rsdrgnlr(amodes, wmodes)
     r, Δr = window_r(wmodes)
-    return r .* .√Δr .* SFB.Windows.precompute_gnlr(amodes, wmodes)
+    G = r .* .√Δr .* SFB.Windows.precompute_gnlr(amodes, wmodes)
+    return Array(G[:, 1:amodes.nmax, 1:amodes.lmax+1])
 end
 
 ############################## calc_Wr_lm ##############################

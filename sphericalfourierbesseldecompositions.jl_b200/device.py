@@ -33,13 +33,13 @@ def shard_rows(costs, ell_of_row, world):
     Returns a list of `world` (lo, hi) tuples covering [0, n)."""
     costs = np.asarray(costs, dtype=np.float64)
     n = costs.size
-    cuts = [0] + [i for i in range(1, n) if ell_of_row[i] != ell_of_row[i - 1]] + [n]
+    ell = np.asarray(ell_of_row)
+    cuts = np.concatenate([[0], np.flatnonzero(np.diff(ell)) + 1, [n]]).astype(np.int64)
     cum = np.concatenate([[0.0], np.cumsum(costs)])
     total = cum[-1]
     bounds = [0]
     for g in range(1, world):
-        target = total * g / world
-        best = min(cuts, key=lambda c: abs(cum[c] - target))
+        best = int(cuts[np.argmin(np.abs(cum[cuts] - total * g / world))])
         bounds.append(max(best, bounds[-1]))
     bounds.append(n)
     return [(bounds[g], bounds[g + 1]) for g in range(world)]

@@ -266,3 +266,39 @@ def test_device_pipeline_row_shards():
         assert np.isfinite(got).all()
         assert relerr(got, ref) < 1e-13
     pipe.close()
+
+
+# --------------------------------------------------------------------------------------------- alternative code paths
+# the kernels behind the environment switches are exercised here (the switches are read at call
+# time), each against the oracle, so none of them is dead code on the GPU box.
+
+@pytest.mark.parametrize("flag", ["SFB_NO_MIRROR", "SFB_CMIX_OLD", "SFB_WHAT_FMA"])
+@pytest.mark.parametrize("nr", [24, 64])
+def test_stage23_alternative_paths(monkeypatch, flag, nr):
+    import warnings
+    sfb, oa, a, owm, wm, oc, c, rng = _setup(kmax=0.03, nr=nr, dnmax=None)
+    win, _, _ = _random_window(rng, owm, smooth=False)
+    ref = ow.power_win_mix(win, win, owm, oc)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        base = sfb.power_win_mix(win, wm, c)
+        monkeypatch.setenv(flag, "1")
+        got = sfb.power_win_mix(win, wm, c)
+    assert relerr(got, ref) < RTOL
+    assert relerr(got, base) < 1e-12
+
+
+@pytest.mark.parametrize("nside,lmax,nr", [(8, 16, 5), (16, 40, 9), (32, 64, 3), (12, 30, 4)])
+def test_stage1_pixel_space_refinement_path(monkeypatch, nside, lmax, nr):
+    """SFB_SHT_PIXEL_ITER=1: Jacobi refinement through pixel space (synthesis kernels + residual + re-analysis, the
+    literal Healpix.jl iteration) instead of the ring-Fourier alias operator."""
+    import sfb_b200 as sfb
+    rng = np.random.default_rng(3 * nside + lmax)
+    win = rng.random((nr, 12 * nside * nside))
+    win[:, ::5] = 0.0
+    ref = ow.calc_Wr_lm(win, lmax, nside)
+    base = sfb.calc_Wr_lm(win, lmax, nside)
+    monkeypatch.setenv("SFB_SHT_PIXEL_ITER", "1")
+    got = sfb.calc_Wr_lm(win, lmax, nside)
+    assert relerr(got, ref) < RTOL
+    assert relerr(got, base) < 1e-11

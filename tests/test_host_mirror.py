@@ -132,3 +132,27 @@ def test_fails_loudly_without_gpu(sfb):
     a = sfb.AnlmModes(2, 3, 500.0, 1000.0)
     with pytest.raises(_lib.SFBError):
         sfb.power_win_mix(np.ones((8, 12 * a.nside ** 2)), sfb.ConfigurationSpaceModes(a, 8), sfb.ClnnModes(a))
+
+
+def test_untrimmed_gnlr_table_is_trimmed_like_the_shim(sfb):
+    """the reference's precompute_gnlr returns nr x size(basisfunctions.knl)... (src/windows.jl:551) and for
+    kmax-built modes that knl is the UNTRIMMED zero table (SphericalBesselGNLs.jl:313-316), wider than
+    amodes.nmax x (amodes.lmax+1).  The C ABI indexes G[r + nr (n + nmax l)], so julia/SFBB200.jl::rsdrgnlr trims it:
+    G[:, 1:amodes.nmax, 1:amodes.lmax+1].  Same operation here on a reference-shaped table."""
+    from oracle import windows as ow
+    kmax, rmin, rmax = 0.03, 500.0, 1000.0
+    oa = om.AnlmModes(kmax, rmin, rmax)
+    knl_untrimmed = om.calc_knl_zeros_kmax(kmax, rmin, rmax)
+    assert knl_untrimmed.shape[0] > oa.nmax and knl_untrimmed.shape[1] > oa.lmax + 1     # the premise of the finding
+    owm = ow.ConfigurationSpaceModes(rmin, rmax, 40, oa.nside)
+    ref_shaped = np.full((40,) + knl_untrimmed.shape, np.nan)                            # fill(NaN, nr, size(knl)...)
+    trimmed = ow.rsdrgnlr(oa, owm)
+    ref_shaped[:, :oa.nmax, :oa.lmax + 1] = trimmed
+    shim = np.asfortranarray(ref_shaped[:, :oa.nmax, :oa.lmax + 1])                      # what the shim passes
+    a = sfb.AnlmModes(kmax, rmin, rmax)
+    G = sfb.rsdrgnlr(a, sfb.ConfigurationSpaceModes(a, 40))
+    assert shim.shape == G.shape == (40, a.nmax, a.lmax + 1)
+    assert np.allclose(shim, G, rtol=1e-7, atol=1e-12, equal_nan=True)
+    # the shim source really trims
+    src = open(os.path.join(ROOT, "julia", "SFBB200.jl")).read()
+    assert "G[:, 1:amodes.nmax, 1:amodes.lmax+1]" in src
