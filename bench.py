@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="CPU work budget of the cpu_baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-assembled", action="store_true", help="N > 1: skip the full-matrix-on-every-GPU variant")
     return ap.parse_args()
 
 
@@ -117,7 +118,8 @@ def cpu_reference_run(wl, seconds, shells=2):
 
     a = wl.amodes
     LMAX, nr, n = wl.LMAX, wl.nr, wl.lnnsize
-    cores = cref.max_threads()
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm must still use every host core
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     win = wl.win
     t0 = time.perf_counter()
     if isinstance(win, SeparableArray):
@@ -141,12 +143,12 @@ def cpu_reference_run(wl, seconds, shells=2):
     rng = np.random.default_rng(1)
     probe = np.sort(rng.choice(n, size=min(n, 2 * cores), replace=False)) + 1
     t0 = time.perf_counter()
-    cref.calc_cmix_rows(wl.cmodes.lnn, probe, wl.G, Wc)
+    cref.calc_cmix_rows(wl.cmodes.lnn, probe, wl.G, Wc, nthreads=cores)
     tp = time.perf_counter() - t0
     nrows = int(max(2 * cores, min(n, seconds / (tp / probe.size))))
     rows = np.unique(np.linspace(0, n - 1, nrows).astype(np.int64)) + 1
     t0 = time.perf_counter()
-    cref.calc_cmix_rows(wl.cmodes.lnn, rows, wl.G, Wc)
+    cref.calc_cmix_rows(wl.cmodes.lnn, rows, wl.G, Wc, nthreads=cores)
     t3_sample = time.perf_counter() - t0
     fl_sample = wl.flops_bruteforce(rows - 1)
     fl_full = wl.flops_bruteforce()
@@ -196,13 +198,26 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ CUDA arm
+def strided_checksum_cols(cols_t, col_lo, n):
+    """Σ M[i, j] over i ∈ 0::n//97, j ∈ 0::n//89 restricted to the columns [col_lo, col_lo + cols) this tensor holds
+    (tensor[j - col_lo, i] = M[i, j]).  Summed over all shards it is the same number for every N."""
+    import torch
+    si, sj = max(1, n // 97), max(1, n // 89)
+    hi = col_lo + cols_t.shape[0]
+    j0 = -(-col_lo // sj) * sj
+    if j0 >= hi:
+        return 0.0
+    jj = torch.arange(j0, hi, sj, device=cols_t.device) - col_lo
+    return float(cols_t[jj][:, ::si].sum().item())
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
 
     import sfb_b200 as sfb
     from sfb_b200 import _lib, configs
-    from sfb_b200.device import DevicePipeline, PeerMatrix, shard_rows
+    from sfb_b200.device import DevicePipeline, PeerBuffer, shard_rows, stream_barrier
     from sfb_b200.separable import SeparableArray
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -224,80 +239,28 @@ def run_b200(args):
     pipe = DevicePipeline(wl.wmodes, wl.cmodes, wl.G)
     # window resident in HBM in Julia memory order: (npix, nr) C-contiguous == (nr, npix) column-major
     d_win = torch.from_numpy(np.ascontiguousarray(win.T)).cuda()
-    # exchange variants (default first): cols = column slabs + in-place NCCL send/recv; cols_dma = column slabs +
-    # IPC copy-engine pushes; dma / stores = row shards via pitched P2P copies / in-kernel P2P stores;
-    # nccl = row slabs + padded all_gather + placement
-    # packed (default) = column shards of the l <= L blocks in upper-packed storage + in-place NCCL all-gather of the
-    # packed slabs (half the matrix bytes) + local unpack/mirror pass
-    # pull (default) = packed slabs left in place in peer-mapped buffers, the expansion kernel pulls every column from
-    # its owner over NVLink (exchange fused into the kernel)
-    xmode = os.environ.get("SFB_BENCH_EXCHANGE", "pull")
-    if xmode in ("packed", "pull"):
-        off = pipe.packed_offsets()
-        ranges = pipe.packed_shard_ranges(world)
-    else:
-        ranges = shard_rows(pipe.col_costs if xmode.startswith("cols") else pipe.row_costs, pipe.ell_of_row, world)
-    lo, hi = ranges[rank]
-    # N = 1: the matrix stays in a device buffer; N > 1: every rank holds the full matrix, rows stored into all
-    # copies by the block kernel itself (all-gather fused into the epilogue over NVLink peer memory)
-    slab = torch.empty((pipe.nout, hi - lo), dtype=torch.float64, device="cuda") if world == 1 else None
-    pm = PeerMatrix(pipe.nout) if (world > 1 and xmode in ("cols_dma", "dma", "stores")) else None
-    full_t = torch.empty((pipe.nout, pipe.nout), dtype=torch.float64, device="cuda") if (world > 1 and xmode in ("cols", "packed", "pull")) else None
-    packed_t = torch.empty(int(off[-1]), dtype=torch.float64, device="cuda") if (world > 1 and xmode == "packed") else None
-    from sfb_b200.device import PeerBuffer, stream_barrier
-    pb = PeerBuffer(int(off[-1])) if (world > 1 and xmode == "pull") else None
 
-    fused = xmode in ("dma", "stores")
-    from sfb_b200.device import allgather_col_slabs, allgather_packed_slabs
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
-    if world > 1 and not fused:
-        from sfb_b200.device import gather_row_slabs
-        slab = torch.empty((pipe.nout, hi - lo), dtype=torch.float64, device="cuda")
+    # Output modes of the device-timed step (`value`):
+    #   N = 1   : the whole matrix in HBM (mirror mode: L >= l blocks + fill pass)
+    #   N > 1   : "sharded" (default) — rank g forms a full-height column range of M, a contiguous slab of the
+    #             column-major matrix, and leaves it in its HBM (what an on-device consumer or the per-GPU host copy of
+    #             sfb_set_devices wants); stage 1 is shell-sharded + NCCL all-gather of W_lm(r).
+    #             "assembled" (also timed, reported under `assembled`) — the full matrix on EVERY GPU: upper-packed column
+    #             shards pulled from their owners over NVLink inside the unpack+mirror kernel.
+    mode = os.environ.get("SFB_BENCH_MODE", "sharded")
+    ranges = shard_rows(pipe.col_costs, pipe.ell_of_row, world)
+    lo, hi = ranges[rank]
+    out_t = torch.empty((max(1, hi - lo), pipe.nout), dtype=torch.float64, device="cuda")
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
 
     def step():
         evs[0].record()
         pipe.calc_wr_lm_sharded(d_win)
         evs[1].record()
-        if world > 1 and xmode == "pull":
-            if hi > lo:
-                pipe.power_win_mix_upper_packed(lo, hi, pb.tensor)
-            evs[3].record()
-            stream_barrier(pipe)
-            evs[4].record()
-            out = pipe.unpack_mirror_pull(pb, ranges, full_t)
-            stream_barrier(pipe)
-        elif world > 1 and xmode == "packed":
-            if hi > lo:
-                pipe.power_win_mix_upper_packed(lo, hi, packed_t)
-            evs[3].record()
-            allgather_packed_slabs(packed_t, [(int(off[l]), int(off[h])) for l, h in ranges])
-            evs[4].record()
-            out = pipe.unpack_mirror(packed_t, full_t)
-        elif world > 1 and xmode == "cols":
-            if hi > lo:
-                pipe.power_win_mix_cols(lo, hi, out=full_t[lo:hi])
-            allgather_col_slabs(full_t, ranges)
-            out = full_t
-        elif world > 1 and xmode == "cols_dma":
-            _lib.check(lib.sfb_power_win_mix_block_dev(pipe._cmix, pipe.alm.data_ptr(), pipe.alm.data_ptr(), 0, 0, 0,
-                                                       pipe.nout, lo, hi, pm.ptr.value + 8 * lo * pipe.nout, pipe.nout,
-                                                       pipe._stream()))
-            _lib.check(lib.sfb_push_cols_to_peers(pm.ptr, pm.peer_array, len(pm.peer_ptrs), lo, hi, pipe.nout,
-                                                  pipe._stream()))
-            out = pm.tensor
-        elif world > 1 and fused:
-            _lib.check(lib.sfb_power_win_mix_dev_peers(pipe._cmix, pipe.alm.data_ptr(), pipe.alm.data_ptr(), 0, 0, lo, hi,
-                                                       pm.ptr, pm.peer_array,
-                                                       len(pm.peer_ptrs) if xmode == "stores" else 0, pipe.nout,
-                                                       pipe._stream()))
-            if xmode == "dma":
-                _lib.check(lib.sfb_push_rows_to_peers(pm.ptr, pm.peer_array, len(pm.peer_ptrs), lo, hi, pipe.nout,
-                                                      pipe.nout, pipe._stream()))
-            out = pm.tensor
+        if world == 1:
+            out = pipe.power_win_mix_rows(0, pipe.nout, out=out_t)
         else:
-            out = pipe.power_win_mix_rows(lo, hi, out=slab)
-            if world > 1:
-                out = gather_row_slabs(slab, ranges, pipe.nout)
+            out = pipe.power_win_mix_cols(lo, hi, out=out_t) if hi > lo else out_t
         evs[2].record()
         return out
 
@@ -306,55 +269,114 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed(fn, steps, collect=None):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+            if collect:
+                collect()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1) / steps
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
     for _ in range(args.warmup):
-        full = step()
+        step()
     barrier()
-    tim = _lib.timings()
-    stage_ms = {"stage1": [], "wl": [], "what": [], "block": [], "fill": [], "stage1_incl_gather": [], "stage23_incl_exchange": []}
-    if world > 1 and xmode in ("packed", "pull"):
-        stage_ms.update({"exchange": [], "unpack": []})
-    launches_per_step = 0
+    stage_ms = {"stage1": [], "wl": [], "what": [], "block": [], "fill": [], "stage1_incl_gather": [], "stage23": []}
+    launches = [0]
+
+    def collect():
+        tim = _lib.timings()
+        for k, key in (("stage1", "stage1_ms"), ("wl", "wl_ms"), ("what", "what_ms"), ("block", "block_ms"), ("fill", "fill_ms")):
+            stage_ms[k].append(tim[key])
+        torch.cuda.synchronize()
+        stage_ms["stage1_incl_gather"].append(evs[0].elapsed_time(evs[1]))
+        stage_ms["stage23"].append(evs[1].elapsed_time(evs[2]))
+        launches[0] = int(tim["launches"])
+        collect.flops = tim["block_flops"]
+
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for _ in range(args.steps):
-        full = step()
-        tim = _lib.timings()
-        stage_ms["stage1"].append(tim["stage1_ms"])
-        stage_ms["wl"].append(tim["wl_ms"])
-        stage_ms["what"].append(tim["what_ms"])
-        stage_ms["block"].append(tim["block_ms"])
-        stage_ms["fill"].append(tim["fill_ms"])
-        torch.cuda.synchronize()
-        stage_ms["stage1_incl_gather"].append(evs[0].elapsed_time(evs[1]))
-        stage_ms["stage23_incl_exchange"].append(evs[1].elapsed_time(evs[2]))
-        if world > 1 and xmode in ("packed", "pull"):
-            stage_ms["exchange"].append(evs[3].elapsed_time(evs[4]))
-            stage_ms["unpack"].append(evs[4].elapsed_time(evs[2]))
-        launches_per_step = int(tim["launches"])
-    ev1.record()
-    barrier()
+    ms = timed(step, args.steps, collect)
     clocks = sampler.stop() if rank == 0 else None
-    ms = ev0.elapsed_time(ev1) / args.steps
-    if world > 1:
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
     value = n * n / (ms * 1e-3)
+    launches_per_step = launches[0]
+    sm = {k: statistics.mean(v) for k, v in stage_ms.items()}
+
+    # ---- correctness carried by the bench line: checksum (same formula for every N) and parity against a 1-rank recompute
+    full = step()
+    torch.cuda.synchronize()
+    if world == 1:
+        checksum = strided_checksum_cols(full, 0, n)
+        parity = None
+    else:
+        cs = torch.tensor([strided_checksum_cols(full, lo, n) if hi > lo else 0.0], device="cuda", dtype=torch.float64)
+        dist.all_reduce(cs)
+        checksum = float(cs.item())
+        # every rank recomputes, on its own GPU alone (full stage 1, no collective), a few of its columns
+        alm_sharded = pipe.alm.clone()
+        pipe.calc_wr_lm(d_win)
+        torch.cuda.synchronize()
+        err = float(((pipe.alm - alm_sharded).norm() / pipe.alm.norm()).item())
+        if hi > lo:
+            for c0 in sorted({lo, (lo + hi) // 2, max(lo, hi - 8)}):
+                c1 = min(hi, c0 + 8)
+                ref = pipe.power_win_mix_cols(c0, c1)
+                torch.cuda.synchronize()
+                err = max(err, float(((full[c0 - lo:c1 - lo] - ref).norm() / ref.norm()).item()))
+        e = torch.tensor([err], device="cuda", dtype=torch.float64)
+        dist.all_reduce(e, op=dist.ReduceOp.MAX)
+        parity = float(e.item())
+        if not parity < 1e-10:
+            raise SystemExit(f"bench.py: sharded result differs from the single-GPU recompute (rel err {parity:.3e})")
+
     per_rank = None
     if world > 1:
-        mine = {"rank": rank, "rows": [int(lo), int(hi)], **{k: round(statistics.mean(v), 3) for k, v in stage_ms.items()}}
+        mine = {"rank": rank, "cols": [int(lo), int(hi)], **{k: round(v, 3) for k, v in sm.items()}}
         per_rank = [None] * world
         dist.all_gather_object(per_rank, mine)
 
+    # ---- N > 1: the assembled mode (full matrix on every GPU), timed the same way and checked the same way
+    assembled = None
+    if world > 1 and not args.no_assembled:
+        off = pipe.packed_offsets()
+        pranges = pipe.packed_shard_ranges(world)
+        plo, phi_ = pranges[rank]
+        pb = PeerBuffer(int(off[-1]))
+        full_t = torch.empty((pipe.nout, pipe.nout), dtype=torch.float64, device="cuda")
+
+        def step_assembled():
+            pipe.calc_wr_lm_sharded(d_win)
+            if phi_ > plo:
+                pipe.power_win_mix_upper_packed(plo, phi_, pb.tensor)
+            stream_barrier(pipe)
+            pipe.unpack_mirror_pull(pb, pranges, full_t)
+            stream_barrier(pipe)
+
+        for _ in range(args.warmup):
+            step_assembled()
+        ams = timed(step_assembled, max(3, args.steps // 2))
+        acs = strided_checksum_cols(full_t, 0, n)
+        aerr = float(((full_t[lo:hi] - full).norm() / full.norm()).item()) if hi > lo else 0.0
+        e = torch.tensor([aerr], device="cuda", dtype=torch.float64)
+        dist.all_reduce(e, op=dist.ReduceOp.MAX)
+        assembled = {"ms_per_step": ams, "value": n * n / (ams * 1e-3), "unit": UNIT, "checksum": acs,
+                     "rel_err_vs_sharded": float(e.item()),
+                     "note": "full matrix on EVERY GPU: upper-packed column shards (l <= L blocks) pulled from their owners "
+                             "over NVLink inside the unpack+mirror kernel"}
+        del full_t
+        pb.close()
+
     # ---- roofline of the dominant kernel (measured live: CUDA events on the launching stream, inside the lib) ----
-    block_ms = statistics.mean(stage_ms["block"])
-    fill_ms = statistics.mean(stage_ms["fill"])
-    kern_ms = block_ms - fill_ms            # the DMMA block kernel(s) alone; block_ms includes the mirror-fill pass
-    stage1_ms = statistics.mean(stage_ms["stage1"])
+    kern_ms = sm["block"] - sm["fill"]     # the DMMA block kernel(s) alone; block_ms includes the mirror-fill pass
     dmma = np.zeros(1)
     _lib.check(lib.sfb_probe_dmma_tflops(_lib.ptr(dmma)))
     peaks, traffic = {}, {}
@@ -366,140 +388,55 @@ def run_b200(args):
         traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["kernels"]
     except (OSError, KeyError):
         pass
-    # algorithmic flops of the block kernel's share of F_alg: the two GEMM terms, for this rank's rows
     nl = np.asarray(wl.amodes.nmax_l, dtype=np.float64)
-    ells_mine = np.unique(wl.cmodes.lnn[0, lo:hi])      # l-blocks (row shard) or L-blocks (column shard): same model
+    ells_mine = np.unique(wl.cmodes.lnn[0, lo:hi])
     nn = nl[ells_mine][:, None] * nl[None, :]
     f_alg_block = float(np.sum(2 * nn * wl.nr ** 2 + 2 * nn * nn * wl.nr))
-    exec_tflops = tim["block_flops"] / (kern_ms * 1e-3) / 1e12
-    # ncu dram traffic of the block kernel launches (cfg4, N = 1 capture): only comparable for that workload
+    exec_tflops = collect.flops / (kern_ms * 1e-3) / 1e12
     regz_traffic = sum(v["traffic_bytes"] for k, v in traffic.items() if k.startswith("cmix_regz_kernel")) or None
     if world > 1 or str(args.config) != "4":
         regz_traffic = None
+    hbm = peaks.get("hbm_gbs")
     roofline = {
         "kernel": "cmix_regz_kernel (stage 2+3 block GEMMs, FP64 DMMA, all tile classes of one step)", "bound": "tensor",
         "achieved": exec_tflops, "peak": float(dmma[0]), "unit": "TFLOP/s", "frac": exec_tflops / float(dmma[0]),
         "traffic": regz_traffic,
-        "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the block-kernel launches of one step from the "
-                        "ncu --set full capture in profiles/r01_traffic.json; algorithmic bytes of these launches = the "
-                        "directly formed half of M (8·n²/2) + the Ŵ blocks read once",
         "algorithmic_bytes": 8.0 * (hi - lo) * n / (2 if world == 1 else 1),
         "peak_source": "FP64 DMMA probe measured in this run (MEASURED_PEAKS.json has no FP64 figure; nominal B200 "
                        "FP64 tensor peak is 37-40 TFLOP/s)",
         "algorithmic_tflops": f_alg_block / (kern_ms * 1e-3) / 1e12,
-        "algorithmic_flops": f_alg_block, "executed_flops": tim["block_flops"], "launch_ms": kern_ms,
-        "note": "achieved/frac count the DMMA flops the kernel EXECUTES (n padded to multiples of 8, +9% at cfg4) over its "
-                "own launch time.  SURVEY §8d's algorithmic count (2·nn·nr² + 2·nn²·nr per (l,L) block) is larger than the "
-                "executed one because only N<=N' tiles are formed and, at N=1, only the L>=l blocks (the mirror-fill pass "
-                "writes the other half): algorithmic_tflops can therefore exceed the peak and is not a utilisation figure",
-        "mirror_fill": {"ms": fill_ms, "bound": "hbm", "algorithmic_bytes": 8.0 * n * n if world == 1 else 0.0,
-                        "achieved_gbs": (8.0 * n * n / (fill_ms * 1e-3) / 1e9) if fill_ms > 0 else None,
-                        "hbm_peak_gbs": peaks.get("hbm_gbs"),
-                        "frac": (8.0 * n * n / (fill_ms * 1e-3) / 1e9 / peaks["hbm_gbs"])
-                        if (fill_ms > 0 and peaks.get("hbm_gbs")) else None,
-                        "traffic": (sum(v["traffic_bytes"] for k, v in traffic.items()
-                                        if k.startswith("cmix_mirror_fill_kernel")) or None) if world == 1 else None},
-        "stage1": {"ms": stage1_ms, "alg_tflops": wl.flops_alg_stage1() / (stage1_ms * 1e-3) / 1e12,
-                   "alg_gbs": wl.bytes_alg_stage1() / (stage1_ms * 1e-3) / 1e9,
-                   "hbm_peak_gbs": peaks.get("hbm_gbs"), "hbm_frac": (wl.bytes_alg_stage1() / (stage1_ms * 1e-3) / 1e9 /
-                                                                      peaks["hbm_gbs"]) if peaks.get("hbm_gbs") else None},
-        "stage3_write_gbs": 8.0 * (hi - lo) * n / (block_ms * 1e-3) / 1e9,
-        "stage_ms": {k: statistics.mean(v) for k, v in stage_ms.items()},
+        "algorithmic_flops": f_alg_block, "executed_flops": collect.flops, "launch_ms": kern_ms,
+        "note": "achieved/frac = DMMA flops the kernel EXECUTES (n padded to multiples of 8) over its own launch time; "
+                "SURVEY §8d's algorithmic count is larger because only N<=N' tiles (and at N=1 only L>=l blocks) are formed",
     }
+    fill_ms, s1_ms = sm["fill"], sm["stage1"]
+    roofline_fill = {"kernel": "cmix_mirror_fill_kernel", "ms": fill_ms, "bound": "hbm",
+                     "achieved": (8.0 * n * n / (fill_ms * 1e-3) / 1e9) if fill_ms > 0 else None, "peak": hbm, "unit": "GB/s",
+                     "frac": (8.0 * n * n / (fill_ms * 1e-3) / 1e9 / hbm) if (fill_ms > 0 and hbm) else None}
+    # useful Legendre-GEMM flops of one map2alm(niter=3) on this rank's shells: 7 passes (4 analyses + 3 syntheses) of
+    # Σ_m [l x ring] x [ring x 2 shells] with north/south rings folded: 2 · lmsize · 2nside · 2·shells per pass
+    shells_here = -(-wl.nr // world)
+    lmsize = (wl.LMAX + 1) * (wl.LMAX + 2) // 2
+    s1_exec = 7 * 2.0 * lmsize * (2 * wl.amodes.nside) * 2 * shells_here
+    roofline_stage1 = {"ms": s1_ms, "bound": "tensor",
+                       "executed_flops": s1_exec, "achieved": s1_exec / (s1_ms * 1e-3) / 1e12 if s1_ms > 0 else None,
+                       "peak": float(dmma[0]), "unit": "TFLOP/s",
+                       "frac": s1_exec / (s1_ms * 1e-3) / 1e12 / float(dmma[0]) if s1_ms > 0 else None,
+                       "alg_flops": wl.flops_alg_stage1() / world, "alg_bytes": wl.bytes_alg_stage1() / world,
+                       "alg_gbs": wl.bytes_alg_stage1() / world / (s1_ms * 1e-3) / 1e9 if s1_ms > 0 else None,
+                       "hbm_frac": (wl.bytes_alg_stage1() / world / (s1_ms * 1e-3) / 1e9 / hbm) if (hbm and s1_ms > 0) else None,
+                       "note": "executed_flops = useful (unpadded) DMMA flops of the 7 Legendre GEMM passes of one "
+                               "map2alm(niter=3) on this rank's shells, over the whole stage-1 time (ring FFT/DFT and alias "
+                               "passes included in the time, not in the flops); alg_* = SURVEY §8d's F1, B1"}
 
-    # ---- e2e through the public host API: pinned host window in, matrix out ----
+    # ---- e2e through the reference-facing host API (C ABI with HOST buffers) on `world` GPUs of this process ----
     e2e = None
-    if not args.no_e2e and world == 1:
-        nr, npix = win.shape
-        host_win_t = torch.empty((npix, nr), dtype=torch.float64).pin_memory()
-        host_win_t.copy_(torch.from_numpy(np.ascontiguousarray(win.T)))
-        host_win = host_win_t.numpy().T            # (nr, npix) Fortran-ordered view of pinned memory
-        out_t = torch.empty((n, n), dtype=torch.float64).pin_memory()
-        out = out_t.numpy().T                      # Fortran-ordered (n, n) view
-        del pipe, slab, full
-        torch.cuda.empty_cache()
-        with warnings.catch_warnings():
-            warnings.simplefilter("ignore", RuntimeWarning)
-            for _ in range(min(args.warmup, 2)):
-                sfb.power_win_mix(host_win, wl.wmodes, wl.cmodes, out=out)
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            k = max(1, min(args.steps, 3))
-            for _ in range(k):
-                M = sfb.power_win_mix(host_win, wl.wmodes, wl.cmodes, out=out)
-            torch.cuda.synchronize()
-            dt = (time.perf_counter() - t0) / k
-        e2e = {"value": n * n / dt, "unit": UNIT, "h2d_bytes_per_step": int(win.nbytes + wl.G.nbytes + wl.cmodes.lnn.nbytes),
-               "d2h_bytes_per_step": int(8 * n * n), "ms_per_step": dt * 1e3,
-               "api": "sfb_b200.power_win_mix(win, wmodes, cmodes) -> sfb_power_win_mix (C ABI, host pointers)",
-               "checksum": float(M[:: max(1, n // 97), :: max(1, n // 89)].sum())}
-        # the binned call of cfg4 (BASELINE.json: "binned ClnnBinnedModes output"): N = w̃ M v, Δl = 4
-        try:
-            wt, vv = sfb.bandpower_binning_weights(wl.cmodes, dl=4)
-            bc = sfb.ClnnBinnedModes(wt, vv, wl.cmodes)
-            outN_t = torch.empty((vv.shape[1], wt.shape[0]), dtype=torch.float64).pin_memory()
-            outN = outN_t.numpy().T
-            with warnings.catch_warnings():
-                warnings.simplefilter("ignore", RuntimeWarning)
-                sfb.power_win_mix(host_win, wt, vv, wl.wmodes, bc, out=outN)
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                for _ in range(k):
-                    sfb.power_win_mix(host_win, wt, vv, wl.wmodes, bc, out=outN)
-                torch.cuda.synchronize()
-                dtb = (time.perf_counter() - t0) / k
-            e2e["binned"] = {"ms_per_step": dtb * 1e3, "value": n * n / dtb, "unit": UNIT, "LNN": int(wt.shape[0]),
-                             "d2h_bytes_per_step": int(8 * wt.shape[0] * vv.shape[1]),
-                             "note": "power_win_mix(win, w̃, v, wmodes, bcmodes) with Δl=4: all lnnsize² elements of M are "
-                                     "formed on the device, only N = w̃Mv returns to the host"}
-        except Exception as exc:  # noqa: BLE001
-            e2e["binned"] = {"error": str(exc)}
-    elif world > 1 and not args.no_e2e:
-        # N > 1: every rank uploads the shells it transforms from pinned host memory, the sharded step runs, and rank 0
-        # reads the assembled matrix back into pinned host memory (what a user of the one-process-per-GPU pipeline
-        # does to obtain M on the host).  Falls back to a note if anything in this leg fails.
-        e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
-               "note": "e2e is measured at N=1 through the host C ABI; multi-GPU runs keep shards device-resident"}
-        from sfb_b200.device import shard_shells
-        s_lo, s_hi = shard_shells(wl.nr, world)[rank]
-        ok, host_shard, host_out, err = 1.0, None, None, ""
-        try:    # the only steps that can fail on one rank alone: host allocations
-            host_shard = torch.empty((d_win.shape[0], max(1, s_hi - s_lo)), dtype=torch.float64).pin_memory()
-            if s_hi > s_lo:
-                host_shard.copy_(d_win[:, s_lo:s_hi].cpu())
-            host_out = torch.empty((n, n), dtype=torch.float64).pin_memory() if rank == 0 else None
-        except Exception as exc:  # noqa: BLE001
-            ok, err = 0.0, str(exc)
-        flag = torch.tensor([ok], device="cuda", dtype=torch.float64)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)     # every rank takes the same branch: no collective can hang
-        if float(flag.item()) == 1.0:
-            def e2e_step():
-                if s_hi > s_lo:
-                    d_win[:, s_lo:s_hi].copy_(host_shard, non_blocking=True)
-                out = step()
-                if rank == 0:
-                    host_out.copy_(out, non_blocking=True)
-                torch.cuda.synchronize()
-
-            e2e_step()
-            barrier()
-            t0 = time.perf_counter()
-            k = max(1, min(args.steps, 3))
-            for _ in range(k):
-                e2e_step()
-            barrier()
-            dt = torch.tensor([(time.perf_counter() - t0) / k], device="cuda", dtype=torch.float64)
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-            dt = float(dt.item())
-            e2e = {"value": n * n / dt, "unit": UNIT, "h2d_bytes_per_step": int(win.nbytes),
-                   "d2h_bytes_per_step": int(8 * n * n), "ms_per_step": dt * 1e3,
-                   "api": "DevicePipeline (one process per GPU): pinned host shells in on every rank, sharded step, "
-                          "assembled matrix out to pinned host memory on rank 0"}
-        elif err:
-            e2e["error"] = err
-    elif world > 1:
-        e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
-               "note": "--no-e2e"}
+    if not args.no_e2e:
+        del full
+        if rank == 0:
+            e2e = run_e2e(sfb, wl, world, args)
+        if world > 1:
+            dist.barrier()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -511,28 +448,105 @@ def run_b200(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": dict(wl.describe(), l2="working set (win 0.4 GB + ring buffers 0.3 GB + M %.1f GB) exceeds the "
-                                             "126 MB L2, no explicit flush" % (8e-9 * n * n),
-                           parallelism=f"sharded x{world}" + (" (stage 1 shell-sharded + NCCL all-gather of W_lm(r); "
-                                                                   "M sharded by columns (L,N,N'): each rank forms the "
-                                                                   "l<=L blocks of its columns in upper-packed storage "
-                                                                   "(half the matrix bytes); pull: the unpack+mirror "
-                                                                   "kernel reads every column from its owner's peer-"
-                                                                   "mapped buffer over NVLink (exchange fused into the "
-                                                                   "kernel); packed: in-place NCCL all-gather of the "
-                                                                   f"slabs first; exchange={xmode})"
-                                                                   if world > 1 else "")),
-            "roofline": roofline, "per_rank": per_rank, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
-            "clocks": clocks,
+            "data": "synthetic", "config": wl.describe(),
+            "l2": "working set (win 0.4 GB + ring buffers 0.3 GB + M %.1f GB) exceeds the 126 MB L2, no explicit flush"
+                  % (8e-9 * n * n),
+            "output_mode": ("full matrix in HBM" if world == 1 else
+                            f"sharded x{world}: stage 1 by shells + NCCL all-gather of W_lm(r); M by full-height column "
+                            "ranges (L,N,N'), each left in its owner's HBM (no assembly); see `assembled` for the "
+                            "all-GPUs-hold-everything variant"),
+            "checksum": checksum, "parity_vs_n1": parity,
+            "roofline": roofline, "roofline_stage1": roofline_stage1, "roofline_mirror_fill": roofline_fill,
+            "stage_ms": sm, "per_rank": per_rank, "assembled": assembled,
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
         }
         print(json.dumps(line))
     if world > 1:
-        if pm is not None:
-            pm.close()
-        if pb is not None:
-            pb.close()
         dist.destroy_process_group()
+
+
+def run_e2e(sfb, wl, ndev, args):
+    """The reference-facing call `power_win_mix(win, wmodes, cmodes)` -> sfb_power_win_mix (C ABI, HOST buffers) with
+    sfb_set_devices(ndev): window in host memory in, full matrix in host memory out, every copy inside the timed region.
+    Page-locked buffers (sfb_host_alloc, what the Julia shim allocates) are the headline; the pageable variant is
+    reported next to it."""
+    n = wl.lnnsize
+    win = wl.win
+    nr, npix = win.shape
+    res = {"value": None, "unit": UNIT, "h2d_bytes_per_step": int(win.nbytes + wl.G.nbytes + wl.cmodes.lnn.nbytes),
+           "d2h_bytes_per_step": int(8 * n * n), "n_gpus": ndev,
+           "api": f"sfb_set_devices({ndev}); sfb_b200.power_win_mix(win, wmodes, cmodes) -> sfb_power_win_mix (C ABI, "
+                  "host pointers, one process)"}
+    try:
+        sfb.set_devices(ndev)
+        host_win = sfb.pinned_empty((nr, npix))
+        host_win[...] = win
+        out = sfb.pinned_empty((n, n))
+        k = max(1, min(args.steps, 5))
+
+        def run(w, o):
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore", RuntimeWarning)
+                for _ in range(2):
+                    sfb.power_win_mix(w, wl.wmodes, wl.cmodes, out=o)
+                t0 = time.perf_counter()
+                for _ in range(k):
+                    M = sfb.power_win_mix(w, wl.wmodes, wl.cmodes, out=o)
+                return (time.perf_counter() - t0) / k, M
+
+        dt, M = run(host_win, out)
+        from sfb_b200 import _lib
+        res.update({"value": n * n / dt, "ms_per_step": dt * 1e3, "buffers": "page-locked (sfb_host_alloc)",
+                    "checksum": float(M[:: max(1, n // 97), :: max(1, n // 89)].sum()), "stage_ms": _lib.timings()})
+        if not np.isfinite(M).all():
+            res["error"] = "non-finite result"
+        # pageable buffers: a plain Julia Matrix{Float64} for the result and the window
+        try:
+            pout = np.empty((n, n), order="F")
+            dtp, Mp = run(win, pout)
+            res["pageable"] = {"ms_per_step": dtp * 1e3, "value": n * n / dtp,
+                               "max_abs_diff_vs_pinned": float(np.abs(Mp[::97, ::89] - M[::97, ::89]).max())}
+            del pout, Mp
+        except Exception as exc:  # noqa: BLE001
+            res["pageable"] = {"error": str(exc)}
+        # the binned call of cfg4 (BASELINE.json: "binned ClnnBinnedModes output"): N = w̃ M v, Δl = 4 (single device)
+        try:
+            sfb.set_devices(1)
+            wt, vv = sfb.bandpower_binning_weights(wl.cmodes, dl=4)
+            bc = sfb.ClnnBinnedModes(wt, vv, wl.cmodes)
+            outN = sfb.pinned_empty((wt.shape[0], vv.shape[1]))
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore", RuntimeWarning)
+                sfb.power_win_mix(host_win, wt, vv, wl.wmodes, bc, out=outN)
+                t0 = time.perf_counter()
+                for _ in range(k):
+                    sfb.power_win_mix(host_win, wt, vv, wl.wmodes, bc, out=outN)
+                dtb = (time.perf_counter() - t0) / k
+            tb = _lib.timings()
+            hbm = None
+            try:
+                hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs")
+            except OSError:
+                pass
+            bms = tb["binned_ms"]
+            res["binned"] = {"ms_per_step": dtb * 1e3, "value": n * n / dtb, "unit": UNIT, "LNN": int(wt.shape[0]),
+                             "d2h_bytes_per_step": int(8 * wt.shape[0] * vv.shape[1]), "n_gpus": 1, "binned_ms": bms,
+                             "roofline": {"kernel": "binned_product_kernel", "bound": "hbm", "unit": "GB/s",
+                                          "achieved": 8.0 * n * n / (bms * 1e-3) / 1e9 if bms > 0 else None, "peak": hbm,
+                                          "frac": (8.0 * n * n / (bms * 1e-3) / 1e9 / hbm) if (hbm and bms > 0) else None,
+                                          "algorithmic_bytes": 8.0 * n * n},
+                             "note": "power_win_mix(win, w̃, v, wmodes, bcmodes) with Δl=4: all lnnsize² elements of M are "
+                                     "formed on the device, only N = w̃Mv returns to the host"}
+        except Exception as exc:  # noqa: BLE001
+            res["binned"] = {"error": str(exc)}
+    except Exception as exc:  # noqa: BLE001
+        res["error"] = str(exc)
+    finally:
+        try:
+            sfb.set_devices(1)
+        except Exception:  # noqa: BLE001
+            pass
+    return res
 
 
 def main():

@@ -39,6 +39,22 @@ int32_t sfb_version(void);
 const char* sfb_last_error(void);
 int32_t sfb_device_count(int32_t* count);
 int32_t sfb_set_device(int32_t device);
+/* Multi-GPU behind the host-pointer boundary.  After sfb_set_devices(n), n in 1..8, the host-pointer
+ * entry points sfb_power_win_mix and sfb_calc_wr_lm run on devices 0..n-1 of THIS process (one worker thread per device
+ * for the duration of the call, peer access over NVLink required): every GPU uploads 1/n of the window over its own
+ * PCIe link, transforms nr/n shells, forms a contiguous full-height column range of M and copies it straight into the
+ * caller's M_out.  This replaces the reference's parallel gather, the pmap over output rows inside _power_win_mix
+ * (src/windows.jl:834-861), and the serial shell loop of calc_Wr_lm (src/windows.jl:531-535).  n = 1 restores the
+ * single-device path on the current device.  The other entry points keep using the current device.                 */
+int32_t sfb_set_devices(int32_t n);
+int32_t sfb_get_devices(int32_t* n);
+/* Page-locked host memory for callers that want full PCIe speed (a pageable Julia Matrix is staged by the driver at a
+ * fraction of it): the Julia shim allocates the result with sfb_host_alloc and wraps it (unsafe_wrap + finalizer), or
+ * pins an existing array for the lifetime of several calls with sfb_host_register / sfb_host_unregister.          */
+int32_t sfb_host_alloc(void** ptr, int64_t bytes);
+int32_t sfb_host_free(void* ptr);
+int32_t sfb_host_register(void* ptr, int64_t bytes);
+int32_t sfb_host_unregister(void* ptr);
 /* times (ms, CUDA events) of the last call on this thread's plans:
  *   [0] stage 1 total, [1] W_{L1} build, [2] 3j table, [3] Ŵ_{ℓL} build, [4] block kernel,
  *   [5] executed DMMA flops of [4], [6] kernel launches of the last power_win_mix, [7] binned products */
@@ -135,20 +151,6 @@ int32_t sfb_cmix_plan_destroy(sfb_cmix_plan* plan);
 int32_t sfb_power_win_mix_dev(sfb_cmix_plan* plan, const double* d_alm1, const double* d_alm2, int32_t div2Lp1,
                               int32_t interchange_NN, int64_t row_lo, int64_t row_hi, double* d_M, int64_t ldM,
                               void* stream);
-/* Fused stage 2+3 + all-gather: rows [row_lo,row_hi) are written into the FULL column-major matrix on this
- * device (d_M_full, leading dimension ldM >= nout) and, with P2P stores over NVLink, into the full matrices of
- * up to 7 peers (pointers obtained with sfb_ipc_open).  Callers synchronise the stream and barrier across ranks
- * before reading.                                                                                   */
-int32_t sfb_power_win_mix_dev_peers(sfb_cmix_plan* plan, const double* d_alm1, const double* d_alm2, int32_t div2Lp1,
-                                    int32_t interchange_NN, int64_t row_lo, int64_t row_hi, double* d_M_full,
-                                    double* const* peer_M_full, int32_t npeers, int64_t ldM, void* stream);
-/* copy-engine variant of the exchange: rows [row_lo,row_hi) of this device's full matrix -> the same rows of each
- * peer's full matrix (one pitched P2P copy per peer, concurrent, ordered after and joined back into `stream`) */
-int32_t sfb_push_rows_to_peers(const double* d_M_full, double* const* peer_M_full, int32_t npeers, int64_t row_lo,
-                               int64_t row_hi, int64_t ncols, int64_t ldM, void* stream);
-/* columns [col_lo,col_hi) (a contiguous slab) -> the same columns of each peer's full matrix */
-int32_t sfb_push_cols_to_peers(const double* d_M_full, double* const* peer_M_full, int32_t npeers, int64_t col_lo,
-                               int64_t col_hi, int64_t ldM, void* stream);
 /* device buffers shareable between the per-GPU processes of one node (cudaIpc*); handle64 is 64 bytes */
 int32_t sfb_ipc_alloc(void** dptr, int64_t bytes, void* handle64);
 int32_t sfb_ipc_open(const void* handle64, void** dptr);

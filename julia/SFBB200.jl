@@ -21,6 +21,20 @@ function check(status::Integer)
     error(msg)                      # ErrorException, like error()/@assert in the reference
 end
 
+# Multi-GPU: ONE call.  After `set_devices(n)` power_win_mix / calc_Wr_lm shard over GPUs 0..n-1 inside the library
+# (it replaces the pmap gather of src/windows.jl:834-861); nothing else in the shim changes.
+set_devices(n::Integer) = check(ccall((:sfb_set_devices, libsfb), Int32, (Int32,), n))
+
+# Result arrays in page-locked memory (sfb_host_alloc), so that every GPU copies its column slab at full PCIe speed;
+# freed by a finalizer.  A plain `Matrix{Float64}(undef, ...)` works too (pageable: the driver stages the copies).
+function pinned_matrix(::Type{T}, dims::Integer...) where {T}
+    p = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:sfb_host_alloc, libsfb), Int32, (Ptr{Ptr{Cvoid}}, Int64), p, max(1, prod(dims) * sizeof(T))))
+    A = unsafe_wrap(Array, Ptr{T}(p[]), dims; own=false)
+    finalizer(_ -> ccall((:sfb_host_free, libsfb), Int32, (Ptr{Cvoid},), p[]), A)
+    return A
+end
+
 # r .* √Δr .* precompute_gnlr(amodes, wmodes)   (src/windows.jl:799) — stays in Julia (input of the path).
 # precompute_gnlr allocates `fill(NaN, nr, size(amodes.basisfunctions.knl)...)` (src/windows.jl:551); for
 # AnlmModes(kmax, rmin, rmax) that knl table is the UNTRIMMED one (SphericalBesselGNLs.jl:313-316), larger than
@@ -87,7 +101,7 @@ function power_win_mix(win1::AbstractMatrix{Float64}, win2::AbstractMatrix{Float
     lnn = cmodes.lnn
     lnnsize = getlnnsize(cmodes)
     n = lnnsize - lnn_min + 1
-    mix = Matrix{Float64}(undef, n, n)
+    mix = pinned_matrix(Float64, n, n)
     w1 = win1 isa Matrix{Float64} ? win1 : Matrix{Float64}(win1)
     w2 = win2 === win1 ? w1 : (win2 isa Matrix{Float64} ? win2 : Matrix{Float64}(win2))
     nr, npix = size(w1)

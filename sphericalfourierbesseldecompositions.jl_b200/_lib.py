@@ -19,6 +19,12 @@ SIGNATURES = {
     "sfb_last_error": (C.c_char_p, []),
     "sfb_device_count": (_i32, [C.POINTER(_i32)]),
     "sfb_set_device": (_i32, [_i32]),
+    "sfb_set_devices": (_i32, [_i32]),
+    "sfb_get_devices": (_i32, [C.POINTER(_i32)]),
+    "sfb_host_alloc": (_i32, [C.POINTER(_vp), _i64]),
+    "sfb_host_free": (_i32, [_vp]),
+    "sfb_host_register": (_i32, [_vp, _i64]),
+    "sfb_host_unregister": (_i32, [_vp]),
     "sfb_get_timings": (_i32, [_f64p, _i32]),
     "sfb_probe_dmma_tflops": (_i32, [_f64p]),
     "sfb_calc_wr_lm": (_i32, [_f64p, _i64, _i64, _i64, _i64, _i64, _i64, _i32, _f64p]),
@@ -49,9 +55,6 @@ SIGNATURES = {
     "sfb_cmix_unpack_mirror_dev": (_i32, [_vp, _f64p, _i32, _i32, _f64p, _i64, _vp]),
     "sfb_cmix_unpack_mirror_peers_dev": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _f64p, _i64, _vp]),
     "sfb_power_win_mix_block_dev": (_i32, [_vp, _f64p, _f64p, _i32, _i32, _i64, _i64, _i64, _i64, _f64p, _i64, _vp]),
-    "sfb_push_cols_to_peers": (_i32, [_f64p, _vp, _i32, _i64, _i64, _i64, _vp]),
-    "sfb_power_win_mix_dev_peers": (_i32, [_vp, _f64p, _f64p, _i32, _i32, _i64, _i64, _f64p, _vp, _i32, _i64, _vp]),
-    "sfb_push_rows_to_peers": (_i32, [_f64p, _vp, _i32, _i64, _i64, _i64, _i64, _vp]),
     "sfb_ipc_alloc": (_i32, [C.POINTER(_vp), _i64, _vp]),
     "sfb_ipc_open": (_i32, [_vp, C.POINTER(_vp)]),
     "sfb_ipc_close": (_i32, [_vp]),

@@ -6,10 +6,14 @@
 #include "common.cuh"
 #include "sht.cuh"
 
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <thread>
+#include <vector>
 
 namespace sfb {
 static thread_local std::string g_err;
@@ -34,24 +38,37 @@ static double g_times[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 static ShtPlan* g_pend_sht = nullptr;
 static CmixPlan* g_pend_cmix = nullptr;
 
-// ---- cached stage-1 plan (tables depend only on nside/lmax/nr) ----
-static ShtPlan* g_sht = nullptr;
-static int g_sht_dev = -1;
+// ---- per-device state: cached plans and the reusable workspace are keyed by the CUDA device they live on ----
+constexpr int kMaxDev = 8;        // devices driven by one call (sfb_set_devices)
+constexpr int kMaxDevId = 64;     // highest CUDA device ordinal + 1 this library keeps state for
+static int g_ndev = 1;            // sfb_set_devices(n): the host-pointer entry points shard over devices 0..n-1
+
+struct ShtCache {
+    ShtPlan* p = nullptr;
+};
+static ShtCache g_sht_cache[kMaxDevId];
+
+static int current_device(int* dev) {
+    SFB_CUDA_OK(cudaGetDevice(dev));
+    SFB_REQUIRE(*dev >= 0 && *dev < kMaxDevId, "CUDA device ordinal out of range");
+    return 0;
+}
+
+// cached stage-1 plan of the current device (tables depend only on nside/lmax/nr)
 static int get_sht_plan(ShtPlan** out, int64_t nside_in, int64_t nside_out, int64_t lmax, int64_t nr) {
     int dev = 0;
-    SFB_CUDA_OK(cudaGetDevice(&dev));
-    if (g_sht && g_sht_dev == dev && g_sht->nside_in == nside_in && g_sht->nside == nside_out && g_sht->lmax == lmax &&
-        g_sht->nr == nr) {
-        *out = g_sht;
+    SFB_TRY(current_device(&dev));
+    ShtPlan*& g = g_sht_cache[dev].p;
+    if (g && g->nside_in == nside_in && g->nside == nside_out && g->lmax == lmax && g->nr == nr) {
+        *out = g;
         return 0;
     }
-    if (g_sht) {
-        sht_plan_destroy(g_sht);
-        g_sht = nullptr;
+    if (g) {
+        sht_plan_destroy(g);
+        g = nullptr;
     }
-    SFB_TRY(sht_plan_create(&g_sht, nside_in, nside_out, lmax, nr));
-    g_sht_dev = dev;
-    *out = g_sht;
+    SFB_TRY(sht_plan_create(&g, nside_in, nside_out, lmax, nr));
+    *out = g;
     return 0;
 }
 
@@ -63,13 +80,19 @@ static int npix2nside(int64_t npix, int64_t* nside) {
 }
 
 // H2D of the Julia array win (nr x npix, leading dimension ld) -> device [pixel][nr]
-static int upload_win(const double* win, int64_t nr, int64_t npix, int64_t ld, DevBuf<double>& d) {
+static int h2d_rows(double* dst, const double* src, int64_t nr, int64_t npix, int64_t ld, cudaStream_t st) {
+    if (ld == nr)
+        SFB_CUDA_OK(cudaMemcpyAsync(dst, src, (size_t)nr * npix * sizeof(double), cudaMemcpyHostToDevice, st));
+    else
+        SFB_CUDA_OK(cudaMemcpy2DAsync(dst, nr * sizeof(double), src, ld * sizeof(double), nr * sizeof(double), (size_t)npix,
+                                      cudaMemcpyHostToDevice, st));
+    return 0;
+}
+static int upload_win(const double* win, int64_t nr, int64_t npix, int64_t ld, DevBuf<double>& d, cudaStream_t st) {
     SFB_REQUIRE(win, "win is null");
     SFB_REQUIRE(ld >= nr, "ld_win < nr");
     SFB_TRY(d.alloc((size_t)nr * npix));
-    SFB_CUDA_OK(cudaMemcpy2D(d.p, nr * sizeof(double), win, ld * sizeof(double), nr * sizeof(double), npix,
-                             cudaMemcpyHostToDevice));
-    return 0;
+    return h2d_rows(d.p, win, nr, npix, ld, st);
 }
 
 __global__ void finite_check_kernel(const double* __restrict__ x, size_t n, int* flag) {
@@ -130,84 +153,112 @@ static bool async_enabled() { return getenv("SFB_SYNC_TIMINGS") == nullptr; }   
         g_pend_cmix = (plan_);                      \
     } while (0)
 
-// Device workspace reused across host-pointer calls (cudaMalloc / cudaFree of multi-GB buffers is slow).
+// Device workspace reused across host-pointer calls (cudaMalloc / cudaFree of multi-GB buffers is slow); one per
+// device, so that a call after sfb_set_device(other) never touches buffers of the previous device.
 struct Workspace {
     DevBuf<double> win, alm1, alm2, slab[2], M;
+    DevBuf<double> slice[2], shard, almshard[2];   // multi-device runs: pixel slice of win1/win2, shell shard, alm shard
     DevBuf<int> flag;
-    cudaStream_t copy = nullptr;
+    cudaStream_t main = nullptr, copy = nullptr;
     cudaEvent_t computed[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
-    int dev = -1;
-    int init() {
-        int d = 0;
-        SFB_CUDA_OK(cudaGetDevice(&d));
-        if (copy && d == dev) return 0;
+    cudaEvent_t ev_slice[2] = {nullptr, nullptr}, ev_alm[2] = {nullptr, nullptr};
+    bool ready = false;
+    int init() {   // on the current device
+        if (ready) return 0;
+        SFB_CUDA_OK(cudaStreamCreateWithFlags(&main, cudaStreamNonBlocking));
         SFB_CUDA_OK(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
         for (int i = 0; i < 2; ++i) {
             SFB_CUDA_OK(cudaEventCreateWithFlags(&computed[i], cudaEventDisableTiming));
             SFB_CUDA_OK(cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming));
+            SFB_CUDA_OK(cudaEventCreateWithFlags(&ev_slice[i], cudaEventDisableTiming));
+            SFB_CUDA_OK(cudaEventCreateWithFlags(&ev_alm[i], cudaEventDisableTiming));
         }
-        dev = d;
+        ready = true;
         return 0;
     }
 };
-static Workspace g_ws;
+static Workspace g_ws_dev[kMaxDevId];
+static int get_ws(Workspace** out) {
+    int dev = 0;
+    SFB_TRY(current_device(&dev));
+    SFB_TRY(g_ws_dev[dev].init());
+    *out = &g_ws_dev[dev];
+    return 0;
+}
 
-// Stage 2+3 for all columns, pipelined with the device->host copy: the matrix is produced in column slabs
-// (contiguous in column-major order); while slab k is copied to the caller's buffer, slab k+1 is computed.
+// Stage 2+3 pipelined with the device->host copy: the matrix is produced in column slabs (contiguous in column-major
+// order); while slab k is copied to the caller's buffer, slab k+1 is computed.
 static bool mirror_enabled() { return getenv("SFB_NO_MIRROR") == nullptr; }
 
-static int cmix_to_host_pipelined(CmixPlan* p, const double* a1, const double* a2, int div2Lp1, int interchange,
-                                  double* M_out) {
-    SFB_TRY(g_ws.init());
+struct CmixTimes {
+    float wl = 0, what = 0, block = 0, fill = 0;
+    double flops = 0;
+    int launches = 0;
+    void add(const CmixPlan* p) {
+        wl += p->t_wl;
+        what += p->t_what;
+        block += p->t_block;
+        fill += p->t_fill;
+        flops += p->flops_executed;
+        launches += p->launches;
+    }
+    void store(CmixPlan* p) const {
+        p->t_wl = wl;
+        p->t_what = what;
+        p->t_block = block;
+        p->t_fill = fill;
+        p->flops_executed = flops;
+        p->launches = launches;
+    }
+};
+
+// Columns [col_lo, col_hi) (all rows) of M -> M_out + col_lo * n on the host.  Whole matrix + auto-correlation: mirror
+// mode (step k forms the blocks (l in chunk k, L >= l) and their mirror images in the full device matrix, after which
+// the columns of chunk k are complete and can leave); otherwise plain full-height column slabs.
+static int cmix_cols_to_host(CmixPlan* p, Workspace& ws, const double* a1, const double* a2, int div2Lp1, int interchange,
+                             int64_t col_lo, int64_t col_hi, int nchunks, double* M_out) {
     const int64_t n = p->nout;
-    const bool mirror = (a1 == a2) && mirror_enabled();
-    // mirror mode: step k forms the blocks (l in chunk k, L >= l) and their mirror images in the full device
-    // matrix, after which the columns of chunk k are complete and can leave; otherwise plain column slabs.
-    const auto chunks = mirror ? cmix_row_chunks_mirror(p, 8) : cmix_col_chunks(p, 8);
+    if (col_hi <= col_lo) return 0;
+    const bool whole = (col_lo == 0 && col_hi == n);
+    const bool mirror = whole && (a1 == a2) && mirror_enabled();
+    const auto chunks = mirror ? cmix_row_chunks_mirror(p, nchunks) : cmix_col_chunks_range(p, col_lo, col_hi, nchunks);
     int64_t maxc = 0;
     for (auto& c : chunks) maxc = std::max(maxc, c.second - c.first);
     if (mirror) {
-        SFB_TRY(g_ws.M.alloc((size_t)n * n));
+        SFB_TRY(ws.M.alloc((size_t)n * n));
     } else {
-        for (int i = 0; i < 2 && i < (int)chunks.size(); ++i) SFB_TRY(g_ws.slab[i].alloc((size_t)maxc * n));
+        for (int i = 0; i < 2 && i < (int)chunks.size(); ++i) SFB_TRY(ws.slab[i].alloc((size_t)maxc * n));
     }
-    SFB_TRY(g_ws.flag.alloc(1));
-    SFB_CUDA_OK(cudaMemsetAsync(g_ws.flag.p, 0, sizeof(int), 0));
-    float t_wl = 0, t_what = 0, t_block = 0;
-    double flops = 0;
-    int launches = 0;
+    SFB_TRY(ws.flag.alloc(1));
+    cudaStream_t st = ws.main;
+    SFB_CUDA_OK(cudaMemsetAsync(ws.flag.p, 0, sizeof(int), st));
+    CmixTimes tt;
     for (size_t k = 0; k < chunks.size(); ++k) {
         const int b = (int)(k & 1);
         const int64_t c0 = chunks[k].first, c1 = chunks[k].second;
         double* src = nullptr;
         if (mirror) {
-            SFB_TRY(cmix_run(p, a1, a2, div2Lp1, interchange, c0, c1, 0, n, g_ws.M.p, n, 0, nullptr, 0, k > 0, true));
-            src = g_ws.M.p + c0 * n;
+            SFB_TRY(cmix_run(p, a1, a2, div2Lp1, interchange, c0, c1, 0, n, ws.M.p, n, st, nullptr, 0, k > 0, true));
+            src = ws.M.p + c0 * n;
         } else {
-            if (k >= 2) SFB_CUDA_OK(cudaEventSynchronize(g_ws.copied[b]));  // slab free again
-            SFB_TRY(cmix_run(p, a1, a2, div2Lp1, interchange, 0, n, c0, c1, g_ws.slab[b].p, n, 0, nullptr, 0, k > 0));
-            src = g_ws.slab[b].p;
+            if (k >= 2) SFB_CUDA_OK(cudaEventSynchronize(ws.copied[b]));  // slab free again
+            SFB_TRY(cmix_run(p, a1, a2, div2Lp1, interchange, 0, n, c0, c1, ws.slab[b].p, n, st, nullptr, 0, k > 0));
+            src = ws.slab[b].p;
         }
-        t_wl += p->t_wl;
-        t_what += p->t_what;
-        t_block += p->t_block;
-        flops += p->flops_executed;
-        launches += p->launches;
-        finite_check_kernel<<<512, 256, 0, 0>>>(src, (size_t)(c1 - c0) * n, g_ws.flag.p);
-        SFB_CUDA_OK(cudaEventRecord(g_ws.computed[b], 0));
-        SFB_CUDA_OK(cudaStreamWaitEvent(g_ws.copy, g_ws.computed[b], 0));
+        tt.add(p);
+        finite_check_kernel<<<512, 256, 0, st>>>(src, (size_t)(c1 - c0) * n, ws.flag.p);
+        SFB_CUDA_OK(cudaEventRecord(ws.computed[b], st));
+        SFB_CUDA_OK(cudaStreamWaitEvent(ws.copy, ws.computed[b], 0));
         SFB_CUDA_OK(cudaMemcpyAsync(M_out + c0 * n, src, (size_t)(c1 - c0) * n * sizeof(double), cudaMemcpyDeviceToHost,
-                                    g_ws.copy));
-        SFB_CUDA_OK(cudaEventRecord(g_ws.copied[b], g_ws.copy));
+                                    ws.copy));
+        SFB_CUDA_OK(cudaEventRecord(ws.copied[b], ws.copy));
     }
-    SFB_CUDA_OK(cudaStreamSynchronize(g_ws.copy));
-    p->t_wl = t_wl;
-    p->t_what = t_what;
-    p->t_block = t_block;
-    p->flops_executed = flops;
-    p->launches = launches + (int)chunks.size();
+    SFB_CUDA_OK(cudaStreamSynchronize(ws.copy));
+    tt.launches += (int)chunks.size();
+    tt.store(p);
     int h = 0;
-    SFB_CUDA_OK(cudaMemcpy(&h, g_ws.flag.p, sizeof(int), cudaMemcpyDeviceToHost));
+    SFB_CUDA_OK(cudaMemcpyAsync(&h, ws.flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SFB_CUDA_OK(cudaStreamSynchronize(st));
     if (h) {  // @assert all(isfinite.(mix))  src/windows.jl:803
         set_error("AssertionError: all(isfinite.(mix))");
         return 4;
@@ -216,7 +267,7 @@ static int cmix_to_host_pipelined(CmixPlan* p, const double* a1, const double* a
 }
 
 // Host-pointer entry points reuse the stage-2/3 plan (index tables, radial basis, 3j table, Ŵ workspace) when the
-// caller passes the same tables again: keyed by the sizes and an FNV-1a hash of the lnn and G bytes.
+// caller passes the same tables again: keyed by the sizes and an FNV-1a hash of the lnn and G bytes, per device.
 static uint64_t fnv1a(const void* data, size_t bytes, uint64_t h = 1469598103934665603ull) {
     const uint64_t* w = static_cast<const uint64_t*>(data);
     for (size_t i = 0; i < bytes / 8; ++i) {
@@ -225,28 +276,38 @@ static uint64_t fnv1a(const void* data, size_t bytes, uint64_t h = 1469598103934
     }
     return h;
 }
+struct PlanKey {
+    uint64_t hash = 0;
+    int64_t dims[5] = {0, 0, 0, 0, 0};
+    bool operator==(const PlanKey& o) const { return hash == o.hash && std::memcmp(dims, o.dims, sizeof(dims)) == 0; }
+};
 struct PlanCache {
     CmixPlan* p = nullptr;
-    uint64_t key = 0;
-    int64_t dims[5] = {0, 0, 0, 0, 0};
-    int dev = -1;
+    PlanKey key;
 };
-static PlanCache g_plan_cache;
+static PlanCache g_plan_cache[kMaxDevId];
 
 struct PlanGuard {  // non-owning handle on the cached plan
     CmixPlan* p = nullptr;
 };
 
-static int get_cmix_plan(CmixPlan** out, const int64_t* lnn, int64_t lnnsize, int64_t lnn_min, const double* G,
-                         int64_t nr, int64_t nmax, int64_t lmax) {
+static int make_plan_key(PlanKey* k, const int64_t* lnn, int64_t lnnsize, int64_t lnn_min, const double* G, int64_t nr,
+                         int64_t nmax, int64_t lmax) {
     SFB_REQUIRE(lnn && G && lnnsize >= 1 && nr >= 1 && nmax >= 1 && lmax >= 0, "bad mode tables");
-    int dev = 0;
-    SFB_CUDA_OK(cudaGetDevice(&dev));
-    uint64_t key = fnv1a(lnn, (size_t)lnnsize * 3 * sizeof(int64_t));
-    key = fnv1a(G, (size_t)nr * nmax * (lmax + 1) * sizeof(double), key);
+    k->hash = fnv1a(lnn, (size_t)lnnsize * 3 * sizeof(int64_t));
+    k->hash = fnv1a(G, (size_t)nr * nmax * (lmax + 1) * sizeof(double), k->hash);
     const int64_t dims[5] = {lnnsize, lnn_min, nr, nmax, lmax};
-    PlanCache& c = g_plan_cache;
-    if (c.p && c.dev == dev && c.key == key && std::memcmp(c.dims, dims, sizeof(dims)) == 0) {
+    std::memcpy(k->dims, dims, sizeof(dims));
+    return 0;
+}
+
+// cached stage-2/3 plan of the current device
+static int get_cmix_plan_keyed(CmixPlan** out, const PlanKey& key, const int64_t* lnn, int64_t lnnsize, int64_t lnn_min,
+                               const double* G, int64_t nr, int64_t nmax, int64_t lmax) {
+    int dev = 0;
+    SFB_TRY(current_device(&dev));
+    PlanCache& c = g_plan_cache[dev];
+    if (c.p && c.key == key) {
         *out = c.p;
         return 0;
     }
@@ -256,36 +317,301 @@ static int get_cmix_plan(CmixPlan** out, const int64_t* lnn, int64_t lnnsize, in
     }
     SFB_TRY(cmix_plan_create(&c.p, lnn, lnnsize, lnn_min, G, nr, nmax, lmax));
     c.key = key;
-    c.dev = dev;
-    std::memcpy(c.dims, dims, sizeof(dims));
     *out = c.p;
     return 0;
 }
+static int get_cmix_plan(CmixPlan** out, const int64_t* lnn, int64_t lnnsize, int64_t lnn_min, const double* G,
+                         int64_t nr, int64_t nmax, int64_t lmax) {
+    PlanKey key;
+    SFB_TRY(make_plan_key(&key, lnn, lnnsize, lnn_min, G, nr, nmax, lmax));
+    return get_cmix_plan_keyed(out, key, lnn, lnnsize, lnn_min, G, nr, nmax, lmax);
+}
 
-// W_lm(r) of one or two windows on the device (planar), shared by the end-to-end entry points
-static int windows_to_alm(const double* win1, const double* win2, int64_t nr, int64_t npix_in, int64_t ld_win,
-                          int64_t nside, int64_t LMAX, DevBuf<double>& alm1, DevBuf<double>& alm2, bool* same) {
+// W_lm(r) of one or two windows on the current device (planar), shared by the single-device end-to-end entry points
+static int windows_to_alm(Workspace& ws, const double* win1, const double* win2, int64_t nr, int64_t npix_in,
+                          int64_t ld_win, int64_t nside, int64_t LMAX, bool* same) {
     int64_t nside_in = 0;
     SFB_TRY(npix2nside(npix_in, &nside_in));
     ShtPlan* sp = nullptr;
     SFB_TRY(get_sht_plan(&sp, nside_in, nside, LMAX, nr));
     const size_t nalm = sp->lmsize * 2 * sp->nrp;
-    DevBuf<double>& d_win = g_ws.win;
-    SFB_TRY(upload_win(win1, nr, npix_in, ld_win, d_win));
-    SFB_TRY(alm1.alloc(nalm));
-    SFB_TRY(sht_map2alm(sp, d_win.p, nr, 3, alm1.p, 0));
+    SFB_TRY(upload_win(win1, nr, npix_in, ld_win, ws.win, ws.main));
+    SFB_TRY(ws.alm1.alloc(nalm));
+    SFB_TRY(sht_map2alm(sp, ws.win.p, nr, 3, ws.alm1.p, ws.main));
     g_times[0] = sp->t_total;
     g_times[6] = sp->launches;
     *same = (win2 == nullptr || win2 == win1);
     if (!*same) {
-        SFB_TRY(upload_win(win2, nr, npix_in, ld_win, d_win));
-        SFB_TRY(alm2.alloc(nalm));
-        SFB_TRY(sht_map2alm(sp, d_win.p, nr, 3, alm2.p, 0));
+        SFB_TRY(upload_win(win2, nr, npix_in, ld_win, ws.win, ws.main));
+        SFB_TRY(ws.alm2.alloc(nalm));
+        SFB_TRY(sht_map2alm(sp, ws.win.p, nr, 3, ws.alm2.p, ws.main));
         g_times[0] += sp->t_total;
         g_times[6] += sp->launches;
     }
     return 0;
 }
+
+// =================================================================================================================
+// Multi-device host path (sfb_set_devices(n), n > 1): ONE process drives n GPUs, one worker thread per device for the
+// duration of the call (nothing outlives it).  It replaces the reference's only parallel gather, the pmap over rows
+// inside _power_win_mix (src/windows.jl:834-861), and the serial shell loop of calc_Wr_lm (:531-535):
+//   A  every device uploads a contiguous PIXEL slice of the window (1/n of the bytes over its own PCIe link);
+//   B  every device gathers ITS SHELLS of all pixels from the peers' slices over NVLink (peer loads in a kernel),
+//      transforms them (stage 1 on nr/n shells) and publishes its W_lm(r) shard;
+//   C  every device gathers all W_lm(r) shards (peer loads), forms a full-height COLUMN range of M — a contiguous slab
+//      of the caller's column-major matrix — and copies it straight into the caller's buffer over its own PCIe link
+//      (sub-slabs pipelined with the compute).  No all-gather of M ever runs.
+struct Gang {
+    int n = 1;
+    std::mutex m;
+    std::condition_variable cv;
+    int count = 0;
+    unsigned gen = 0;
+    std::atomic<int> failed{0};
+    int rc[kMaxDev] = {0, 0, 0, 0, 0, 0, 0, 0};
+    std::string err[kMaxDev];
+    void sync() {
+        std::unique_lock<std::mutex> lk(m);
+        const unsigned g = gen;
+        if (++count == n) {
+            count = 0;
+            ++gen;
+            cv.notify_all();
+        } else {
+            cv.wait(lk, [&] { return gen != g; });
+        }
+    }
+    void fail(int d, int code) {
+        rc[d] = code;
+        err[d] = g_err;
+        failed.store(1);
+    }
+};
+
+struct PtrTable8 {
+    const double* p[kMaxDev];
+    long long bound[kMaxDev + 1];
+    int stride[kMaxDev];
+    int n;
+};
+
+// dst[pix][j] (j < cnt, row stride ldd) = window[pix][s_lo + j], pixel `pix` living in the slice of the device that
+// uploaded it: slice g holds pixels [bound[g], bound[g+1]) as [pixel - bound[g]][nr]
+__global__ void win_shard_gather_kernel(PtrTable8 t, long long npix, int nr, int s_lo, int cnt, int ldd,
+                                        double* __restrict__ dst) {
+    const long long total = npix * cnt;
+    for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < total; x += (long long)gridDim.x * blockDim.x) {
+        const long long pix = x / cnt;
+        const int j = (int)(x - pix * cnt);
+        int g = 0;
+        while (g + 1 < t.n && pix >= t.bound[g + 1]) ++g;
+        dst[pix * ldd + j] = t.p[g][(pix - t.bound[g]) * nr + s_lo + j];
+    }
+}
+
+// full planar alm [row = lm*2+comp][nrp] <- shards [row][stride[g]], shard g holding shells [bound[g], bound[g+1])
+__global__ void alm_shard_gather_kernel(PtrTable8 t, long long rows, int nr, int nrp, double* __restrict__ dst) {
+    const long long total = rows * nrp;
+    for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < total; x += (long long)gridDim.x * blockDim.x) {
+        const long long row = x / nrp;
+        const int r = (int)(x - row * nrp);
+        double v = 0.0;
+        if (r < nr) {
+            int g = 0;
+            while (g + 1 < t.n && r >= t.bound[g + 1]) ++g;
+            v = t.p[g][row * t.stride[g] + (r - t.bound[g])];
+        }
+        dst[x] = v;
+    }
+}
+
+struct MdJob {
+    // inputs of the call
+    const double* win[2] = {nullptr, nullptr};
+    int nwin = 1;
+    int64_t nr = 0, npix_in = 0, ld_win = 0, nside_in = 0, nside = 0, LMAX = 0, niter = 3;
+    // stage 2+3 (absent for calc_Wr_lm)
+    bool want_cmix = false;
+    PlanKey key;
+    const double* G = nullptr;
+    int64_t nmax = 0, lmax = 0, lnnsize = 0, lnn_min = 1;
+    const int64_t* lnn = nullptr;
+    int div2Lp1 = 0, interchange = 0;
+    double* M_out = nullptr;
+    // calc_Wr_lm output (device 0 gathers and converts)
+    double* wr_out = nullptr;
+    int layout = 0;
+    // sharding
+    int ndev = 1;
+    int64_t shell[kMaxDev + 1] = {0}, pix[kMaxDev + 1] = {0}, col[kMaxDev + 1] = {0};
+    // published by the workers
+    Workspace* ws[kMaxDev] = {nullptr};
+    int nrp_shard[kMaxDev] = {0};
+    CmixPlan* cplan[kMaxDev] = {nullptr};
+    double t_stage1[kMaxDev] = {0};
+    int launches1[kMaxDev] = {0};
+    Gang gang;
+};
+
+static int md_phase_upload(MdJob& J, int d) {
+    SFB_CUDA_OK(cudaSetDevice(d));
+    Workspace* ws = nullptr;
+    SFB_TRY(get_ws(&ws));
+    J.ws[d] = ws;
+    if (J.want_cmix) SFB_TRY(get_cmix_plan_keyed(&J.cplan[d], J.key, J.lnn, J.lnnsize, J.lnn_min, J.G, J.nr, J.nmax, J.lmax));
+    const int64_t p0 = J.pix[d], p1 = J.pix[d + 1];
+    for (int w = 0; w < J.nwin; ++w) {
+        SFB_TRY(ws->slice[w].alloc((size_t)std::max<int64_t>(1, p1 - p0) * J.nr));
+        if (p1 > p0) SFB_TRY(h2d_rows(ws->slice[w].p, J.win[w] + p0 * J.ld_win, J.nr, p1 - p0, J.ld_win, ws->main));
+        SFB_CUDA_OK(cudaEventRecord(ws->ev_slice[w], ws->main));
+    }
+    return 0;
+}
+
+static int md_phase_stage1(MdJob& J, int d) {
+    Workspace& ws = *J.ws[d];
+    const int64_t s0 = J.shell[d], s1 = J.shell[d + 1], cnt = s1 - s0;
+    J.nrp_shard[d] = (int)round_up(std::max<int64_t>(cnt, 1), 8);
+    if (cnt <= 0) {
+        for (int w = 0; w < J.nwin; ++w) SFB_CUDA_OK(cudaEventRecord(ws.ev_alm[w], ws.main));
+        return 0;
+    }
+    ShtPlan* sp = nullptr;
+    SFB_TRY(get_sht_plan(&sp, J.nside_in, J.nside, J.LMAX, cnt));
+    SFB_TRY(ws.shard.alloc((size_t)J.npix_in * cnt));
+    PtrTable8 t;
+    t.n = J.ndev;
+    for (int w = 0; w < J.nwin; ++w) {
+        for (int g = 0; g < J.ndev; ++g) {
+            t.p[g] = J.ws[g]->slice[w].p;
+            t.bound[g] = J.pix[g];
+            t.stride[g] = (int)J.nr;
+            SFB_CUDA_OK(cudaStreamWaitEvent(ws.main, J.ws[g]->ev_slice[w], 0));
+        }
+        t.bound[J.ndev] = J.pix[J.ndev];
+        win_shard_gather_kernel<<<2048, 256, 0, ws.main>>>(t, J.npix_in, (int)J.nr, (int)s0, (int)cnt, (int)cnt, ws.shard.p);
+        SFB_CUDA_OK(cudaGetLastError());
+        SFB_TRY(ws.almshard[w].alloc(sp->lmsize * 2 * sp->nrp));
+        SFB_TRY(sht_map2alm(sp, ws.shard.p, cnt, (int)J.niter, ws.almshard[w].p, ws.main));   // synchronous
+        J.t_stage1[d] += sp->t_total;
+        J.launches1[d] += sp->launches + 1;
+        SFB_CUDA_OK(cudaEventRecord(ws.ev_alm[w], ws.main));
+    }
+    return 0;
+}
+
+// full planar W_lm(r) of window w on device d (gathered from every device's shard)
+static int md_gather_alm(MdJob& J, int d, int w, DevBuf<double>& dst, int nrp) {
+    Workspace& ws = *J.ws[d];
+    const size_t lmsize = (size_t)(J.LMAX + 1) * (J.LMAX + 2) / 2;
+    SFB_TRY(dst.alloc(lmsize * 2 * nrp));
+    PtrTable8 t;
+    t.n = 0;
+    for (int g = 0; g < J.ndev; ++g) {
+        if (J.shell[g + 1] <= J.shell[g]) continue;
+        t.p[t.n] = J.ws[g]->almshard[w].p;
+        t.bound[t.n] = J.shell[g];
+        t.stride[t.n] = J.nrp_shard[g];
+        ++t.n;
+        SFB_CUDA_OK(cudaStreamWaitEvent(ws.main, J.ws[g]->ev_alm[w], 0));
+    }
+    t.bound[t.n] = J.nr;
+    alm_shard_gather_kernel<<<1024, 256, 0, ws.main>>>(t, (long long)lmsize * 2, (int)J.nr, nrp, dst.p);
+    SFB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+static int md_phase_cmix(MdJob& J, int d) {
+    Workspace& ws = *J.ws[d];
+    if (J.wr_out) {   // calc_Wr_lm: device 0 assembles, converts to ComplexF64 in the requested column order, copies out
+        if (d != 0) return 0;
+        const int nrp = (int)round_up(J.nr, 8);
+        SFB_TRY(md_gather_alm(J, d, 0, ws.alm1, nrp));
+        const size_t lmsize = (size_t)(J.LMAX + 1) * (J.LMAX + 2) / 2;
+        SFB_TRY(ws.M.alloc(lmsize * 2 * J.nr));
+        SFB_TRY(alm_planar_to_complex(ws.alm1.p, (int)J.LMAX, (int)J.nr, nrp, J.layout, ws.M.p, ws.main));
+        SFB_CUDA_OK(cudaMemcpyAsync(J.wr_out, ws.M.p, lmsize * 2 * J.nr * sizeof(double), cudaMemcpyDeviceToHost, ws.main));
+        SFB_CUDA_OK(cudaStreamSynchronize(ws.main));
+        return 0;
+    }
+    CmixPlan* p = J.cplan[d];
+    SFB_TRY(md_gather_alm(J, d, 0, ws.alm1, p->nrp));
+    if (J.nwin == 2) SFB_TRY(md_gather_alm(J, d, 1, ws.alm2, p->nrp));
+    const double* a1 = ws.alm1.p;
+    const double* a2 = J.nwin == 2 ? ws.alm2.p : a1;
+    SFB_TRY(cmix_cols_to_host(p, ws, a1, a2, J.div2Lp1, J.interchange, J.col[d], J.col[d + 1], 4, J.M_out));
+    return 0;
+}
+
+static void md_worker(MdJob* Jp, int d) {
+    MdJob& J = *Jp;
+    int (*phases[3])(MdJob&, int) = {md_phase_upload, md_phase_stage1, md_phase_cmix};
+    for (int ph = 0; ph < 3; ++ph) {
+        if (!J.gang.failed.load()) {
+            const int rc = phases[ph](J, d);
+            if (rc) J.gang.fail(d, rc);
+        }
+        J.gang.sync();   // every worker arrives at every barrier, failed or not
+    }
+    // nobody may reuse a slice / alm shard while a peer still reads it: drain this device before the call returns
+    if (J.ws[d]) {
+        cudaSetDevice(d);
+        cudaStreamSynchronize(J.ws[d]->main);
+        cudaStreamSynchronize(J.ws[d]->copy);
+    }
+}
+
+static int md_run(MdJob& J) {
+    const int n = J.ndev;
+    J.gang.n = n;
+    // shells and pixels: equal contiguous ranges
+    for (int g = 0; g <= n; ++g) {
+        J.shell[g] = std::min<int64_t>(J.nr, ceil_div(J.nr, n) * g);
+        J.pix[g] = J.npix_in * g / n;
+    }
+    int dev0 = 0;
+    SFB_CUDA_OK(cudaGetDevice(&dev0));
+    std::vector<std::thread> th;
+    for (int d = 1; d < n; ++d) th.emplace_back(md_worker, &J, d);
+    md_worker(&J, 0);
+    for (auto& t : th) t.join();
+    cudaSetDevice(dev0);
+    for (int d = 0; d < n; ++d)
+        if (J.gang.rc[d]) {
+            set_error("device " + std::to_string(d) + ": " + J.gang.err[d]);
+            return J.gang.rc[d];
+        }
+    // timings: the slowest device per stage
+    g_times[0] = 0;
+    g_times[6] = 0;
+    for (int d = 0; d < n; ++d) {
+        g_times[0] = std::max(g_times[0], J.t_stage1[d]);
+        g_times[6] = std::max(g_times[6], (double)J.launches1[d]);
+    }
+    if (J.want_cmix) {
+        double t[5] = {0, 0, 0, 0, 0}, launches = 0;
+        for (int d = 0; d < n; ++d) {
+            const CmixPlan* p = J.cplan[d];
+            if (!p || J.col[d + 1] <= J.col[d]) continue;
+            t[0] = std::max<double>(t[0], p->t_wl);
+            t[1] = std::max<double>(t[1], p->t_fill);
+            t[2] = std::max<double>(t[2], p->t_what);
+            t[3] = std::max<double>(t[3], p->t_block);
+            t[4] += p->flops_executed;
+            launches = std::max<double>(launches, p->launches);
+        }
+        g_times[1] = t[0];
+        g_times[2] = t[1];
+        g_times[3] = t[2];
+        g_times[4] = t[3];
+        g_times[5] = t[4];
+        g_times[6] += launches;
+    }
+    return 0;
+}
+
+// number of devices a call of this size is spread over
+static int md_devices_for(int64_t nr) { return (int)std::max<int64_t>(1, std::min<int64_t>(g_ndev, nr)); }
 }  // namespace sfb
 
 using namespace sfb;
@@ -306,6 +632,70 @@ int32_t sfb_device_count(int32_t* count) {
 int32_t sfb_set_device(int32_t device) {
     std::lock_guard<std::mutex> lk(g_mutex);
     SFB_CUDA_OK(cudaSetDevice(device));
+    return 0;
+}
+
+int32_t sfb_set_devices(int32_t n) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    int have = 0;
+    SFB_CUDA_OK(cudaGetDeviceCount(&have));
+    SFB_REQUIRE(n >= 1 && n <= kMaxDev, "sfb_set_devices: n must be in 1..8");
+    if (n > have) {
+        set_error("sfb_set_devices: " + std::to_string(n) + " devices requested, " + std::to_string(have) + " visible");
+        return 2;
+    }
+    int dev0 = 0;
+    SFB_CUDA_OK(cudaGetDevice(&dev0));
+    // the workers read each other's buffers in kernels: every pair needs peer access (NVLink / NVSwitch)
+    for (int i = 0; i < n && n > 1; ++i) {
+        SFB_CUDA_OK(cudaSetDevice(i));
+        for (int j = 0; j < n; ++j) {
+            if (i == j) continue;
+            int can = 0;
+            SFB_CUDA_OK(cudaDeviceCanAccessPeer(&can, i, j));
+            if (!can) {
+                cudaSetDevice(dev0);
+                set_error("sfb_set_devices: device " + std::to_string(i) + " cannot access device " + std::to_string(j) +
+                          " (peer access is required)");
+                return 2;
+            }
+            const cudaError_t e = cudaDeviceEnablePeerAccess(j, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) {
+                cudaGetLastError();
+            } else if (e != cudaSuccess) {
+                cudaSetDevice(dev0);
+                set_error(std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+                return 1;
+            }
+        }
+    }
+    SFB_CUDA_OK(cudaSetDevice(n > 1 ? 0 : dev0));
+    g_ndev = n;
+    return 0;
+}
+int32_t sfb_get_devices(int32_t* n) {
+    SFB_REQUIRE(n, "null pointer");
+    *n = g_ndev;
+    return 0;
+}
+
+int32_t sfb_host_alloc(void** ptr, int64_t bytes) {
+    SFB_REQUIRE(ptr && bytes > 0, "sfb_host_alloc: bad arguments");
+    SFB_CUDA_OK(cudaHostAlloc(ptr, (size_t)bytes, cudaHostAllocPortable));
+    return 0;
+}
+int32_t sfb_host_free(void* ptr) {
+    if (ptr) SFB_CUDA_OK(cudaFreeHost(ptr));
+    return 0;
+}
+int32_t sfb_host_register(void* ptr, int64_t bytes) {
+    SFB_REQUIRE(ptr && bytes > 0, "sfb_host_register: bad arguments");
+    SFB_CUDA_OK(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable));
+    return 0;
+}
+int32_t sfb_host_unregister(void* ptr) {
+    SFB_REQUIRE(ptr, "sfb_host_unregister: null pointer");
+    SFB_CUDA_OK(cudaHostUnregister(ptr));
     return 0;
 }
 
@@ -337,17 +727,31 @@ int32_t sfb_calc_wr_lm(const double* win, int64_t nr, int64_t npix_in, int64_t l
     SFB_REQUIRE(layout == 0 || layout == 1, "bad layout");
     int64_t nside_in = 0;
     SFB_TRY(npix2nside(npix_in, &nside_in));
+    SFB_REQUIRE(ld_win >= nr, "ld_win < nr");
+    SFB_REQUIRE(niter >= 0, "niter < 0");
+    if (md_devices_for(nr) > 1) {   // shells sharded over the devices of sfb_set_devices
+        MdJob J;
+        J.win[0] = win;
+        J.nr = nr, J.npix_in = npix_in, J.ld_win = ld_win, J.nside_in = nside_in, J.nside = nside_out, J.LMAX = lmax;
+        J.niter = niter;
+        J.wr_out = out, J.layout = layout;
+        J.ndev = md_devices_for(nr);
+        return md_run(J);
+    }
     ShtPlan* sp = nullptr;
     SFB_TRY(get_sht_plan(&sp, nside_in, nside_out, lmax, nr));
-    DevBuf<double> d_win, d_alm, d_out;
-    SFB_TRY(upload_win(win, nr, npix_in, ld_win, d_win));
-    SFB_TRY(d_alm.alloc(sp->lmsize * 2 * sp->nrp));
+    Workspace* ws = nullptr;
+    SFB_TRY(get_ws(&ws));
+    DevBuf<double> d_out;
+    SFB_TRY(upload_win(win, nr, npix_in, ld_win, ws->win, ws->main));
+    SFB_TRY(ws->alm1.alloc(sp->lmsize * 2 * sp->nrp));
     SFB_TRY(d_out.alloc(sp->lmsize * 2 * nr));
-    SFB_TRY(sht_map2alm(sp, d_win.p, nr, (int)niter, d_alm.p, 0));
+    SFB_TRY(sht_map2alm(sp, ws->win.p, nr, (int)niter, ws->alm1.p, ws->main));
     g_times[0] = sp->t_total;
     g_times[6] = sp->launches;
-    SFB_TRY(sht_alm_to_complex(sp, d_alm.p, layout, d_out.p, 0));
-    SFB_CUDA_OK(cudaMemcpy(out, d_out.p, sp->lmsize * 2 * nr * sizeof(double), cudaMemcpyDeviceToHost));
+    SFB_TRY(sht_alm_to_complex(sp, ws->alm1.p, layout, d_out.p, ws->main));
+    SFB_CUDA_OK(cudaMemcpyAsync(out, d_out.p, sp->lmsize * 2 * nr * sizeof(double), cudaMemcpyDeviceToHost, ws->main));
+    SFB_CUDA_OK(cudaStreamSynchronize(ws->main));
     return 0;
 }
 
@@ -389,14 +793,36 @@ int32_t sfb_power_win_mix(const double* win1, const double* win2, int64_t nr, in
     std::lock_guard<std::mutex> lk(g_mutex);
     SFB_REQUIRE(win1 && M_out, "null pointer");
     Trace tr;
+    if (md_devices_for(nr) > 1) {   // sfb_set_devices(n): shells, then columns of M, sharded over n GPUs
+        MdJob J;
+        SFB_TRY(make_plan_key(&J.key, lnn, lnnsize, lnn_min, G, nr, nmax, lmax));
+        SFB_REQUIRE(lnn_min >= 1 && lnn_min <= lnnsize, "lnn_min out of range");
+        SFB_REQUIRE(ld_win >= nr, "ld_win < nr");
+        J.win[0] = win1;
+        J.nwin = (win2 == nullptr || win2 == win1) ? 1 : 2;
+        J.win[1] = win2;
+        J.nr = nr, J.npix_in = npix_in, J.ld_win = ld_win, J.nside = nside, J.LMAX = 2 * lmax;
+        SFB_TRY(npix2nside(npix_in, &J.nside_in));
+        J.want_cmix = true;
+        J.G = G, J.nmax = nmax, J.lmax = lmax, J.lnn = lnn, J.lnnsize = lnnsize, J.lnn_min = lnn_min;
+        J.div2Lp1 = div2Lp1, J.interchange = interchange_NN, J.M_out = M_out;
+        J.ndev = md_devices_for(nr);
+        // column ranges (L-block aligned, balanced on the full-height cost): needs the mode tables only
+        SFB_TRY(cmix_col_bounds_from_lnn(lnn, lnnsize, lnn_min, nr, nmax, lmax, J.ndev, J.col));
+        SFB_TRY(md_run(J));
+        tr.mark("multi-device power_win_mix");
+        return 0;
+    }
     PlanGuard pg;
     SFB_TRY(get_cmix_plan(&pg.p, lnn, lnnsize, lnn_min, G, nr, nmax, lmax));
     tr.mark("plan");
-    DevBuf<double>&a1 = g_ws.alm1, &a2 = g_ws.alm2;
+    Workspace* ws = nullptr;
+    SFB_TRY(get_ws(&ws));
     bool same = true;
-    SFB_TRY(windows_to_alm(win1, win2, nr, npix_in, ld_win, nside, 2 * lmax, a1, a2, &same));
+    SFB_TRY(windows_to_alm(*ws, win1, win2, nr, npix_in, ld_win, nside, 2 * lmax, &same));
     tr.mark("H2D + stage 1");
-    SFB_TRY(cmix_to_host_pipelined(pg.p, a1.p, same ? a1.p : a2.p, div2Lp1, interchange_NN, M_out));
+    SFB_TRY(cmix_cols_to_host(pg.p, *ws, ws->alm1.p, same ? ws->alm1.p : ws->alm2.p, div2Lp1, interchange_NN, 0,
+                              pg.p->nout, 8, M_out));
     record_cmix_times(pg.p);
     tr.mark("stage 2+3 pipelined with D2H");
     return 0;
@@ -414,10 +840,12 @@ int32_t sfb_power_win_mix_binned(const double* win1, int64_t nr, int64_t npix_in
     PlanGuard pg;
     SFB_TRY(get_cmix_plan(&pg.p, lnn, lnnsize, 1, G, nr, nmax, lmax));
     tr.mark("binned: plan");
-    DevBuf<double>&a1 = g_ws.alm1, &a2 = g_ws.alm2, &dM = g_ws.M;
+    Workspace* ws = nullptr;
+    SFB_TRY(get_ws(&ws));
+    DevBuf<double>&a1 = ws->alm1, &dM = ws->M;
     bool same = true;
     // like the reference, W2r_lm is computed from win1 as well (src/windows.jl:1005-1006)
-    SFB_TRY(windows_to_alm(win1, nullptr, nr, npix_in, ld_win, nside, 2 * lmax, a1, a2, &same));
+    SFB_TRY(windows_to_alm(*ws, win1, nullptr, nr, npix_in, ld_win, nside, 2 * lmax, &same));
     tr.mark("binned: H2D + stage 1");
     const int64_t n = pg.p->nout;
     SFB_TRY(dM.alloc((size_t)n * n));
@@ -438,9 +866,11 @@ int32_t sfb_win_lnn(const double* win, int64_t nr, int64_t npix_in, int64_t ld_w
     SFB_REQUIRE(win && Wlnn_out, "null pointer");
     PlanGuard pg;
     SFB_TRY(get_cmix_plan(&pg.p, lnn, lnnsize, 1, G, nr, nmax, lmax));
-    DevBuf<double>&a1 = g_ws.alm1, &a2 = g_ws.alm2;
+    Workspace* ws = nullptr;
+    SFB_TRY(get_ws(&ws));
+    DevBuf<double>& a1 = ws->alm1;
     bool same = true;
-    SFB_TRY(windows_to_alm(win, nullptr, nr, npix_in, ld_win, nside, 2 * lmax, a1, a2, &same));
+    SFB_TRY(windows_to_alm(*ws, win, nullptr, nr, npix_in, ld_win, nside, 2 * lmax, &same));
     // Wr_00 / √(4π) enters under a square root in the reference (src/windows.jl:400): negative values throw there
     std::vector<double> w00((size_t)nr);
     SFB_CUDA_OK(cudaMemcpy(w00.data(), a1.p, (size_t)nr * sizeof(double), cudaMemcpyDeviceToHost));
@@ -479,7 +909,7 @@ int32_t sfb_power_win_mix_separable(const double* phi, const double* mask, int64
     ShtPlan* sp = nullptr;
     SFB_TRY(get_sht_plan(&sp, nside_in, nside, 2 * lmax, 1));
     DevBuf<double> d_mask, d_wlm, dM;
-    SFB_TRY(upload_win(mask, 1, npix_in, 1, d_mask));
+    SFB_TRY(upload_win(mask, 1, npix_in, 1, d_mask, 0));
     SFB_TRY(d_wlm.alloc(sp->lmsize * 2 * sp->nrp));
     SFB_TRY(sht_map2alm(sp, d_mask.p, 1, 3, d_wlm.p, 0));
     g_times[0] = sp->t_total;
@@ -596,76 +1026,6 @@ int32_t sfb_power_win_mix_block_dev(sfb_cmix_plan* plan, const double* d_alm1, c
     g_times[6] = t0 + p->launches;
     return 0;
 }
-int32_t sfb_power_win_mix_dev_peers(sfb_cmix_plan* plan, const double* d_alm1, const double* d_alm2, int32_t div2Lp1,
-                                    int32_t interchange_NN, int64_t row_lo, int64_t row_hi, double* d_M_full,
-                                    double* const* peer_M_full, int32_t npeers, int64_t ldM, void* stream) {
-    std::lock_guard<std::mutex> lk(g_mutex);
-    auto* p = reinterpret_cast<CmixPlan*>(plan);
-    SFB_REQUIRE(p && d_M_full, "null pointer");
-    SFB_REQUIRE(npeers >= 0 && npeers <= 7, "at most 7 peers");
-    SFB_REQUIRE(ldM >= p->nout, "ldM must be the leading dimension of the full matrix");
-    double* peers[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    for (int i = 0; i < npeers; ++i) {
-        SFB_REQUIRE(peer_M_full && peer_M_full[i], "null peer pointer");
-        peers[i] = peer_M_full[i] + row_lo;
-    }
-    const double t0 = g_times[6];
-    SFB_CMIX_RUN_ASYNC(p, cmix_run(p, d_alm1, d_alm2, div2Lp1, interchange_NN, row_lo, row_hi, 0, p->nout,
-                                   d_M_full + row_lo, ldM, (cudaStream_t)stream, peers, npeers));
-    g_times[6] = t0 + p->launches;
-    return 0;
-}
-
-// Push rows [row_lo,row_hi) of this device's full matrix into the same rows of every peer's full matrix with one
-// pitched peer-to-peer copy per peer (copy engines over NVLink), each on its own stream, ordered after `stream`.
-int32_t sfb_push_rows_to_peers(const double* d_M_full, double* const* peer_M_full, int32_t npeers, int64_t row_lo,
-                               int64_t row_hi, int64_t ncols, int64_t ldM, void* stream) {
-    std::lock_guard<std::mutex> lk(g_mutex);
-    SFB_REQUIRE(d_M_full && npeers >= 0 && npeers <= 7, "bad arguments");
-    SFB_REQUIRE(0 <= row_lo && row_lo <= row_hi && row_hi <= ldM, "bad row range");
-    if (row_hi == row_lo || npeers == 0) return 0;
-    static cudaStream_t ps[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    static cudaEvent_t ready = nullptr, done[7];
-    static int ps_dev = -1;
-    int dev = 0;
-    SFB_CUDA_OK(cudaGetDevice(&dev));
-    if (!ready || ps_dev != dev) {
-        SFB_CUDA_OK(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
-        for (int i = 0; i < 7; ++i) {
-            SFB_CUDA_OK(cudaStreamCreateWithFlags(&ps[i], cudaStreamNonBlocking));
-            SFB_CUDA_OK(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
-        }
-        ps_dev = dev;
-    }
-    cudaStream_t st = (cudaStream_t)stream;
-    SFB_CUDA_OK(cudaEventRecord(ready, st));
-    const size_t pitch = (size_t)ldM * sizeof(double), width = (size_t)(row_hi - row_lo) * sizeof(double);
-    for (int i = 0; i < npeers; ++i) {
-        SFB_REQUIRE(peer_M_full && peer_M_full[i], "null peer pointer");
-        SFB_CUDA_OK(cudaStreamWaitEvent(ps[i], ready, 0));
-        SFB_CUDA_OK(cudaMemcpy2DAsync(peer_M_full[i] + row_lo, pitch, d_M_full + row_lo, pitch, width, (size_t)ncols,
-                                      cudaMemcpyDeviceToDevice, ps[i]));
-        SFB_CUDA_OK(cudaEventRecord(done[i], ps[i]));
-        SFB_CUDA_OK(cudaStreamWaitEvent(st, done[i], 0));
-    }
-    return 0;
-}
-
-// Column slabs are contiguous in a column-major matrix: one plain peer copy per peer.
-int32_t sfb_push_cols_to_peers(const double* d_M_full, double* const* peer_M_full, int32_t npeers, int64_t col_lo,
-                               int64_t col_hi, int64_t ldM, void* stream) {
-    SFB_REQUIRE(d_M_full && npeers >= 0 && npeers <= 7 && col_lo >= 0 && col_lo <= col_hi, "bad arguments");
-    if (col_hi == col_lo || npeers == 0) return 0;
-    double* shifted[7];
-    for (int i = 0; i < npeers; ++i) {
-        SFB_REQUIRE(peer_M_full && peer_M_full[i], "null peer pointer");
-        shifted[i] = peer_M_full[i] + col_lo * ldM;
-    }
-    // the slab is one contiguous run of (col_hi-col_lo)*ldM doubles == a single "row" of a pitched copy
-    const int64_t run = (col_hi - col_lo) * ldM;
-    return sfb_push_rows_to_peers(d_M_full + col_lo * ldM, shifted, npeers, 0, run, 1, run, stream);
-}
-
 int32_t sfb_ipc_alloc(void** dptr, int64_t bytes, void* handle64) {
     std::lock_guard<std::mutex> lk(g_mutex);
     SFB_REQUIRE(dptr && handle64 && bytes > 0, "bad arguments");

@@ -1075,6 +1075,101 @@ std::vector<std::pair<int64_t, int64_t>> cmix_col_chunks(const CmixPlan* p, int 
     return out;
 }
 
+// The same split restricted to the columns [lo, hi): at most k ranges of roughly equal full-height cost, cut on L-block
+// boundaries inside the range (lo and hi themselves may lie anywhere).
+std::vector<std::pair<int64_t, int64_t>> cmix_col_chunks_range(const CmixPlan* p, int64_t lo, int64_t hi, int k) {
+    std::vector<std::pair<int64_t, int64_t>> out;
+    if (hi <= lo) return out;
+    if (lo == 0 && hi == p->nout) return cmix_col_chunks(p, k);
+    if (!p->ell_sorted || k <= 1) {
+        out.emplace_back(lo, hi);
+        return out;
+    }
+    const int lmax = p->lmax;
+    // l-sorted table: block L covers the output columns [first[L], first[L+1])
+    std::vector<int64_t> first(lmax + 2, 0);
+    for (int L = 0; L <= lmax; ++L) first[L + 1] = first[L] + (p->ell_ptr[L + 1] - p->ell_ptr[L]);
+    std::vector<double> cost(lmax + 1, 0.0);
+    double total = 0;
+    for (int L = 0; L <= lmax; ++L) {
+        const int64_t c0 = std::max(first[L], lo), c1 = std::min(first[L + 1], hi);
+        if (c1 <= c0) continue;
+        const double b = p->a_of_ell[L];
+        double c = 0;
+        for (int l = 0; l <= lmax; ++l) {
+            if (p->ell_ptr[l + 1] == p->ell_ptr[l]) continue;
+            const double ap = 8.0 * ((p->a_of_ell[l] + 7) / 8);
+            c += 2.0 * ap * p->nrp * p->nrp * b + 2.0 * ap * ap * p->nrp * b * (b + 1) / 2 +
+                 2.0 * p->nrp * p->nrp * (std::min(l, L) + 1);
+        }
+        cost[L] = c;    // a partially covered block still costs (almost) the whole block
+        total += c;
+    }
+    double acc = 0;
+    int64_t start = lo;
+    int made = 0;
+    for (int L = 0; L <= lmax; ++L) {
+        if (cost[L] == 0) continue;
+        acc += cost[L];
+        const int64_t end = std::min(first[L + 1], hi);
+        if (acc >= total * (made + 1) / k && end > start && made < k - 1 && end < hi) {
+            out.emplace_back(start, end);
+            start = end;
+            ++made;
+        }
+    }
+    if (start < hi) out.emplace_back(start, hi);
+    return out;
+}
+
+// Column bounds for `ndev` devices straight from the caller's mode table (no plan needed): bounds[0..ndev], cut where l
+// changes (when the table is sorted by l) so that every device forms whole (l, L) blocks, balanced on the full-height cost.
+int cmix_col_bounds_from_lnn(const int64_t* lnn, int64_t lnnsize, int64_t lnn_min, int64_t nr, int64_t nmax, int64_t lmax,
+                             int ndev, int64_t* bounds) {
+    SFB_REQUIRE(lnn && bounds && ndev >= 1, "cmix_col_bounds_from_lnn: bad arguments");
+    SFB_REQUIRE(lnn_min >= 1 && lnn_min <= lnnsize, "lnn_min out of range");
+    const int64_t n = lnnsize - lnn_min + 1;
+    std::vector<int> a(lmax + 1, 0), cols(lmax + 1, 0);
+    bool sorted = true;
+    for (int64_t i = lnn_min - 1; i < lnnsize; ++i) {
+        const int64_t l = lnn[3 * i], n1 = lnn[3 * i + 1], n2 = lnn[3 * i + 2];
+        SFB_REQUIRE(l >= 0 && l <= lmax && n1 >= 1 && n2 >= 1 && n1 <= nmax && n2 <= nmax, "lnn entry out of range");
+        a[l] = std::max(a[l], (int)std::max(n1, n2));
+        cols[l]++;
+        if (i > lnn_min - 1 && l < lnn[3 * (i - 1)]) sorted = false;
+    }
+    const double nrp = (double)round_up(nr, 8);
+    std::vector<double> colcost(lmax + 1, 0.0);
+    for (int L = 0; L <= lmax; ++L) {
+        if (!cols[L]) continue;
+        const double b = a[L];
+        double c = 0;
+        for (int l = 0; l <= lmax; ++l) {
+            if (!cols[l]) continue;
+            const double ap = 8.0 * ((a[l] + 7) / 8);
+            c += 2.0 * ap * nrp * nrp * b + 2.0 * ap * ap * nrp * b * (b + 1) / 2 + 2.0 * nrp * nrp * (std::min(l, L) + 1);
+        }
+        colcost[L] = c / cols[L];
+    }
+    std::vector<double> cum((size_t)n + 1, 0.0);
+    for (int64_t o = 0; o < n; ++o) cum[o + 1] = cum[o] + colcost[lnn[3 * (o + lnn_min - 1)]];
+    bounds[0] = 0;
+    for (int g = 1; g < ndev; ++g) {
+        const double target = cum[n] * g / ndev;
+        int64_t c = std::lower_bound(cum.begin(), cum.end(), target) - cum.begin();
+        c = std::min<int64_t>(std::max<int64_t>(c, 0), n);
+        if (sorted && c > 0 && c < n) {   // snap to the nearest l-block boundary
+            int64_t up = c, dn = c;
+            while (up < n && lnn[3 * (up + lnn_min - 1)] == lnn[3 * (up + lnn_min - 2)]) ++up;
+            while (dn > 0 && dn < n && lnn[3 * (dn + lnn_min - 1)] == lnn[3 * (dn + lnn_min - 2)]) --dn;
+            c = (cum[up] - target <= target - cum[dn]) ? up : dn;
+        }
+        bounds[g] = std::max(c, bounds[g - 1]);
+    }
+    bounds[ndev] = n;
+    return 0;
+}
+
 // l-block aligned ranges of rows (== columns: same index set) with roughly equal mirror-mode cost
 // (block (l, L) is only formed for L >= l).  One range when the table does not keep l-blocks contiguous.
 std::vector<std::pair<int64_t, int64_t>> cmix_row_chunks_mirror(const CmixPlan* p, int k) {

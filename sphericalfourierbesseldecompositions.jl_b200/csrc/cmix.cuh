@@ -99,6 +99,10 @@ int cmix_mirror_fill(CmixPlan* p, int64_t c0, int64_t c1, int div2Lp1, int inter
 std::vector<std::pair<int64_t, int64_t>> cmix_row_chunks_mirror(const CmixPlan* p, int k);
 // column ranges of roughly equal cost (L-block aligned) for pipelining compute with the D2H of finished slabs
 std::vector<std::pair<int64_t, int64_t>> cmix_col_chunks(const CmixPlan* p, int k);
+std::vector<std::pair<int64_t, int64_t>> cmix_col_chunks_range(const CmixPlan* p, int64_t lo, int64_t hi, int k);
+// column bounds[0..ndev] for a multi-device run, from the caller's mode table alone (l-block aligned, cost balanced)
+int cmix_col_bounds_from_lnn(const int64_t* lnn, int64_t lnnsize, int64_t lnn_min, int64_t nr, int64_t nmax, int64_t lmax,
+                             int ndev, int64_t* bounds);
 
 // win_lnn (src/windows.jl:382-418) from the planar alm of stage 1: out[i] = Σ_r G_ln G_ln' W_00(r)/√(4π), nout values
 int win_lnn_run(CmixPlan* p, const double* d_alm, double* d_out, cudaStream_t stream);

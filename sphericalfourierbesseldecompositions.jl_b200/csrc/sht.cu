@@ -1321,11 +1321,16 @@ int sht_resolve_times(ShtPlan* p) {
     return 0;
 }
 
-int sht_alm_to_complex(const ShtPlan* p, const double* d_alm, int layout, double* d_out, cudaStream_t st) {
-    SFB_REQUIRE(p && d_alm && d_out, "sht_alm_to_complex: null pointer");
-    alm_to_complex_kernel<<<dim3(p->lmax + 1, p->lmax + 1), 64, 0, st>>>(d_alm, p->lmax, p->nr, p->nrp, layout, d_out);
+int alm_planar_to_complex(const double* d_alm, int lmax, int nr, int nrp, int layout, double* d_out, cudaStream_t st) {
+    SFB_REQUIRE(d_alm && d_out, "alm_planar_to_complex: null pointer");
+    alm_to_complex_kernel<<<dim3(lmax + 1, lmax + 1), 64, 0, st>>>(d_alm, lmax, nr, nrp, layout, d_out);
     SFB_CUDA_OK(cudaGetLastError());
     return 0;
+}
+
+int sht_alm_to_complex(const ShtPlan* p, const double* d_alm, int layout, double* d_out, cudaStream_t st) {
+    SFB_REQUIRE(p, "sht_alm_to_complex: null pointer");
+    return alm_planar_to_complex(d_alm, p->lmax, p->nr, p->nrp, layout, d_out, st);
 }
 
 }  // namespace sfb

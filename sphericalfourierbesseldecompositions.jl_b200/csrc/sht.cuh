@@ -49,5 +49,7 @@ int sht_map2alm(ShtPlan* p, const double* d_win, int64_t ldw, int niter, double*
 int sht_resolve_times(ShtPlan* p);
 // planar -> ComplexF64 nr x lmsize (device), layout 0 = m-major, 1 = m-fast
 int sht_alm_to_complex(const ShtPlan* p, const double* d_alm, int layout, double* d_out, cudaStream_t stream);
+// the same conversion without a plan (multi-device runs assemble W_lm(r) from shards of several plans)
+int alm_planar_to_complex(const double* d_alm, int lmax, int nr, int nrp, int layout, double* d_out, cudaStream_t stream);
 
 }  // namespace sfb

@@ -181,42 +181,6 @@ class DevicePipeline:
         return self.power_win_mix_rows(0, self.nout, **kw)
 
     # ---- multi-GPU -----------------------------------------------------------------------------
-    def power_win_mix_fused(self, d_win, peer_matrix, div2Lp1=False, interchange_NN=False, sync=True, mode="cols"):
-        """Sharded coupling matrix assembled in `peer_matrix` on every GPU without NCCL or a placement pass.
-        mode="cols" (default): shard the COLUMN index (L,N,N') — a column range is a contiguous slab of the
-          column-major matrix, so each rank pushes its slab to every peer with one plain P2P copy per peer;
-        mode="dma": shard rows (l,n,n'), pushed with pitched P2P copies (strided, slower);
-        mode="stores": shard rows, the block kernel itself stores every element into all copies over NVLink.
-        Returns (tensor view of the local full matrix, ranges); the tensor holds Mᵀ in C order (= M in Julia's
-        column-major order)."""
-        torch = _torch()
-        import torch.distributed as dist
-        pm = peer_matrix
-        self.calc_wr_lm_sharded(d_win, pm.group)
-        if mode == "cols":
-            ranges = shard_rows(self.col_costs, self.ell_of_row, pm.world)
-            lo, hi = ranges[pm.rank]
-            _lib.check(self.lib.sfb_power_win_mix_block_dev(self._cmix, self.alm.data_ptr(), self.alm.data_ptr(),
-                                                            int(div2Lp1), int(interchange_NN), 0, self.nout, lo, hi,
-                                                            pm.ptr.value + 8 * lo * self.nout, self.nout,
-                                                            self._stream()))
-            _lib.check(self.lib.sfb_push_cols_to_peers(pm.ptr, pm.peer_array, len(pm.peer_ptrs), lo, hi, self.nout,
-                                                       self._stream()))
-        else:
-            ranges = shard_rows(self.row_costs, self.ell_of_row, pm.world)
-            lo, hi = ranges[pm.rank]
-            nstore = len(pm.peer_ptrs) if mode == "stores" else 0
-            _lib.check(self.lib.sfb_power_win_mix_dev_peers(self._cmix, self.alm.data_ptr(), self.alm.data_ptr(),
-                                                            int(div2Lp1), int(interchange_NN), lo, hi, pm.ptr,
-                                                            pm.peer_array, nstore, self.nout, self._stream()))
-            if mode != "stores":
-                _lib.check(self.lib.sfb_push_rows_to_peers(pm.ptr, pm.peer_array, len(pm.peer_ptrs), lo, hi,
-                                                           self.nout, self.nout, self._stream()))
-        if sync:
-            torch.cuda.synchronize()
-            dist.barrier(pm.group)   # every rank's stores have landed in every copy
-        return pm.tensor, ranges
-
     def power_win_mix_allgather(self, d_win, full=None, group=None, div2Lp1=False, interchange_NN=False):
         """The multi-GPU path: stage 1 shell-sharded, stage 2+3 sharded over the COLUMN index (L,N,N') with a cost
         prefix sum, each rank writing its contiguous column slab straight into its copy of the full matrix, then
@@ -436,48 +400,6 @@ class PeerBuffer:
             self.lib.sfb_ipc_free(self.ptr)
             self.ptr = C.c_void_p()
             self._opened = []
-
-
-class PeerMatrix:
-    """Full nout x nout matrix on every rank, IPC-mapped into all peers of the node, so that the block kernel can
-    store each element it produces directly into every GPU's copy over NVLink (fused all-gather)."""
-
-    def __init__(self, nout, group=None):
-        torch = _torch()
-        import torch.distributed as dist
-        self.lib = _lib.load()
-        self.nout = nout
-        self.group = group
-        self.world = dist.get_world_size(group)
-        self.rank = dist.get_rank(group)
-        if self.world > 8:
-            raise ValueError("PeerMatrix supports at most 8 GPUs of one node")
-        self.ptr = C.c_void_p()
-        handle = C.create_string_buffer(64)
-        _lib.check(self.lib.sfb_ipc_alloc(C.byref(self.ptr), 8 * nout * nout, handle))
-        handles = [None] * self.world
-        dist.all_gather_object(handles, bytes(handle.raw), group=group)
-        self.peer_ptrs = []
-        for g, h in enumerate(handles):
-            if g == self.rank:
-                continue
-            q = C.c_void_p()
-            _lib.check(self.lib.sfb_ipc_open(C.create_string_buffer(h, 64), C.byref(q)))
-            self.peer_ptrs.append(q)
-        self.peer_array = (C.c_void_p * max(1, len(self.peer_ptrs)))(*[q.value for q in self.peer_ptrs])
-        self.tensor = torch.as_tensor(_DevArray(self.ptr.value, (nout, nout)), device=torch.device("cuda", torch.cuda.current_device()))
-
-    def close(self):
-        import torch.distributed as dist
-        if self.ptr:
-            _torch().cuda.synchronize()
-            dist.barrier(self.group)
-            for q in self.peer_ptrs:
-                self.lib.sfb_ipc_close(q)
-            dist.barrier(self.group)
-            self.lib.sfb_ipc_free(self.ptr)
-            self.ptr = C.c_void_p()
-            self.peer_ptrs = []
 
 
 def gather_row_slabs(slab, ranges, nout, group=None):

@@ -28,9 +28,39 @@ from .modes import AnlmModes, ClnnBinnedModes, ClnnModes, getlmsize, getlnnsize
 from .separable import SeparableArray
 
 __all__ = ["ConfigurationSpaceModes", "window_r", "calc_Wr_lm", "optimize_Wr_lm_layout", "precompute_gnlr",
-           "check_nsamp", "power_win_mix", "rsdrgnlr"]
+           "check_nsamp", "power_win_mix", "rsdrgnlr", "set_devices", "get_devices", "pinned_empty"]
 
 LAYOUT_MMAJOR, LAYOUT_MFAST = 0, 1
+
+
+def set_devices(n):
+    """sfb_set_devices(n): the host-pointer calls (power_win_mix, calc_Wr_lm of a dense window) shard over the GPUs
+    0..n-1 of this process — the multi-GPU form of the drop-in (it replaces the reference's pmap gather,
+    src/windows.jl:834-861).  n = 1 restores the single-GPU path."""
+    _lib.check(_lib.load().sfb_set_devices(int(n)))
+
+
+def get_devices():
+    import ctypes
+    n = ctypes.c_int32(0)
+    _lib.check(_lib.load().sfb_get_devices(ctypes.byref(n)))
+    return int(n.value)
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """Fortran-ordered array in page-locked host memory from sfb_host_alloc (freed with the array): what the Julia shim
+    uses for results so that every GPU's device->host copy runs at full PCIe speed."""
+    import ctypes
+    import weakref
+    lib = _lib.load()
+    shape = (shape,) if np.isscalar(shape) else tuple(int(x) for x in shape)
+    nbytes = int(np.prod(shape, dtype=np.int64)) * np.dtype(dtype).itemsize
+    ptr = ctypes.c_void_p()
+    _lib.check(lib.sfb_host_alloc(ctypes.byref(ptr), max(nbytes, 1)))
+    buf = (ctypes.c_char * max(nbytes, 1)).from_address(ptr.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape, dtype=np.int64))).reshape(shape, order="F")
+    weakref.finalize(buf, lib.sfb_host_free, ptr)
+    return arr
 
 
 class ConfigurationSpaceModes:

@@ -1,5 +1,9 @@
-"""Multi-GPU parity (needs >= 2 CUDA devices; run with `gpurun --gpus 2`): shell-sharded stage 1 + row-sharded
-stage 2/3 + NCCL all-gather must reproduce the single-GPU matrix (to rounding: narrower column tiles are used)."""
+"""Multi-GPU parity (needs >= 2 CUDA devices; run with `gpurun --gpus 2`).
+
+1. one process per GPU (torch.distributed / NCCL): shell-sharded stage 1 + sharded stage 2/3 + all-gather variants must
+   reproduce the single-GPU matrix (to rounding: narrower column tiles are used);
+2. ONE process, sfb_set_devices(n): the host-pointer C ABI itself shards over the GPUs and must return the same
+   arrays as with one device (this is what the Julia drop-in uses)."""
 import os
 import sys
 
@@ -48,15 +52,6 @@ def _worker(rank, world, port, ret):
         ref = pipe.power_win_mix_rows(0, pipe.nout, **kw)
         ok = ok and rel(pl, ref) < 1e-13
     pb.close()
-    from sfb_b200.device import PeerMatrix
-    pm = PeerMatrix(pipe.nout)
-    for mode in ("cols", "dma", "stores"):
-        pm.tensor.zero_()
-        torch.cuda.synchronize()
-        dist.barrier()
-        fused, _ = pipe.power_win_mix_fused(d_win, pm, mode=mode)
-        ok = ok and rel(fused, single) < 1e-13
-    pm.close()
     flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
@@ -80,3 +75,65 @@ def test_sharded_equals_single_gpu():
         assert p.exitcode == 0
     ok, ranges, err = ret.get()
     assert ok == 1.0, (ranges, err)
+
+
+def _set_devices_case(sfb, ndev):
+    import warnings
+    rng = np.random.default_rng(17)
+    a = sfb.AnlmModes(0.03, 500.0, 1000.0)
+    c = sfb.ClnnModes(a)
+    wm = sfb.ConfigurationSpaceModes(a, 21)              # 21 shells: uneven shell shards
+    win = np.asfortranarray(rng.random((wm.nr, wm.npix)))
+    win[:, ::4] = 0
+    win2 = np.asfortranarray(rng.random((wm.nr, wm.npix)))
+    res = {}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sfb.set_devices(ndev)
+        try:
+            res["M"] = sfb.power_win_mix(win, wm, c)
+            res["M_flags"] = sfb.power_win_mix(win, wm, c, div2Lp1=True, interchange_NN=True, lnn_min=7)
+            res["M_cross"] = sfb.power_win_mix(win, win2, wm, c)
+            res["Wr"] = sfb.calc_Wr_lm(win, 2 * a.lmax, a.nside)
+            res["Wr_fast"] = sfb.calc_Wr_lm(win, 2 * a.lmax, a.nside, layout=1)
+            res["Wr_up"] = sfb.calc_Wr_lm(np.asfortranarray(win2[:, :12 * 8 * 8]), 2 * a.lmax, a.nside)  # nside 8 -> udgrade
+            out = sfb.pinned_empty(res["M"].shape)
+            res["M_pinned"] = sfb.power_win_mix(win, wm, c, out=out).copy()
+        finally:
+            sfb.set_devices(1)
+    return res
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_set_devices_host_api_equals_single_gpu():
+    import sfb_b200 as sfb
+    from conftest import relerr
+    ref = _set_devices_case(sfb, 1)
+    for ndev in sorted({2, min(torch.cuda.device_count(), 8)}):
+        got = _set_devices_case(sfb, ndev)
+        assert sfb.get_devices() == 1
+        for k in ref:
+            assert got[k].shape == ref[k].shape, k
+            assert relerr(got[k], ref[k]) < 1e-13, (ndev, k)
+    with pytest.raises(sfb._lib.SFBError, match="devices requested"):
+        sfb.set_devices(torch.cuda.device_count() + 1)
+
+
+def test_set_devices_one_is_the_default_and_pinned_buffers_work():
+    # runs on a 1-GPU box: sfb_set_devices(1), page-locked result buffer, same numbers as a pageable one
+    import warnings
+
+    import sfb_b200 as sfb
+    from conftest import relerr
+    assert sfb.get_devices() == 1
+    sfb.set_devices(1)
+    a = sfb.AnlmModes(2, 4, 500.0, 1000.0)
+    c = sfb.ClnnModes(a)
+    wm = sfb.ConfigurationSpaceModes(a, 24)
+    win = np.random.default_rng(2).random((wm.nr, wm.npix))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        M = sfb.power_win_mix(win, wm, c)
+        out = sfb.pinned_empty(M.shape)
+        M2 = sfb.power_win_mix(win, wm, c, out=out)
+    assert M2 is out and out.flags.f_contiguous and relerr(M2, M) == 0.0
