@@ -93,6 +93,70 @@ __global__ void __launch_bounds__(256) wl_build_kernel(const double* __restrict_
     }
 }
 
+// The same contraction on the FP64 tensor cores: for one L1 it is the rank-2(L1+1) product
+//   W_{L1} = A_{L1}ᵀ B_{L1},  A[k][i] = c_M (Re|Im) W1[i, L1 M],  B[k][j] = (Re|Im) W2[j, L1 M],  k = (M, re/im),
+// whose operand rows are the contiguous shell vectors of the planar alm.  CTA = (L1, 64 x 64 tile of (i, j)), 8 warps as
+// 4 x 2, k-chunks of 16 M's (32 rows) staged in shared memory with the next chunk's loads in flight in registers.
+__global__ void __launch_bounds__(256) wl_build_dmma_kernel(const double* __restrict__ alm1, const double* __restrict__ alm2,
+                                                            double* __restrict__ W, int LMAX, int nrp) {
+    constexpr int LD = 72;   // 64 + 8: At/B fragment loads (t * LD + g) hit distinct banks
+    __shared__ double As[32 * LD];
+    __shared__ double Bs[32 * LD];
+    const int L1 = LMAX - blockIdx.x;                 // heaviest L1 first
+    const int i0 = blockIdx.y * 64, j0 = blockIdx.z * 64;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int wm = warp >> 1, wn = warp & 1;
+    double acc[2][4][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    const int nk = 2 * (L1 + 1);                      // k rows: (M, comp)
+    double ra[8], rb[8];
+    auto prefetch = [&](int k0) {
+        const int c = tid & 63;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int k = k0 + (tid >> 6) + 4 * q;
+            ra[q] = rb[q] = 0.0;
+            if (k < nk) {
+                const int M = k >> 1, comp = k & 1;
+                const size_t row = ((size_t)L1 + ((size_t)M * (2 * LMAX + 1 - M)) / 2) * 2 + comp;
+                const double cm = (M == 0) ? 1.0 : 2.0;
+                if (i0 + c < nrp) ra[q] = cm * alm1[row * nrp + i0 + c];
+                if (j0 + c < nrp) rb[q] = alm2[row * nrp + j0 + c];
+            }
+        }
+    };
+    prefetch(0);
+    for (int k0 = 0; k0 < nk; k0 += 32) {
+        {
+            const int c = tid & 63;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int kk = (tid >> 6) + 4 * q;
+                As[kk * LD + c] = ra[q];
+                Bs[kk * LD + c] = rb[q];
+            }
+        }
+        __syncthreads();
+        if (k0 + 32 < nk) prefetch(k0 + 32);
+        warp_gemm_ts<2, 4>(acc, As + wm * 16, LD, Bs + wn * 32, LD, 32);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int row = i0 + wm * 16 + i * 8 + g;
+        if (row >= nrp) continue;
+        double* dst = W + (size_t)L1 * nrp * nrp + (size_t)row * nrp + j0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int col = wn * 32 + j * 8 + 2 * t;
+            if (j0 + col < nrp) *reinterpret_cast<double2*>(dst + col) = make_double2(acc[i][j][0], acc[i][j][1]);
+        }
+    }
+}
+
 // =============================================================================================
 // Ŵ_{ℓL}[r][r'] = Σ_{L1} (ℓ L L1;000)² W_{L1}[r][r']   — the L1 loop of src/windows.jl:619-622 hoisted out of
 // the per-element work (the quadratic form is linear in W).  One CTA = one ℓ and four L of equal parity, so
@@ -827,7 +891,11 @@ int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp
     // ---- W_{L1} ----
     SFB_CUDA_OK(cudaEventRecord(ev[0], stream));
     if (!reuse_wl) {
-        wl_build_kernel<<<p->LMAX + 1, 256, 0, stream>>>(d_alm1, d_alm2, p->d_W.p, p->LMAX, nrp);
+        if (getenv("SFB_WL_FMA"))
+            wl_build_kernel<<<p->LMAX + 1, 256, 0, stream>>>(d_alm1, d_alm2, p->d_W.p, p->LMAX, nrp);
+        else
+            wl_build_dmma_kernel<<<dim3(p->LMAX + 1, (unsigned)ceil_div(nrp, 64), (unsigned)ceil_div(nrp, 64)), 256, 0,
+                                   stream>>>(d_alm1, d_alm2, p->d_W.p, p->LMAX, nrp);
         SFB_CUDA_OK(cudaGetLastError());
         p->launches = 1;
     }

@@ -767,9 +767,10 @@ static constexpr int cap_synthesis_smem_bytes() {
 template <int NI>
 __global__ void __launch_bounds__(kT) legendre_analysis_kernel(const double* __restrict__ F,
                                                                const double* __restrict__ lam, int nrings, int nhalf,
-                                                               int lmax, int nrp, double w, int accumulate,
+                                                               int kend, int lmax, int nrp, double w, int accumulate,
                                                                const double* __restrict__ add,
                                                                double* __restrict__ alm) {
+    // kend: only the north rings [0, kend) (and their southern mirrors) contribute (kend = nhalf: all rings)
     constexpr int BW = ColTile<NI>::BW, LD = ColTile<NI>::LD;
     extern __shared__ double la_smem[];
     double* As = la_smem;              // [64][kLdA]
@@ -803,19 +804,19 @@ __global__ void __launch_bounds__(kT) legendre_analysis_kernel(const double* __r
         const int kk = tid & 31;
 #pragma unroll
         for (int q = 0; q < 8; ++q)
-            ra[q] = (arow[q] != (size_t)-1 && k0 + kk < nhalf) ? lam[arow[q] + k0 + kk] : 0.0;
+            ra[q] = (arow[q] != (size_t)-1 && k0 + kk < kend) ? lam[arow[q] + k0 + kk] : 0.0;
 #pragma unroll
         for (int u = 0; u < NB; ++u) {
             const int x = tid + u * kT, k2 = x / BW, c = x % BW, k = k0 + k2;
             rn[u] = rs[u] = 0.0;
-            if (k < nhalf && c0 + c < ncol) {
+            if (k < kend && c0 + c < ncol) {
                 rn[u] = Fm[(size_t)k * ncol + c0 + c];
                 if (k != nhalf - 1) rs[u] = Fm[(size_t)(nrings - 1 - k) * ncol + c0 + c];
             }
         }
     };
     prefetch(0);
-    for (int k0 = 0; k0 < nhalf; k0 += 32) {
+    for (int k0 = 0; k0 < kend; k0 += 32) {
         {
             const int kk = tid & 31;
 #pragma unroll
@@ -828,7 +829,7 @@ __global__ void __launch_bounds__(kT) legendre_analysis_kernel(const double* __r
             }
         }
         __syncthreads();
-        if (k0 + 32 < nhalf) prefetch(k0 + 32);
+        if (k0 + 32 < kend) prefetch(k0 + 32);
         warp_gemm_ss<2, NI>(acc, As + wm * 16 * kLdA, kLdA, Bsel + wn * 8 * NI, LD, 32);
         __syncthreads();
     }
@@ -863,9 +864,10 @@ __global__ void __launch_bounds__(kT) legendre_analysis_kernel(const double* __r
 template <int NI>
 __global__ void __launch_bounds__(kT, 2) legendre_synthesis_kernel(const double* __restrict__ alm,
                                                                 const double* __restrict__ lam, int nrings, int nhalf,
-                                                                int lmax, int nrp, double* __restrict__ G,
+                                                                int kend, int lmax, int nrp, double* __restrict__ G,
                                                                 double* __restrict__ F2,
                                                                 const int* __restrict__ nphi_tab) {
+    // kend: only the north rings [0, kend) and their mirrors are synthesised (the grid covers ceil(kend/64) tiles)
     // F2 (optional): rings with nφ > 2 lmax have no aliases, their re-analysed Fourier coefficients are F'_m = nφ G_m
     // (imaginary part of m = 0 dropped; see ring_alias_kernel), so they are written there directly and the alias pass
     // only visits the short polar rings.
@@ -891,7 +893,7 @@ __global__ void __launch_bounds__(kT, 2) legendre_synthesis_kernel(const double*
         for (int q = 0; q < 8; ++q) {
             const int k2 = (tid >> 6) + 4 * q;
             const int l = l0 + ((k2 < 16) ? 2 * k2 : 2 * (k2 - 16) + 1);
-            rl[q] = (l <= lmax && k0 + x < nhalf) ? lam[lm_mmajor(lmax, l, m) * nhalf + k0 + x] : 0.0;
+            rl[q] = (l <= lmax && k0 + x < kend) ? lam[lm_mmajor(lmax, l, m) * nhalf + k0 + x] : 0.0;
         }
 #pragma unroll
         for (int u = 0; u < NB; ++u) {
@@ -921,7 +923,7 @@ __global__ void __launch_bounds__(kT, 2) legendre_synthesis_kernel(const double*
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
         const int k = k0 + wm * 16 + i * 8 + g;
-        if (k >= nhalf) continue;
+        if (k >= kend) continue;
         const int nph = F2 ? nphi_tab[k] : 0;
         const bool direct = nph > 2 * lmax;
         const double sc = direct ? (double)nph : 1.0;
@@ -945,6 +947,125 @@ __global__ void __launch_bounds__(kT, 2) legendre_synthesis_kernel(const double*
 }
 
 // ---------------------------------------------------------------------------------------------
+// Alias-free rings through a precomputed Gram matrix.  On a ring with nφ > 2 lmax the re-analysed coefficients are
+// F'_m = nφ G_m, so the part of a Jacobi pass that runs over those rings,  alm -> w Λ_direct nφ Λ_directᵀ alm,  is the
+// data-independent operator (block diagonal in m; even and odd l-m decouple because λ_lm(π-θ) = (-1)^{l+m} λ_lm(θ))
+//   K_m[l][l'] = w Σ_{north rings k >= kpolar} mult_k nφ_k λ_lm(θ_k) λ_l'm(θ_k),   mult = 2 (1 on the equator).
+// A pass applies K_m (2 L² flops per column and m, L = number of l of one parity) instead of going through the rings
+// twice (4 L · nrings): ≈ 8x fewer flops for these rings at cfg4.  Only the polar rings [0, kpolar) keep
+// synthesis -> alias -> analysis.  (Reduction checked on CPU: tests/test_oracle_sht.py::test_belt_rings_reduce_to_gram_matrices.)
+//
+// Storage: block (m, par) at gram_off[2m+par], row-major [Lp][ldk], ldk = Lp rounded up to 32, zero padded columns.
+
+// K tile 32x32 per CTA, plain FMAs (runs once per plan).  grid = (col tiles, row tiles, 2(lmax+1))
+__global__ void __launch_bounds__(256) gram_build_kernel(const double* __restrict__ lam, const int* __restrict__ nphi_tab,
+                                                         const long long* __restrict__ gram_off, int lmax, int nhalf,
+                                                         int kpolar, double w, double* __restrict__ K) {
+    const int m = blockIdx.z >> 1, par = blockIdx.z & 1;
+    const int Lp = (m + par <= lmax) ? (lmax - m - par) / 2 + 1 : 0;
+    const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+    if (i0 >= Lp || j0 >= Lp) return;
+    const int ldk = (Lp + 31) & ~31;
+    __shared__ double Ai[32][33], Aj[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int k0 = kpolar; k0 < nhalf; k0 += 32) {
+        for (int r = ty; r < 32; r += 8) {
+            const int k = k0 + tx;
+            const int li = m + par + 2 * (i0 + r), lj = m + par + 2 * (j0 + r);
+            double sc = 0.0;
+            if (k < nhalf) sc = w * (double)nphi_tab[k] * ((k == nhalf - 1) ? 1.0 : 2.0);
+            Ai[r][tx] = (k < nhalf && li <= lmax) ? sc * lam[lm_mmajor(lmax, li, m) * nhalf + k] : 0.0;
+            Aj[r][tx] = (k < nhalf && lj <= lmax) ? lam[lm_mmajor(lmax, lj, m) * nhalf + k] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int kk = 0; kk < 32; ++kk) {
+            const double b = Aj[tx][kk];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[q] = fma(Ai[ty + 8 * q][kk], b, acc[q]);
+        }
+        __syncthreads();
+    }
+    double* dst = K + gram_off[blockIdx.z];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int i = i0 + ty + 8 * q, j = j0 + tx;
+        if (i < Lp && j < ldk) dst[(size_t)i * ldk + j] = (j < Lp) ? acc[q] : 0.0;
+    }
+}
+
+// out[l][c] = add[l][c] - Σ_l' K_m[l][l'] x[l'][c]      CTA = ((m, parity), 64 l's of that parity, BW columns)
+template <int NI>
+__global__ void __launch_bounds__(kT) gram_apply_kernel(const double* __restrict__ K, const long long* __restrict__ gram_off,
+                                                        const double* __restrict__ x, const double* __restrict__ add,
+                                                        int lmax, int nrp, double* __restrict__ out) {
+    constexpr int BW = ColTile<NI>::BW, LD = ColTile<NI>::LD;
+    __shared__ double As[64 * kLdA];
+    __shared__ double Bs[32 * LD];
+    const int m = blockIdx.z >> 1, par = blockIdx.z & 1;
+    const int Lp = (m + par <= lmax) ? (lmax - m - par) / 2 + 1 : 0;
+    const int r0 = blockIdx.x * 64, c0 = blockIdx.y * BW;
+    if (r0 >= Lp) return;
+    const int ldk = (Lp + 31) & ~31, ncol = 2 * nrp;
+    const double* Km = K + gram_off[blockIdx.z];
+    const size_t lm0 = lm_mmajor(lmax, m + par, m);            // alm row of the first l of this parity; rows step by 2
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int wm = warp >> 1, wn = warp & 1;
+    double acc[2][NI][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    constexpr int NB = (32 * BW) / kT;
+    double ra[8], rb[NB];
+    auto prefetch = [&](int k0) {
+        const int kk = tid & 31;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int row = r0 + (tid >> 5) + 8 * q;
+            ra[q] = (row < Lp) ? Km[(size_t)row * ldk + k0 + kk] : 0.0;      // k0 + kk < ldk always (zero padded)
+        }
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+            const int y = tid + u * kT, k2 = y / BW, c = y % BW, j = k0 + k2;
+            rb[u] = (j < Lp && c0 + c < ncol) ? x[(lm0 + 2 * (size_t)j) * ncol + c0 + c] : 0.0;
+        }
+    };
+    prefetch(0);
+    for (int k0 = 0; k0 < Lp; k0 += 32) {
+        {
+            const int kk = tid & 31;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) As[((tid >> 5) + 8 * q) * kLdA + kk] = ra[q];
+#pragma unroll
+            for (int u = 0; u < NB; ++u) {
+                const int y = tid + u * kT;
+                Bs[(y / BW) * LD + (y % BW)] = rb[u];
+            }
+        }
+        __syncthreads();
+        if (k0 + 32 < Lp) prefetch(k0 + 32);
+        warp_gemm_ss<2, NI>(acc, As + wm * 16 * kLdA, kLdA, Bs + wn * 8 * NI, LD, 32);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int row = r0 + wm * 16 + i * 8 + g;
+        if (row >= Lp) continue;
+        const size_t off = (lm0 + 2 * (size_t)row) * ncol + c0;
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+            const int col = wn * 8 * NI + j * 8 + 2 * t;
+            if (c0 + col < ncol) {
+                out[off + col] = add[off + col] - acc[i][j][0];
+                out[off + col + 1] = add[off + col + 1] - acc[i][j][1];
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Ring-space form of the Jacobi refinement.  Re-analysing a synthesised ring needs no pixels: with
 // f_j = Σ_{m'} c_{m'} Re(G_{m'} e^{im'φ_j}) and Σ_j e^{ikφ_j} = nφ e^{ikφ0} [k ≡ 0 mod nφ],
 //   F'_m = Σ_j f_j e^{-imφ_j}
@@ -953,6 +1074,51 @@ __global__ void __launch_bounds__(kT, 2) legendre_synthesis_kernel(const double*
 // F'_m = nφ G_m; short polar rings pick up their exact aliases.  So map - S(alm) is never formed in the iterations:
 //   alm <- alm + A f - LegendreAnalysis(F'(LegendreSynthesis(alm))).
 // thread = (ring, m, column c of the re plane); G and F2 are [m][ring][re/im][nrp].
+// Shared-memory form: CTA = (aliased ring, 16 shells); all G_{m'} of the ring and those shells are staged once (halved for
+// m' = 0), then every F'_m is combined from shared memory — each G element is read from L2/HBM exactly once instead of
+// once per aliased m (ring i = 1: 140 times).
+constexpr int kAliasCW = 16;
+__global__ void __launch_bounds__(256) ring_alias_smem_kernel(const double* __restrict__ G, double* __restrict__ F2,
+                                                              const int* __restrict__ ring_list,
+                                                              const int* __restrict__ nphi_tab,
+                                                              const int* __restrict__ shift_tab, int nrings, int lmax,
+                                                              int nrp) {
+    extern __shared__ double Gs[];   // [m'][re/im][kAliasCW]
+    constexpr int CW = kAliasCW;
+    const int ring = ring_list[blockIdx.x], c0 = blockIdx.y * CW;
+    const int n = nphi_tab[ring];
+    const double sig = shift_tab[ring] ? -1.0 : 1.0;
+    const size_t stride_m = (size_t)nrings * 2 * nrp;
+    const double* g = G + (size_t)ring * 2 * nrp + c0;
+    for (int x = threadIdx.x; x < (lmax + 1) * 2 * CW; x += blockDim.x) {
+        const int c = x % CW, comp = (x / CW) & 1, mp = x / (2 * CW);
+        double v = 0.0;
+        if (c0 + c < nrp) v = g[(size_t)mp * stride_m + (size_t)comp * nrp + c];
+        Gs[x] = (mp == 0) ? 0.5 * v : v;
+    }
+    __syncthreads();
+    double* f = F2 + (size_t)ring * 2 * nrp + c0;
+    for (int x = threadIdx.x; x < (lmax + 1) * CW; x += blockDim.x) {
+        const int c = x % CW, m = x / CW;
+        if (c0 + c >= nrp) continue;
+        double re = 0.0, im = 0.0;
+        for (int mp = m % n; mp <= lmax; mp += n) {                 // m' ≡ m (mod n)
+            const int tt = (mp - m) / n;
+            const double s = (tt & 1) ? sig : 1.0;
+            re += s * Gs[(mp * 2) * CW + c];
+            im += s * Gs[(mp * 2 + 1) * CW + c];
+        }
+        for (int mp = (n - m % n) % n; mp <= lmax; mp += n) {       // m' ≡ -m (mod n)
+            const int tt = (mp + m) / n;
+            const double s = (tt & 1) ? sig : 1.0;
+            re += s * Gs[(mp * 2) * CW + c];
+            im -= s * Gs[(mp * 2 + 1) * CW + c];
+        }
+        f[(size_t)m * stride_m + c] = n * re;
+        f[(size_t)m * stride_m + nrp + c] = n * im;
+    }
+}
+
 __global__ void ring_alias_kernel(const double* __restrict__ G, double* __restrict__ F2, const int* __restrict__ nphi_tab,
                                   const int* __restrict__ shift_tab, int nrings, int lmax, int nrp) {
     const int ring = blockIdx.x, m = blockIdx.y;
@@ -1112,6 +1278,47 @@ int sht_plan_create(ShtPlan** out, int64_t nside_in, int64_t nside_out, int64_t 
     twiddle_table_kernel<<<ns, 256>>>(p->d_tw.p, ns);
     lambda_table_kernel<<<dim3((unsigned)ceil_div(p->nhalf, 128), (unsigned)(lmax + 1)), 128>>>(p->d_lam.p, ns, (int)lmax,
                                                                                               p->nhalf);
+    {
+        // rings [0, kpolar) keep synthesis -> alias -> analysis in a Jacobi pass; the alias-free rings beyond go through
+        // the Gram matrices.  kpolar = the aliased north rings (nφ <= 2 lmax) rounded up to the synthesis tile of 64.
+        int kalias = 0;
+        for (int k = 0; k < p->nhalf; ++k)
+            if (nphi[k] <= 2 * lmax) kalias = k + 1;
+        std::vector<int> alias_rings;     // both hemispheres, shortest rings last (they do the most work per CTA: first)
+        for (int idx = 0; idx < p->nrings; ++idx)
+            if (nphi[idx] <= 2 * lmax) alias_rings.push_back(idx);
+        std::sort(alias_rings.begin(), alias_rings.end(), [&](int a, int b) { return nphi[a] < nphi[b]; });
+        p->n_alias_rings = (int)alias_rings.size();
+        rc = up(p->d_alias_rings, alias_rings);
+        if (rc) {
+            delete p;
+            return rc;
+        }
+        p->kpolar = (int)std::min<int64_t>(p->nhalf, round_up(kalias, 64));
+        if (getenv("SFB_SHT_NO_GRAM")) p->kpolar = p->nhalf;
+        if (p->kpolar < p->nhalf) {
+            std::vector<long long> off(2 * (lmax + 1) + 1, 0);
+            for (int m = 0; m <= lmax; ++m)
+                for (int par = 0; par < 2; ++par) {
+                    const long long Lp = (m + par <= lmax) ? (lmax - m - par) / 2 + 1 : 0;
+                    off[2 * m + par + 1] = off[2 * m + par] + Lp * round_up(Lp, 32);
+                }
+            rc = p->d_gram_off.alloc(off.size());
+            if (!rc && cudaMemcpy(p->d_gram_off.p, off.data(), off.size() * sizeof(long long), cudaMemcpyHostToDevice) !=
+                           cudaSuccess)
+                rc = 1;
+            rc = rc ? rc : p->d_gram.alloc((size_t)std::max<long long>(1, off.back()));
+            if (rc) {
+                set_error("sht_plan_create: Gram-matrix tables");
+                delete p;
+                return rc;
+            }
+            const unsigned tiles = (unsigned)ceil_div(lmax / 2 + 1, 32);
+            gram_build_kernel<<<dim3(tiles, tiles, 2 * (unsigned)(lmax + 1)), 256>>>(
+                p->d_lam.p, p->d_nphi.p, p->d_gram_off.p, (int)lmax, p->nhalf, p->kpolar,
+                4.0 * 3.14159265358979323846 / (double)p->npix, p->d_gram.p);
+        }
+    }
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         set_error(std::string("sht_plan_create setup kernels: ") + cudaGetErrorString(e));
@@ -1167,7 +1374,8 @@ static int run_ring_analysis(ShtPlan* p, const double* map, int64_t ldw, cudaStr
 
 // F (ring-Fourier coefficients, in `Fsrc`) -> alm:  alm = [accumulate ? alm : 0] + [add ? add : 0] + w Λ F
 static int run_legendre_analysis(ShtPlan* p, const double* Fsrc, double w, int accumulate, const double* add,
-                                 double* d_alm, cudaStream_t st) {
+                                 double* d_alm, cudaStream_t st, int kend = -1) {
+    if (kend < 0) kend = p->nhalf;
     const int lmax = p->lmax, nrp = p->nrp;
     const int nil = pick_ni(2 * nrp);
     dim3 g2((unsigned)ceil_div(lmax + 1, 64), (unsigned)ceil_div(2 * nrp, 16 * nil), lmax + 1);
@@ -1176,8 +1384,8 @@ static int run_legendre_analysis(ShtPlan* p, const double* Fsrc, double w, int a
     do {                                                                                                              \
         SFB_CUDA_OK(cudaFuncSetAttribute(legendre_analysis_kernel<NI_>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                          la_smem_bytes));                                                             \
-        legendre_analysis_kernel<NI_><<<g2, kT, la_smem_bytes, st>>>(Fsrc, p->d_lam.p, p->nrings, p->nhalf, lmax, nrp, \
-                                                                     w, accumulate, add, d_alm);                     \
+        legendre_analysis_kernel<NI_><<<g2, kT, la_smem_bytes, st>>>(Fsrc, p->d_lam.p, p->nrings, p->nhalf, kend, lmax,  \
+                                                                     nrp, w, accumulate, add, d_alm);                \
     } while (0)
     if (nil == 4)
         SFB_LAUNCH_LA(4);
@@ -1218,19 +1426,19 @@ int sht_map2alm(ShtPlan* p, const double* d_win, int64_t ldw, int niter, double*
     RingTabs rt{p->d_nphi.p, p->d_start.p, p->d_shift.p, p->d_twoff.p, p->d_tw.p};
     const double w = 4.0 * 3.14159265358979323846 / (double)p->npix;
     const bool pixel_iter = getenv("SFB_SHT_PIXEL_ITER") != nullptr;  // cross-check: refine through pixel space
-    auto legendre_synthesis = [&](bool ring_iter) -> int {
+    auto legendre_synthesis = [&](bool ring_iter, int kend) -> int {
         double* f2 = ring_iter ? p->d_F2.p : nullptr;
         const int nil = pick_ni(2 * p->nrp);
-        dim3 gs(p->lmax + 1, (unsigned)ceil_div(p->nhalf, 64), (unsigned)ceil_div(2 * p->nrp, 16 * nil));
+        dim3 gs(p->lmax + 1, (unsigned)ceil_div(kend, 64), (unsigned)ceil_div(2 * p->nrp, 16 * nil));
         if (nil == 4)
-            legendre_synthesis_kernel<4><<<gs, kT, 0, st>>>(d_alm, p->d_lam.p, p->nrings, p->nhalf, p->lmax, p->nrp, p->d_FG.p,
-                                                            f2, p->d_nphi.p);
+            legendre_synthesis_kernel<4><<<gs, kT, 0, st>>>(d_alm, p->d_lam.p, p->nrings, p->nhalf, kend, p->lmax, p->nrp,
+                                                            p->d_FG.p, f2, p->d_nphi.p);
         else if (nil == 2)
-            legendre_synthesis_kernel<2><<<gs, kT, 0, st>>>(d_alm, p->d_lam.p, p->nrings, p->nhalf, p->lmax, p->nrp, p->d_FG.p,
-                                                            f2, p->d_nphi.p);
+            legendre_synthesis_kernel<2><<<gs, kT, 0, st>>>(d_alm, p->d_lam.p, p->nrings, p->nhalf, kend, p->lmax, p->nrp,
+                                                            p->d_FG.p, f2, p->d_nphi.p);
         else
-            legendre_synthesis_kernel<1><<<gs, kT, 0, st>>>(d_alm, p->d_lam.p, p->nrings, p->nhalf, p->lmax, p->nrp, p->d_FG.p,
-                                                            f2, p->d_nphi.p);
+            legendre_synthesis_kernel<1><<<gs, kT, 0, st>>>(d_alm, p->d_lam.p, p->nrings, p->nhalf, kend, p->lmax, p->nrp,
+                                                            p->d_FG.p, f2, p->d_nphi.p);
         SFB_CUDA_OK(cudaGetLastError());
         p->launches += 1;
         return 0;
@@ -1243,19 +1451,50 @@ int sht_map2alm(ShtPlan* p, const double* d_win, int64_t ldw, int niter, double*
         SFB_TRY(run_ring_analysis(p, map, ldm, st));
         SFB_TRY(run_legendre_analysis(p, p->d_FG.p, w, 0, nullptr, p->d_a0.p, st));
         SFB_CUDA_OK(cudaMemcpyAsync(d_alm, p->d_a0.p, nalm * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        const bool gram = p->kpolar < p->nhalf;
+        if (gram) SFB_TRY(p->d_t.alloc(nalm));
         for (int it = 0; it < niter; ++it) {
-            SFB_TRY(legendre_synthesis(true));
-            ring_alias_kernel<<<dim3(p->nrings, p->lmax + 1), 64, 0, st>>>(p->d_FG.p, p->d_F2.p, p->d_nphi.p, p->d_shift.p,
-                                                                          p->nrings, p->lmax, p->nrp);
-            SFB_CUDA_OK(cudaGetLastError());
-            p->launches++;
-            SFB_TRY(run_legendre_analysis(p, p->d_F2.p, -w, 1, p->d_a0.p, d_alm, st));
+            const double* add = p->d_a0.p;
+            if (gram) {   // t = A f - K alm  (alias-free rings), from the alm of the previous pass
+                const int nil = pick_ni(2 * p->nrp);
+                dim3 gg((unsigned)ceil_div(p->lmax / 2 + 1, 64), (unsigned)ceil_div(2 * p->nrp, 16 * nil),
+                        2 * (unsigned)(p->lmax + 1));
+                if (nil == 4)
+                    gram_apply_kernel<4><<<gg, kT, 0, st>>>(p->d_gram.p, p->d_gram_off.p, d_alm, p->d_a0.p, p->lmax, p->nrp,
+                                                            p->d_t.p);
+                else if (nil == 2)
+                    gram_apply_kernel<2><<<gg, kT, 0, st>>>(p->d_gram.p, p->d_gram_off.p, d_alm, p->d_a0.p, p->lmax, p->nrp,
+                                                            p->d_t.p);
+                else
+                    gram_apply_kernel<1><<<gg, kT, 0, st>>>(p->d_gram.p, p->d_gram_off.p, d_alm, p->d_a0.p, p->lmax, p->nrp,
+                                                            p->d_t.p);
+                SFB_CUDA_OK(cudaGetLastError());
+                p->launches++;
+                add = p->d_t.p;
+            }
+            if (p->kpolar > 0) {
+                SFB_TRY(legendre_synthesis(true, p->kpolar));
+                const int alias_smem = (p->lmax + 1) * 2 * kAliasCW * (int)sizeof(double);
+                if (p->n_alias_rings > 0 && alias_smem <= 200 * 1024 && !getenv("SFB_ALIAS_OLD")) {
+                    SFB_CUDA_OK(cudaFuncSetAttribute(ring_alias_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     alias_smem));
+                    ring_alias_smem_kernel<<<dim3(p->n_alias_rings, (unsigned)ceil_div(p->nrp, kAliasCW)), 256, alias_smem,
+                                             st>>>(p->d_FG.p, p->d_F2.p, p->d_alias_rings.p, p->d_nphi.p, p->d_shift.p,
+                                                   p->nrings, p->lmax, p->nrp);
+                } else if (p->n_alias_rings > 0) {
+                    ring_alias_kernel<<<dim3(p->nrings, p->lmax + 1), 64, 0, st>>>(p->d_FG.p, p->d_F2.p, p->d_nphi.p,
+                                                                                  p->d_shift.p, p->nrings, p->lmax, p->nrp);
+                }
+                SFB_CUDA_OK(cudaGetLastError());
+                p->launches++;
+                SFB_TRY(run_legendre_analysis(p, p->d_F2.p, -w, 1, add, d_alm, st, p->kpolar));
+            }
         }
     } else {
     SFB_TRY(run_analysis(p, map, ldm, 0, d_alm, st));
     if (niter > 0) SFB_TRY(p->d_resid.alloc((size_t)p->npix * p->nrp));
     for (int it = 0; it < niter; ++it) {
-        SFB_TRY(legendre_synthesis(false));
+        SFB_TRY(legendre_synthesis(false, p->nhalf));
         if (p->ntiles > 0) {
             dim3 gr(p->ntiles, (unsigned)ceil_div(p->nrp, 64));
             ring_synthesis_kernel<<<gr, kT, 0, st>>>(p->d_FG.p, rt, p->d_tile_ring.p, p->d_tile_j0.p, p->nrings,

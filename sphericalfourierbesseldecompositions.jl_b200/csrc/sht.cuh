@@ -32,6 +32,12 @@ struct ShtPlan {
     DevBuf<double> d_resid;  // residual maps [npix][nrp] (pixel-space refinement only)
     DevBuf<double> d_F2;     // aliased ring-Fourier coefficients of the synthesised field (ring-space refinement)
     DevBuf<double> d_a0;     // A f, the first-pass alm
+    DevBuf<int> d_alias_rings;   // rings with nφ <= 2 lmax (both hemispheres): the alias pass visits only these
+    int n_alias_rings = 0;
+    int kpolar = 0;          // north rings [0, kpolar) keep synthesis -> alias -> analysis in a Jacobi pass ...
+    DevBuf<double> d_gram;   // ... the alias-free rings beyond act through Gram matrices K_m (see sht.cu)
+    DevBuf<long long> d_gram_off;
+    DevBuf<double> d_t;      // A f - K alm
 
     float t_total = 0;
     int launches = 0;

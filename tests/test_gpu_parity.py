@@ -272,7 +272,7 @@ def test_device_pipeline_row_shards():
 # the kernels behind the environment switches are exercised here (the switches are read at call
 # time), each against the oracle, so none of them is dead code on the GPU box.
 
-@pytest.mark.parametrize("flag", ["SFB_NO_MIRROR", "SFB_CMIX_OLD", "SFB_WHAT_FMA"])
+@pytest.mark.parametrize("flag", ["SFB_NO_MIRROR", "SFB_CMIX_OLD", "SFB_WHAT_FMA", "SFB_WL_FMA"])
 @pytest.mark.parametrize("nr", [24, 64])
 def test_stage23_alternative_paths(monkeypatch, flag, nr):
     import warnings
@@ -302,3 +302,25 @@ def test_stage1_pixel_space_refinement_path(monkeypatch, nside, lmax, nr):
     got = sfb.calc_Wr_lm(win, lmax, nside)
     assert relerr(got, ref) < RTOL
     assert relerr(got, base) < 1e-11
+
+
+@pytest.mark.parametrize("flag", ["SFB_SHT_NO_GRAM", "SFB_ALIAS_OLD"])
+@pytest.mark.parametrize("nside,lmax,nr", [(16, 24, 9), (32, 40, 3), (64, 100, 2)])
+def test_stage1_ring_space_variants(monkeypatch, flag, nside, lmax, nr):
+    """The ring-Fourier Jacobi pass in its three forms must agree: Gram matrices for the alias-free rings + shared-memory
+    alias kernel (default), every ring through synthesis/analysis (SFB_SHT_NO_GRAM, read at plan creation), and the
+    per-(ring, m) alias kernel (SFB_ALIAS_OLD)."""
+    import sfb_b200 as sfb
+    rng = np.random.default_rng(nside + lmax)
+    win = rng.random((nr, 12 * nside * nside))
+    win[:, ::3] = 0.0
+    ref = ow.calc_Wr_lm(win, lmax, nside) if nside <= 32 else None
+    base = sfb.calc_Wr_lm(win, lmax, nside)
+    monkeypatch.setenv(flag, "1")
+    sfb.calc_Wr_lm(win[:1, :12 * 4 * 4].copy(), 4, 4)          # evict the cached plan so that it is rebuilt under the flag
+    got = sfb.calc_Wr_lm(win, lmax, nside)
+    monkeypatch.delenv(flag)
+    sfb.calc_Wr_lm(win[:1, :12 * 4 * 4].copy(), 4, 4)
+    if ref is not None:
+        assert relerr(base, ref) < RTOL and relerr(got, ref) < RTOL
+    assert relerr(got, base) < 1e-12
