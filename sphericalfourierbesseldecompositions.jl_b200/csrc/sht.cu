@@ -1074,48 +1074,53 @@ __global__ void __launch_bounds__(kT) gram_apply_kernel(const double* __restrict
 // F'_m = nφ G_m; short polar rings pick up their exact aliases.  So map - S(alm) is never formed in the iterations:
 //   alm <- alm + A f - LegendreAnalysis(F'(LegendreSynthesis(alm))).
 // thread = (ring, m, column c of the re plane); G and F2 are [m][ring][re/im][nrp].
-// Shared-memory form: CTA = (aliased ring, 16 shells); all G_{m'} of the ring and those shells are staged once (halved for
-// m' = 0), then every F'_m is combined from shared memory — each G element is read from L2/HBM exactly once instead of
-// once per aliased m (ring i = 1: 140 times).
+// Class-sum form (identity checked on CPU: tests/test_oracle_sht.py::test_alias_operator_class_sum_form).
+// F'_m depends on m only through ρ = m mod nφ and q = m div nφ: with the alternating class sums
+//   Q[ρ] = Σ_j σ^j c_{ρ+j nφ} G_{ρ+j nφ}      (c_0 = 1/2, c_{m'} = 1 otherwise; σ = -1 on shifted rings)
+//   F'_m = nφ σ^q ( Q[ρ] + σ^{[ρ≠0]} conj Q[(nφ-ρ) mod nφ] ).
+// CTA = (aliased ring, 16 shells): one pass over m' builds Q in shared memory (every G element is read exactly once,
+// the per-(ring, m) kernel below reads it once per aliased m: 140 times on ring 1), one pass over m writes F'.
 constexpr int kAliasCW = 16;
 __global__ void __launch_bounds__(256) ring_alias_smem_kernel(const double* __restrict__ G, double* __restrict__ F2,
                                                               const int* __restrict__ ring_list,
                                                               const int* __restrict__ nphi_tab,
                                                               const int* __restrict__ shift_tab, int nrings, int lmax,
                                                               int nrp) {
-    extern __shared__ double Gs[];   // [m'][re/im][kAliasCW]
+    extern __shared__ double Qs[];   // [ρ < min(nφ, lmax+1)][re/im][kAliasCW]
     constexpr int CW = kAliasCW;
     const int ring = ring_list[blockIdx.x], c0 = blockIdx.y * CW;
     const int n = nphi_tab[ring];
     const double sig = shift_tab[ring] ? -1.0 : 1.0;
     const size_t stride_m = (size_t)nrings * 2 * nrp;
     const double* g = G + (size_t)ring * 2 * nrp + c0;
-    for (int x = threadIdx.x; x < (lmax + 1) * 2 * CW; x += blockDim.x) {
-        const int c = x % CW, comp = (x / CW) & 1, mp = x / (2 * CW);
-        double v = 0.0;
-        if (c0 + c < nrp) v = g[(size_t)mp * stride_m + (size_t)comp * nrp + c];
-        Gs[x] = (mp == 0) ? 0.5 * v : v;
+    const int nrho = min(n, lmax + 1);
+    for (int x = threadIdx.x; x < nrho * 2 * CW; x += blockDim.x) {
+        const int c = x % CW, comp = (x / CW) & 1, rho = x / (2 * CW);
+        double q = 0.0;
+        if (c0 + c < nrp) {
+            double s = (rho == 0) ? 0.5 : 1.0;
+            for (int mp = rho; mp <= lmax; mp += n) {
+                q = fma(s, g[(size_t)mp * stride_m + (size_t)comp * nrp + c], q);
+                s = (mp == 0) ? sig : s * sig;           // c_0 = 1/2 applies to m' = 0 only
+            }
+        }
+        Qs[x] = q;
     }
     __syncthreads();
     double* f = F2 + (size_t)ring * 2 * nrp + c0;
     for (int x = threadIdx.x; x < (lmax + 1) * CW; x += blockDim.x) {
         const int c = x % CW, m = x / CW;
         if (c0 + c >= nrp) continue;
-        double re = 0.0, im = 0.0;
-        for (int mp = m % n; mp <= lmax; mp += n) {                 // m' ≡ m (mod n)
-            const int tt = (mp - m) / n;
-            const double s = (tt & 1) ? sig : 1.0;
-            re += s * Gs[(mp * 2) * CW + c];
-            im += s * Gs[(mp * 2 + 1) * CW + c];
+        const int rho = m % n, q = m / n, rho2 = (n - rho) % n;
+        const double sq = (q & 1) ? sig : 1.0, s2 = (rho != 0) ? sig : 1.0;
+        const double re1 = Qs[(rho * 2) * CW + c], im1 = Qs[(rho * 2 + 1) * CW + c];
+        double re2 = 0.0, im2 = 0.0;
+        if (rho2 < nrho) {
+            re2 = Qs[(rho2 * 2) * CW + c];
+            im2 = Qs[(rho2 * 2 + 1) * CW + c];
         }
-        for (int mp = (n - m % n) % n; mp <= lmax; mp += n) {       // m' ≡ -m (mod n)
-            const int tt = (mp + m) / n;
-            const double s = (tt & 1) ? sig : 1.0;
-            re += s * Gs[(mp * 2) * CW + c];
-            im -= s * Gs[(mp * 2 + 1) * CW + c];
-        }
-        f[(size_t)m * stride_m + c] = n * re;
-        f[(size_t)m * stride_m + nrp + c] = n * im;
+        f[(size_t)m * stride_m + c] = n * sq * (re1 + s2 * re2);
+        f[(size_t)m * stride_m + nrp + c] = n * sq * (im1 - s2 * im2);
     }
 }
 
