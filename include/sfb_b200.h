@@ -115,6 +115,15 @@ int32_t sfb_power_win_mix_binned(const double* win1, int64_t nr, int64_t npix_in
  * Wr_00 is an error, as the reference takes its square root (:400).                                              */
 int32_t sfb_win_lnn(const double* win, int64_t nr, int64_t npix_in, int64_t ld_win, int64_t nside, const double* G,
                     int64_t nmax, int64_t lmax, const int64_t* lnn, int64_t lnnsize, double* Wlnn_out);
+/* calc_wmix(win, wmodes, amodes; neg_m) (src/windows.jl:299-364, calc_wmix_ii :273-294, calc_gaunts_L :449-464;
+ * SURVEY §8f row 1): the full window mixing matrix W_{nlm}^{n'l'm'} for m, m' >= 0 (neg_m != 0: m -> -m), nlmsize x
+ * nlmsize ComplexF64 in getidx(amodes, n, l, m) order (src/modes.jl:222-232).  Stage 1 as for power_win_mix
+ * (calc_Wr_lm(win, 2 lmax, nside)), overlap integrals on DMMA, general-m 3j families by a warp-cooperative
+ * Schulten-Gordon recursion (WignerFamilies semantics, src/windows.jl:434-446).  nmax_l (lmax+1 entries) and lmax_n
+ * (nmax entries) are the AnlmModes tables; calc_wmix_all (src/window_chains.jl:578-582) = the two calls neg_m = 0, 1. */
+int32_t sfb_calc_wmix(const double* win, int64_t nr, int64_t npix_in, int64_t ld_win, int64_t nside, const double* G,
+                      int64_t nmax, int64_t lmax, const int64_t* nmax_l, const int64_t* lmax_n, int32_t neg_m,
+                      double* wmix_out);
 /* device-resident form: d_alm = planar W_lm(r) of sfb_calc_wr_lm_dev, d_Wlnn = nout doubles */
 int32_t sfb_win_lnn_dev(sfb_cmix_plan* plan, const double* d_alm, double* d_Wlnn, void* stream);
 

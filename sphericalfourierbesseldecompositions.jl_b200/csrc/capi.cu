@@ -5,6 +5,7 @@
 #include "cmix.cuh"
 #include "common.cuh"
 #include "sht.cuh"
+#include "wmix.cuh"
 
 #include <atomic>
 #include <chrono>
@@ -888,6 +889,28 @@ int32_t sfb_win_lnn(const double* win, int64_t nr, int64_t npix_in, int64_t ld_w
     SFB_CUDA_OK(cudaMemcpy(Wlnn_out, d_out.p, (size_t)pg.p->nout * sizeof(double), cudaMemcpyDeviceToHost));
     return 0;
 }
+int32_t sfb_calc_wmix(const double* win, int64_t nr, int64_t npix_in, int64_t ld_win, int64_t nside, const double* G,
+                      int64_t nmax, int64_t lmax, const int64_t* nmax_l, const int64_t* lmax_n, int32_t neg_m,
+                      double* wmix_out) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    SFB_REQUIRE(win && G && nmax_l && lmax_n && wmix_out, "null pointer");
+    Workspace* ws = nullptr;
+    SFB_TRY(get_ws(&ws));
+    bool same = true;
+    SFB_TRY(windows_to_alm(*ws, win, nullptr, nr, npix_in, ld_win, nside, 2 * lmax, &same));
+    int64_t nlmsize = 0;
+    for (int64_t n = 0; n < nmax; ++n) nlmsize += (lmax_n[n] + 1) * (lmax_n[n] + 2) / 2;
+    SFB_REQUIRE(nlmsize >= 1, "calc_wmix: empty mode set");
+    DevBuf<double> d_out;
+    SFB_TRY(d_out.alloc((size_t)nlmsize * nlmsize * 2));
+    SFB_TRY(wmix_run(ws->alm1.p, (int)round_up(nr, 8), G, nr, nmax, lmax, nmax_l, lmax_n, neg_m, d_out.p, nullptr,
+                     ws->main));
+    g_times[6] += 1;
+    SFB_TRY(check_finite(d_out.p, (size_t)nlmsize * nlmsize * 2, "wmix"));
+    SFB_CUDA_OK(cudaMemcpy(wmix_out, d_out.p, (size_t)nlmsize * nlmsize * 2 * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 int32_t sfb_win_lnn_dev(sfb_cmix_plan* plan, const double* d_alm, double* d_Wlnn, void* stream) {
     std::lock_guard<std::mutex> lk(g_mutex);
     return win_lnn_run(reinterpret_cast<CmixPlan*>(plan), d_alm, d_Wlnn, (cudaStream_t)stream);

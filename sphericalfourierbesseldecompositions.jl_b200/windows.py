@@ -28,7 +28,8 @@ from .modes import AnlmModes, ClnnBinnedModes, ClnnModes, getlmsize, getlnnsize
 from .separable import SeparableArray
 
 __all__ = ["ConfigurationSpaceModes", "window_r", "calc_Wr_lm", "optimize_Wr_lm_layout", "precompute_gnlr",
-           "check_nsamp", "power_win_mix", "rsdrgnlr", "set_devices", "get_devices", "pinned_empty"]
+           "check_nsamp", "power_win_mix", "rsdrgnlr", "set_devices", "get_devices", "pinned_empty", "calc_wmix",
+           "calc_wmix_all"]
 
 LAYOUT_MMAJOR, LAYOUT_MFAST = 0, 1
 
@@ -293,6 +294,33 @@ def win_lnn(win, wmodes, cmodes):
     _lib.check(lib.sfb_win_lnn(_lib.ptr(w), nr, npix, w.strides[1] // 8, amodes.nside, _lib.ptr(G), amodes.nmax,
                                amodes.lmax, _lib.ptr(lnn), lnn.shape[1], _lib.ptr(out)))
     return out
+
+
+def calc_wmix(win, wmodes, amodes, neg_m=False):
+    """calc_wmix(win, wmodes, amodes; neg_m=false) (src/windows.jl:299-364): W_{nlm}^{n'l'm'} for m, m' >= 0 (or m -> -m),
+    (nlmsize, nlmsize) ComplexF64 in getidx(amodes, n, l, m) order."""
+    from .modes import getnlmsize
+    lib = _lib.load()
+    G = rsdrgnlr(amodes, wmodes)
+    if isinstance(win, SeparableArray):
+        win = np.outer(win.phi, win.mask)
+    w = _as_julia_matrix(win)
+    nr, npix = w.shape
+    if nr != wmodes.nr:
+        raise ValueError("window has %d shells, wmodes.nr = %d" % (nr, wmodes.nr))
+    n = getnlmsize(amodes)
+    out = np.empty((n, n), dtype=np.complex128, order="F")
+    nmax_l = np.ascontiguousarray(amodes.nmax_l, dtype=np.int64)
+    lmax_n = np.ascontiguousarray(amodes.lmax_n, dtype=np.int64)
+    _lib.check(lib.sfb_calc_wmix(_lib.ptr(w), nr, npix, w.strides[1] // 8, amodes.nside, _lib.ptr(G), amodes.nmax,
+                                 amodes.lmax, _lib.ptr(nmax_l), _lib.ptr(lmax_n), int(bool(neg_m)), _lib.ptr(out)))
+    return out
+
+
+def calc_wmix_all(win, wmodes, amodes):
+    """calc_wmix_all (src/window_chains.jl:578-582): (wmix, wmix_negm).  A SeparableArray is materialised (the reference
+    takes a different, mathematically equal route through WindowChainsCacheSeparableWmix, :585-589)."""
+    return calc_wmix(win, wmodes, amodes), calc_wmix(win, wmodes, amodes, neg_m=True)
 
 
 def power_win_mix_from_wrlm(W1r_lm, W2r_lm, wmodes, cmodes, layout=LAYOUT_MMAJOR, div2Lp1=False, interchange_NN=False,
