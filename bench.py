@@ -502,6 +502,8 @@ def run_e2e(sfb, wl, ndev, args):
             res["error"] = "non-finite result"
         # pageable buffers: a plain Julia Matrix{Float64} for the result and the window
         try:
+            if 8.0 * n * n > 6e9:
+                raise RuntimeError("skipped: matrix larger than 6 GB")
             pout = np.empty((n, n), order="F")
             dtp, Mp = run(win, pout)
             res["pageable"] = {"ms_per_step": dtp * 1e3, "value": n * n / dtp,

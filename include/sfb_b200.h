@@ -124,6 +124,31 @@ int32_t sfb_win_lnn(const double* win, int64_t nr, int64_t npix_in, int64_t ld_w
 int32_t sfb_calc_wmix(const double* win, int64_t nr, int64_t npix_in, int64_t ld_win, int64_t nside, const double* G,
                       int64_t nmax, int64_t lmax, const int64_t* nmax_l, const int64_t* lmax_n, int32_t neg_m,
                       double* wmix_out);
+/* ---- SFB transforms next to the window path; they reuse the batched HEALPix kernels of stage 1.
+ * Radial tables are nr x amodes.nmax x (amodes.lmax+1) Float64 (NaN where n > nmax_l[l+1], never read); nmax_l / lmax_n are
+ * the AnlmModes tables; f_nlm vectors are nlmsize ComplexF64 in getidx(amodes, n, l, m) order (src/modes.jl:222-232).
+ *
+ * field2anlm(f_xyz, wmodes, amodes) (src/cat2anlm.jl:326-362): per shell map2alm!(map, alm) with lmax = amodes.lmax,
+ *   niter = 3, then f_nlm = Σ_r T[r,n,l] a_lm(r) with T = g_nl(r) r² Δr.  f_xyz: nr x npix (leading dimension ld).     */
+int32_t sfb_field2anlm(const double* f_xyz, int64_t nr, int64_t npix, int64_t ld, const double* T, int64_t nmax,
+                       int64_t lmax, const int64_t* nmax_l, const int64_t* lmax_n, double* f_nlm_out);
+/* anlm2field(f_nlm, wmodes, amodes) (src/cat2anlm.jl:385-422): a_lm(r) = Σ_n g[r,n,l] f_nlm, alm2map! per shell at
+ *   amodes.nside; f_xyz_out: nr x 12 nside² (leading dimension ld_out).  g = g_nl(r).                                  */
+int32_t sfb_anlm2field(const double* f_nlm, const double* g, int64_t nr, int64_t nside, int64_t nmax, int64_t lmax,
+                       const int64_t* nmax_l, const int64_t* lmax_n, double* f_xyz_out, int64_t ld_out);
+/* win_rhat_ln(win, wmodes, amodes) (src/windows.jl:244-256): out[p, l+1, n] = Σ_r win[r,p] T[r,n,l], T = r² g_nl(r) Δr;
+ *   out: npix x (lmax+1) x nmax, NaN where l > lmax_n[n] (like the reference's NaN-filled array).                      */
+int32_t sfb_win_rhat_ln(const double* win, int64_t nr, int64_t npix, int64_t ld_win, const double* T, int64_t nmax,
+                        int64_t lmax, const int64_t* nmax_l, const int64_t* lmax_n, double* out);
+/* cat2amln(rθϕ, amodes, nbar, win_rhat_ln, weights) (src/cat2anlm.jl:257-314), one batch of nb (n,l) modes: for mode b
+ *   map = Σ_{gal} gw[gal,b] δ_{pix(gal)} / (nbar ΔΩ_pix) − win_rhat_ln[:, l_b+1, n_b], mymap2alm!(map, alm) (lmax = amodes.lmax,
+ *   niter = 3), anlm[(n_b, l_b, m)] = a_{l_b m}.  The shim evaluates gw[gal,b] = weight g_{n_b l_b}(r_gal) (splines stay in
+ *   Julia) and groups the galaxies by RING pixel: pixptr (npix+1, 0-based CSR) and gidx (galaxy indices, catalogue order
+ *   within a pixel, as transform_gnl_spmap! sums them :92-99).  mode_n is 1-based.  anlm_inout: the full nlmsize vector;
+ *   only the entries of the batch are written.                                                                         */
+int32_t sfb_cat2amln(const int64_t* pixptr, const int64_t* gidx, int64_t ngal, const double* gw, const int64_t* mode_n,
+                     const int64_t* mode_l, int64_t nb, double nbar, const double* win_rhat_ln, int64_t nside,
+                     int64_t nmax, int64_t lmax, const int64_t* nmax_l, const int64_t* lmax_n, double* anlm_inout);
 /* device-resident form: d_alm = planar W_lm(r) of sfb_calc_wr_lm_dev, d_Wlnn = nout doubles */
 int32_t sfb_win_lnn_dev(sfb_cmix_plan* plan, const double* d_alm, double* d_Wlnn, void* stream);
 

@@ -39,6 +39,11 @@ SIGNATURES = {
                                            _i64p, _i64p, _f64p, _i64, _i64p, _i64p, _f64p, _i64, _i32, _i32, _f64p]),
     "sfb_win_lnn": (_i32, [_f64p, _i64, _i64, _i64, _i64, _f64p, _i64, _i64, _i64p, _i64, _f64p]),
     "sfb_calc_wmix": (_i32, [_f64p, _i64, _i64, _i64, _i64, _f64p, _i64, _i64, _i64p, _i64p, _i32, _f64p]),
+    "sfb_field2anlm": (_i32, [_f64p, _i64, _i64, _i64, _f64p, _i64, _i64, _i64p, _i64p, _f64p]),
+    "sfb_anlm2field": (_i32, [_f64p, _f64p, _i64, _i64, _i64, _i64, _i64p, _i64p, _f64p, _i64]),
+    "sfb_win_rhat_ln": (_i32, [_f64p, _i64, _i64, _i64, _f64p, _i64, _i64, _i64p, _i64p, _f64p]),
+    "sfb_cat2amln": (_i32, [_i64p, _i64p, _i64, _f64p, _i64p, _i64p, _i64, C.c_double, _f64p, _i64, _i64, _i64, _i64p,
+                            _i64p, _f64p]),
     "sfb_win_lnn_dev": (_i32, [_vp, _f64p, _f64p, _vp]),
     "sfb_sht_plan_create": (_i32, [C.POINTER(_vp), _i64, _i64, _i64, _i64]),
     "sfb_sht_plan_destroy": (_i32, [_vp]),

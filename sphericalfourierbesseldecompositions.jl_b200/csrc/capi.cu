@@ -4,6 +4,7 @@
 #include "binned.cuh"
 #include "cmix.cuh"
 #include "common.cuh"
+#include "sfbt.cuh"
 #include "sht.cuh"
 #include "wmix.cuh"
 
@@ -908,6 +909,81 @@ int32_t sfb_calc_wmix(const double* win, int64_t nr, int64_t npix_in, int64_t ld
     g_times[6] += 1;
     SFB_TRY(check_finite(d_out.p, (size_t)nlmsize * nlmsize * 2, "wmix"));
     SFB_CUDA_OK(cudaMemcpy(wmix_out, d_out.p, (size_t)nlmsize * nlmsize * 2 * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// ---- SFB transforms next to the window path ----
+int32_t sfb_field2anlm(const double* f_xyz, int64_t nr, int64_t npix, int64_t ld, const double* T, int64_t nmax,
+                       int64_t lmax, const int64_t* nmax_l, const int64_t* lmax_n, double* f_nlm_out) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    SFB_REQUIRE(f_xyz && T && f_nlm_out, "null pointer");
+    int64_t nside = 0;
+    SFB_TRY(npix2nside(npix, &nside));
+    ShtPlan* sp = nullptr;
+    SFB_TRY(get_sht_plan(&sp, nside, nside, lmax, nr));
+    Workspace* ws = nullptr;
+    SFB_TRY(get_ws(&ws));
+    SFB_TRY(upload_win(f_xyz, nr, npix, ld, ws->win, ws->main));
+    SFB_TRY(ws->alm1.alloc(sp->lmsize * 2 * sp->nrp));
+    SFB_TRY(sfbt_field2anlm(sp, ws->win.p, nr, T, nmax, lmax, nmax_l, lmax_n, ws->alm1.p, f_nlm_out, ws->main));
+    g_times[0] = sp->t_total;
+    g_times[6] = sp->launches + 1;
+    return 0;
+}
+
+int32_t sfb_anlm2field(const double* f_nlm, const double* g, int64_t nr, int64_t nside, int64_t nmax, int64_t lmax,
+                       const int64_t* nmax_l, const int64_t* lmax_n, double* f_xyz_out, int64_t ld_out) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    SFB_REQUIRE(f_nlm && g && f_xyz_out, "null pointer");
+    ShtPlan* sp = nullptr;
+    SFB_TRY(get_sht_plan(&sp, nside, nside, lmax, nr));
+    Workspace* ws = nullptr;
+    SFB_TRY(get_ws(&ws));
+    SFB_TRY(ws->alm1.alloc(sp->lmsize * 2 * sp->nrp));
+    SFB_TRY(ws->win.alloc((size_t)sp->npix * sp->nrp));
+    SFB_TRY(sfbt_anlm2field(sp, f_nlm, g, nmax, lmax, nmax_l, lmax_n, ws->alm1.p, ws->win.p, f_xyz_out, ld_out, ws->main));
+    g_times[6] = sp->launches + 1;
+    return 0;
+}
+
+int32_t sfb_win_rhat_ln(const double* win, int64_t nr, int64_t npix, int64_t ld_win, const double* T, int64_t nmax,
+                        int64_t lmax, const int64_t* nmax_l, const int64_t* lmax_n, double* out) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    SFB_REQUIRE(win && T && out, "null pointer");
+    Workspace* ws = nullptr;
+    SFB_TRY(get_ws(&ws));
+    SFB_TRY(upload_win(win, nr, npix, ld_win, ws->win, ws->main));
+    const size_t nout = (size_t)npix * (lmax + 1) * nmax;
+    SFB_TRY(ws->M.alloc(nout));
+    SFB_TRY(sfbt_win_rhat_ln(ws->win.p, nr, npix, nr, T, nmax, lmax, nmax_l, lmax_n, ws->M.p, ws->main));
+    SFB_CUDA_OK(cudaMemcpyAsync(out, ws->M.p, nout * sizeof(double), cudaMemcpyDeviceToHost, ws->main));
+    SFB_CUDA_OK(cudaStreamSynchronize(ws->main));
+    g_times[6] = 1;
+    return 0;
+}
+
+int32_t sfb_cat2amln(const int64_t* pixptr, const int64_t* gidx, int64_t ngal, const double* gw, const int64_t* mode_n,
+                     const int64_t* mode_l, int64_t nb, double nbar, const double* win_rhat_ln, int64_t nside,
+                     int64_t nmax, int64_t lmax, const int64_t* nmax_l, const int64_t* lmax_n, double* anlm_inout) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    SFB_REQUIRE(pixptr && mode_n && mode_l && win_rhat_ln && nmax_l && lmax_n && anlm_inout && nb >= 1, "bad arguments");
+    ShtPlan* sp = nullptr;
+    SFB_TRY(get_sht_plan(&sp, nside, nside, lmax, nb));
+    Workspace* ws = nullptr;
+    SFB_TRY(get_ws(&ws));
+    const size_t nw = (size_t)sp->npix * (lmax + 1) * nmax;
+    SFB_TRY(ws->M.alloc(nw));
+    SFB_CUDA_OK(cudaMemcpyAsync(ws->M.p, win_rhat_ln, nw * sizeof(double), cudaMemcpyHostToDevice, ws->main));
+    const int64_t nlmsize = sfbt_nlmsize(nmax, lmax_n);
+    DevBuf<double> d_anlm;
+    SFB_TRY(d_anlm.alloc((size_t)nlmsize * 2));
+    SFB_CUDA_OK(cudaMemcpyAsync(d_anlm.p, anlm_inout, (size_t)nlmsize * 2 * sizeof(double), cudaMemcpyHostToDevice, ws->main));
+    SFB_TRY(sfbt_cat2amln_batch(sp, pixptr, gidx, ngal, gw, mode_n, mode_l, nb, nbar, ws->M.p, nmax, lmax, nmax_l, lmax_n,
+                                d_anlm.p, ws->main));
+    SFB_CUDA_OK(cudaMemcpyAsync(anlm_inout, d_anlm.p, (size_t)nlmsize * 2 * sizeof(double), cudaMemcpyDeviceToHost, ws->main));
+    SFB_CUDA_OK(cudaStreamSynchronize(ws->main));
+    g_times[0] = sp->t_total;
+    g_times[6] = sp->launches + 2;
     return 0;
 }
 

@@ -1410,6 +1410,52 @@ static int run_analysis(ShtPlan* p, const double* map, int64_t ldw, int accumula
                                  st);
 }
 
+// ring-Fourier coefficients G (d_FG) -> pixels: out[pixel][nrp] = residual ? map - f : f
+static int run_ring_synthesis(ShtPlan* p, const double* map, int64_t ldm, int residual, double* out, cudaStream_t st) {
+    RingTabs rt{p->d_nphi.p, p->d_start.p, p->d_shift.p, p->d_twoff.p, p->d_tw.p};
+    if (p->ntiles > 0) {
+        dim3 gr(p->ntiles, (unsigned)ceil_div(p->nrp, 64));
+        ring_synthesis_kernel<<<gr, kT, 0, st>>>(p->d_FG.p, rt, p->d_tile_ring.p, p->d_tile_j0.p, p->nrings,
+                                                 p->lmax, p->nr, p->nrp, map, ldm, residual, out);
+        SFB_CUDA_OK(cudaGetLastError());
+        p->launches++;
+    }
+    if (p->n_ctiles > 0) {
+        const int ni = pick_ni(p->nrp);
+        dim3 gc(p->n_ctiles, (unsigned)ceil_div(p->nrp, 16 * ni));
+#define SFB_LAUNCH_CS(NI_)                                                                                             \
+do {                                                                                                               \
+    constexpr int cs_bytes = cap_synthesis_smem_bytes<NI_>();                                                      \
+    SFB_CUDA_OK(cudaFuncSetAttribute(cap_synthesis_kernel<NI_>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                     cs_bytes));                                                                   \
+    cap_synthesis_kernel<NI_><<<gc, kT, cs_bytes, st>>>(p->d_FG.p, rt, p->d_ctile_ring.p, p->d_ctile_q0.p,         \
+                                                        p->nrings, p->lmax, p->nr, p->nrp, map, ldm, residual,     \
+                                                        out);                                             \
+} while (0)
+        if (ni == 4)
+            SFB_LAUNCH_CS(4);
+        else if (ni == 2)
+            SFB_LAUNCH_CS(2);
+        else
+            SFB_LAUNCH_CS(1);
+#undef SFB_LAUNCH_CS
+        SFB_CUDA_OK(cudaGetLastError());
+        p->launches++;
+    }
+    if (p->n_fft_rings > 0) {
+        const int n = 4 * p->nside, sch = p->fft_sch;
+        const int smem = n * sch * (int)sizeof(double2);
+        SFB_CUDA_OK(
+            cudaFuncSetAttribute(belt_synthesis_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        dim3 gf(p->n_fft_rings, (unsigned)ceil_div(p->nrp, 2 * sch));
+        belt_synthesis_fft_kernel<<<gf, kT, smem, st>>>(p->d_FG.p, rt, p->d_fft_rings.p, p->nrings, p->lmax, p->log2n,
+                                                        sch, p->nr, p->nrp, map, ldm, residual, out);
+        SFB_CUDA_OK(cudaGetLastError());
+        p->launches++;
+    }
+    return 0;
+}
+
 int sht_map2alm(ShtPlan* p, const double* d_win, int64_t ldw, int niter, double* d_alm, cudaStream_t st) {
     SFB_REQUIRE(p && d_win && d_alm, "sht_map2alm: null pointer");
     SFB_REQUIRE(ldw >= p->nr, "sht_map2alm: ld_win < nr");
@@ -1500,46 +1546,7 @@ int sht_map2alm(ShtPlan* p, const double* d_win, int64_t ldw, int niter, double*
     if (niter > 0) SFB_TRY(p->d_resid.alloc((size_t)p->npix * p->nrp));
     for (int it = 0; it < niter; ++it) {
         SFB_TRY(legendre_synthesis(false, p->nhalf));
-        if (p->ntiles > 0) {
-            dim3 gr(p->ntiles, (unsigned)ceil_div(p->nrp, 64));
-            ring_synthesis_kernel<<<gr, kT, 0, st>>>(p->d_FG.p, rt, p->d_tile_ring.p, p->d_tile_j0.p, p->nrings,
-                                                     p->lmax, p->nr, p->nrp, map, ldm, 1, p->d_resid.p);
-            SFB_CUDA_OK(cudaGetLastError());
-            p->launches++;
-        }
-        if (p->n_ctiles > 0) {
-            const int ni = pick_ni(p->nrp);
-            dim3 gc(p->n_ctiles, (unsigned)ceil_div(p->nrp, 16 * ni));
-#define SFB_LAUNCH_CS(NI_)                                                                                             \
-    do {                                                                                                               \
-        constexpr int cs_bytes = cap_synthesis_smem_bytes<NI_>();                                                      \
-        SFB_CUDA_OK(cudaFuncSetAttribute(cap_synthesis_kernel<NI_>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
-                                         cs_bytes));                                                                   \
-        cap_synthesis_kernel<NI_><<<gc, kT, cs_bytes, st>>>(p->d_FG.p, rt, p->d_ctile_ring.p, p->d_ctile_q0.p,         \
-                                                            p->nrings, p->lmax, p->nr, p->nrp, map, ldm, 1,            \
-                                                            p->d_resid.p);                                             \
-    } while (0)
-            if (ni == 4)
-                SFB_LAUNCH_CS(4);
-            else if (ni == 2)
-                SFB_LAUNCH_CS(2);
-            else
-                SFB_LAUNCH_CS(1);
-#undef SFB_LAUNCH_CS
-            SFB_CUDA_OK(cudaGetLastError());
-            p->launches++;
-        }
-        if (p->n_fft_rings > 0) {
-            const int n = 4 * p->nside, sch = p->fft_sch;
-            const int smem = n * sch * (int)sizeof(double2);
-            SFB_CUDA_OK(
-                cudaFuncSetAttribute(belt_synthesis_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            dim3 gf(p->n_fft_rings, (unsigned)ceil_div(p->nrp, 2 * sch));
-            belt_synthesis_fft_kernel<<<gf, kT, smem, st>>>(p->d_FG.p, rt, p->d_fft_rings.p, p->nrings, p->lmax, p->log2n,
-                                                            sch, p->nr, p->nrp, map, ldm, 1, p->d_resid.p);
-            SFB_CUDA_OK(cudaGetLastError());
-            p->launches++;
-        }
+        SFB_TRY(run_ring_synthesis(p, map, ldm, 1, p->d_resid.p, st));
         SFB_TRY(run_analysis(p, p->d_resid.p, p->nrp, 1, d_alm, st));
     }
     }
@@ -1552,6 +1559,25 @@ int sht_map2alm(ShtPlan* p, const double* d_win, int64_t ldw, int niter, double*
     p->tev1 = e1;
     p->pending = true;
     return p->async_times ? 0 : sht_resolve_times(p);
+}
+
+// alm2map for all shells of the plan: planar alm -> d_out[pixel][nrp] (Healpix.alm2map! per shell, src/cat2anlm.jl:415)
+int sht_alm2map(ShtPlan* p, const double* d_alm, double* d_out, cudaStream_t st) {
+    SFB_REQUIRE(p && d_alm && d_out, "sht_alm2map: null pointer");
+    const int nil = pick_ni(2 * p->nrp);
+    dim3 gs(p->lmax + 1, (unsigned)ceil_div(p->nhalf, 64), (unsigned)ceil_div(2 * p->nrp, 16 * nil));
+    if (nil == 4)
+        legendre_synthesis_kernel<4><<<gs, kT, 0, st>>>(d_alm, p->d_lam.p, p->nrings, p->nhalf, p->nhalf, p->lmax, p->nrp,
+                                                        p->d_FG.p, nullptr, p->d_nphi.p);
+    else if (nil == 2)
+        legendre_synthesis_kernel<2><<<gs, kT, 0, st>>>(d_alm, p->d_lam.p, p->nrings, p->nhalf, p->nhalf, p->lmax, p->nrp,
+                                                        p->d_FG.p, nullptr, p->d_nphi.p);
+    else
+        legendre_synthesis_kernel<1><<<gs, kT, 0, st>>>(d_alm, p->d_lam.p, p->nrings, p->nhalf, p->nhalf, p->lmax, p->nrp,
+                                                        p->d_FG.p, nullptr, p->d_nphi.p);
+    SFB_CUDA_OK(cudaGetLastError());
+    p->launches = 1;
+    return run_ring_synthesis(p, d_out, p->nrp, 0, d_out, st);
 }
 
 int sht_resolve_times(ShtPlan* p) {

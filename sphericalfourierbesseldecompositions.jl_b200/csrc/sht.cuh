@@ -53,6 +53,8 @@ void sht_plan_destroy(ShtPlan* p);
 // d_win: [pixel][shell], pixel stride ldw (>= nr).  d_alm: planar [lm (m-major)][re,im][nrp].
 int sht_map2alm(ShtPlan* p, const double* d_win, int64_t ldw, int niter, double* d_alm, cudaStream_t stream);
 int sht_resolve_times(ShtPlan* p);
+// alm2map of every shell: planar alm -> d_out[pixel][nrp] (RING order, nside of the plan)
+int sht_alm2map(ShtPlan* p, const double* d_alm, double* d_out, cudaStream_t stream);
 // planar -> ComplexF64 nr x lmsize (device), layout 0 = m-major, 1 = m-fast
 int sht_alm_to_complex(const ShtPlan* p, const double* d_alm, int layout, double* d_out, cudaStream_t stream);
 // the same conversion without a plan (multi-device runs assemble W_lm(r) from shards of several plans)
