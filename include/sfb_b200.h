@@ -177,6 +177,12 @@ int32_t sfb_calc_wr_lm_dev(sfb_sht_plan* plan, const double* d_win, int64_t ld_w
 int32_t sfb_alm_to_complex_dev(const sfb_sht_plan* plan, const double* d_alm, int32_t layout, double* d_out,
                                void* stream);
 
+/* planar W_lm(r) of all nr shells (nr rounded up to 8 per row) <- shell shards: shard g holds the shells
+ * [shell_bounds[g], shell_bounds[g+1]) as [lm][re,im][strides[g]] at shard_ptrs[g] (device pointers on the current device,
+ * e.g. slices of an all-gather receive buffer): the placement step of the shell-sharded stage 1 in one kernel          */
+int32_t sfb_alm_gather_shards_dev(const double* const* shard_ptrs, const int64_t* shell_bounds, const int64_t* strides,
+                                  int32_t nshards, int64_t LMAX, int64_t nr, double* d_alm, void* stream);
+
 int32_t sfb_cmix_plan_create(sfb_cmix_plan** plan, const int64_t* lnn, int64_t lnnsize, int64_t lnn_min,
                              const double* G, int64_t nr, int64_t nmax, int64_t lmax);
 int32_t sfb_cmix_plan_destroy(sfb_cmix_plan* plan);

@@ -50,6 +50,7 @@ SIGNATURES = {
     "sfb_sht_alm_doubles": (_i64, [_vp]),
     "sfb_calc_wr_lm_dev": (_i32, [_vp, _f64p, _i64, _i64, _f64p, _vp]),
     "sfb_alm_to_complex_dev": (_i32, [_vp, _f64p, _i32, _f64p, _vp]),
+    "sfb_alm_gather_shards_dev": (_i32, [_vp, _i64p, _i64p, _i32, _i64, _i64, _f64p, _vp]),
     "sfb_cmix_plan_create": (_i32, [C.POINTER(_vp), _i64p, _i64, _i64, _f64p, _i64, _i64, _i64]),
     "sfb_cmix_plan_destroy": (_i32, [_vp]),
     "sfb_power_win_mix_dev": (_i32, [_vp, _f64p, _f64p, _i32, _i32, _i64, _i64, _f64p, _i64, _vp]),

@@ -1089,6 +1089,29 @@ int32_t sfb_alm_to_complex_dev(const sfb_sht_plan* plan, const double* d_alm, in
     return sht_alm_to_complex(reinterpret_cast<const ShtPlan*>(plan), d_alm, layout, d_out, (cudaStream_t)stream);
 }
 
+// full planar W_lm(r) <- the shell shards of several ranks (all pointers on the current device, e.g. the receive buffer of
+// an NCCL all-gather): one placement kernel instead of a per-rank strided copy
+int32_t sfb_alm_gather_shards_dev(const double* const* shard_ptrs, const int64_t* shell_bounds, const int64_t* strides,
+                                  int32_t nshards, int64_t LMAX, int64_t nr, double* d_alm, void* stream) {
+    SFB_REQUIRE(shard_ptrs && shell_bounds && strides && d_alm && nshards >= 1 && nshards <= kMaxDev, "bad arguments");
+    PtrTable8 t;
+    t.n = 0;
+    for (int g = 0; g < nshards; ++g) {
+        if (shell_bounds[g + 1] <= shell_bounds[g]) continue;
+        SFB_REQUIRE(shard_ptrs[g], "null shard pointer");
+        t.p[t.n] = shard_ptrs[g];
+        t.bound[t.n] = shell_bounds[g];
+        t.stride[t.n] = (int)strides[g];
+        ++t.n;
+    }
+    SFB_REQUIRE(t.n >= 1 && shell_bounds[nshards] == nr, "shell bounds do not cover [0, nr)");
+    t.bound[t.n] = nr;
+    const long long rows = (LMAX + 1) * (LMAX + 2);   // lmsize * 2
+    alm_shard_gather_kernel<<<1024, 256, 0, (cudaStream_t)stream>>>(t, rows, (int)nr, (int)round_up(nr, 8), d_alm);
+    SFB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 int32_t sfb_cmix_plan_create(sfb_cmix_plan** plan, const int64_t* lnn, int64_t lnnsize, int64_t lnn_min,
                              const double* G, int64_t nr, int64_t nmax, int64_t lmax) {
     std::lock_guard<std::mutex> lk(g_mutex);
@@ -1233,8 +1256,9 @@ int32_t sfb_cmix_col_costs(const sfb_cmix_plan* plan, double* cost, int64_t n) {
         for (int l = 0; l <= p->lmax; ++l) {
             if (p->ell_ptr[l + 1] == p->ell_ptr[l]) continue;
             const double ap = 8.0 * ((p->a_of_ell[l] + 7) / 8);
+            // the Ŵ build (banded DMMA GEMM, L2-bound) runs ≈ 3x slower per flop than the block kernel (per-rank timings, cfg4)
             c += 2.0 * ap * p->nrp * p->nrp * b + 2.0 * ap * ap * p->nrp * b * (b + 1) / 2 +
-                 2.0 * p->nrp * p->nrp * (std::min(l, L) + 1);
+                 3.0 * 2.0 * p->nrp * p->nrp * (std::min(l, L) + 1);
         }
         for (int s = p->ell_ptr[L]; s < p->ell_ptr[L + 1]; ++s) cost[p->h_row_out[s]] = c / cols;
     }

@@ -143,13 +143,15 @@ class DevicePipeline:
         if nrp_mine != nrp_g:
             send = torch.nn.functional.pad(send.view(self.lmsize, 2, nrp_mine), (0, nrp_g - nrp_mine)).contiguous().view(-1)
         dist.all_gather_into_tensor(self._alm_recv, send, group=group)
-        nrp = self.alm.numel() // (self.lmsize * 2)
-        full = self.alm.view(self.lmsize, 2, nrp)
-        full.zero_()
-        recv = self._alm_recv.view(world, self.lmsize, 2, nrp_g)
-        for g, (l, h) in enumerate(ranges):
-            if h > l:
-                full[:, :, l:h] = recv[g, :, :, :h - l]
+        # placement of the shards into the planar [lm][re,im][nrp] buffer: one library kernel
+        if getattr(self, "_gather_args", None) is None:
+            per = self.lmsize * 2 * nrp_g
+            self._gather_args = ((C.c_void_p * world)(*[self._alm_recv.data_ptr() + 8 * g * per for g in range(world)]),
+                                 np.asarray([r[0] for r in ranges] + [self.nr], dtype=np.int64),
+                                 np.full(world, nrp_g, dtype=np.int64))
+        ptrs, bounds, strides = self._gather_args
+        _lib.check(self.lib.sfb_alm_gather_shards_dev(ptrs, _lib.ptr(bounds), _lib.ptr(strides), world, self.LMAX, self.nr,
+                                                      self.alm.data_ptr(), self._stream()))
         return self.alm
 
     # ---- stage 2+3 -----------------------------------------------------------------------------
