@@ -354,6 +354,7 @@ struct CmixArgs {
     int col_lo, col_hi;     // output columns [col_lo, col_hi) are written, relative to col_lo
     int div2Lp1, interchange;
     int mirror;             // 1: only blocks with L >= l are formed; each tile also fills M[(L,N,N'),(l,n,n')]
+    int gl_global;          // 1: G_L rows are read from global memory (L1/L2) instead of being staged: long radial grids
     int dbg;                // profiling aid (SFB_CMIX_DBG): 1 skip epilogue stores, 2 skip Z phase, 4 skip T-phase DMMA
 };
 
@@ -379,8 +380,11 @@ __global__ void __launch_bounds__(kCmixThreads, 2) cmix_block_kernel(CmixArgs p)
     const int r0 = p.ell_ptr[ell], nrows = p.ell_ptr[ell + 1] - r0;
 
     double* Gl = sm;                            // [AP][S]        G_ln[r]
-    double* GL = Gl + AP * S;                   // [nmax][S]      G_LN[r]
-    double* Zs = GL + p.nmax * S;               // [NC][AP][S]
+    double* GLs = Gl + AP * S;                  // [nmax][S]      G_LN[r]  (absent with gl_global)
+    const bool glg = p.gl_global != 0;
+    const double* GL = glg ? p.G + (size_t)L * p.nmax * nrp : GLs;
+    const int gS = glg ? nrp : S;               // row stride of GL
+    double* Zs = GLs + (glg ? 0 : p.nmax * S);  // [NC][AP][S]
     double* Zt = Zs + (size_t)p.NC * AP * S;    // [NC][AP][S] (only if !SYM)
     double* Ts = Zs + (size_t)NZ * p.NC * AP * S;  // [warps][NZ][AP][TLD]
     int* coltab = reinterpret_cast<int*>(Ts + kCmixWarps * NZ * AP * TLD);  // [NC][nmax] output column of (N, N') or -1
@@ -391,9 +395,9 @@ __global__ void __launch_bounds__(kCmixThreads, 2) cmix_block_kernel(CmixArgs p)
         const double* src = p.G + ((size_t)ell * p.nmax + n) * nrp;
         for (int r = lane; r < S; r += 32) Gl[n * S + r] = (n < a && r < nrp) ? src[r] : 0.0;
     }
-    for (int n = warp; n < b; n += kCmixWarps) {
+    for (int n = warp; n < b && !glg; n += kCmixWarps) {
         const double* src = p.G + ((size_t)L * p.nmax + n) * nrp;
-        for (int r = lane; r < S; r += 32) GL[n * S + r] = (r < nrp) ? src[r] : 0.0;
+        for (int r = lane; r < S; r += 32) GLs[n * S + r] = (r < nrp) ? src[r] : 0.0;
     }
     for (int x = tid; x < nrows; x += kCmixThreads) {
         rowtab[x] = p.row_out[r0 + x];
@@ -429,7 +433,7 @@ __global__ void __launch_bounds__(kCmixThreads, 2) cmix_block_kernel(CmixArgs p)
                     }
                 }
                 for (int Nloc = wn; Nloc < nN; Nloc += nlane) {
-                    const double* glN = GL + (N0 + Nloc) * S;
+                    const double* glN = GL + (N0 + Nloc) * gS;
                     double acc[AT][2][2];
 #pragma unroll
                     for (int i = 0; i < AT; ++i) acc[i][0][0] = acc[i][0][1] = acc[i][1][0] = acc[i][1][1] = 0.0;
@@ -457,7 +461,7 @@ __global__ void __launch_bounds__(kCmixThreads, 2) cmix_block_kernel(CmixArgs p)
                 }
             } else {
                 for (int Nloc = wn; Nloc < nN; Nloc += nlane) {
-                    const double* glN = GL + (N0 + Nloc) * S;
+                    const double* glN = GL + (N0 + Nloc) * gS;
                     double acc[AT][2][2], acct[AT][2][2];
 #pragma unroll
                     for (int i = 0; i < AT; ++i)
@@ -537,8 +541,8 @@ __global__ void __launch_bounds__(kCmixThreads, 2) cmix_block_kernel(CmixArgs p)
 #pragma unroll
                     for (int j = 0; j < (SYM ? 1 : AT); ++j) acc2[i][j][0] = acc2[i][j][1] = 0.0;
             }
-            const double* glA = GL + N2 * S;
-            const double* glB = GL + ((N2 + 1 < b) ? N2 + 1 : N2) * S;
+            const double* glA = GL + N2 * gS;
+            const double* glB = GL + ((N2 + 1 < b) ? N2 + 1 : N2) * gS;
 #pragma unroll 2
             for (int k0 = 0; k0 < ((p.dbg & 4) ? 4 : nrp); k0 += 4) {
                 double sc[P], zv[AT], gv[AT];
@@ -627,16 +631,16 @@ __global__ void __launch_bounds__(kCmixThreads, 2) cmix_block_kernel(CmixArgs p)
 }
 
 template <int AT, bool SYM>
-static size_t cmix_smem_bytes(int S, int nmax, int NC, int max_rows) {
+static size_t cmix_smem_bytes(int S, int nmax, int NC, int max_rows, bool glg) {
     const int AP = AT * 8, NZ = SYM ? 1 : 2;
-    return sizeof(double) * ((size_t)AP * S + (size_t)nmax * S + (size_t)NZ * NC * AP * S +
+    return sizeof(double) * ((size_t)AP * S + (glg ? 0 : (size_t)nmax * S) + (size_t)NZ * NC * AP * S +
                              (size_t)kCmixWarps * NZ * AP * cmix_tld(AP)) +
            sizeof(int) * (2 * (size_t)max_rows + (size_t)NC * nmax);
 }
 
 template <int AT, bool SYM>
 static int launch_cmix(const CmixArgs& args, int nchunks, int nells, int nmax, int max_rows, cudaStream_t stream) {
-    const size_t smem = cmix_smem_bytes<AT, SYM>(args.S, nmax, args.NC, max_rows);
+    const size_t smem = cmix_smem_bytes<AT, SYM>(args.S, nmax, args.NC, max_rows, args.gl_global != 0);
     SFB_REQUIRE(smem <= 227 * 1024, "cmix_block_kernel: shared memory footprint exceeds 227 KB (nr * nmax too large)");
     SFB_CUDA_OK(cudaFuncSetAttribute(cmix_block_kernel<AT, SYM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(nchunks, nells);
@@ -660,18 +664,25 @@ static int launch_cmix_at(int AT, const CmixArgs& args, int nchunks, int nells, 
 }
 
 // number of N values whose Z fits next to the fixed buffers in ~110 KB of shared memory (two CTAs per SM)
-static int cmix_chunk_size_for(size_t budget, int AT, bool sym, int S, int nmax, int max_rows) {
+static int cmix_chunk_size_for(size_t budget, int AT, bool sym, int S, int nmax, int max_rows, bool glg = false) {
     const int AP = AT * 8, NZ = sym ? 1 : 2;
-    const size_t fixed = sizeof(double) * ((size_t)AP * S + (size_t)nmax * S + (size_t)kCmixWarps * NZ * AP * cmix_tld(AP)) +
+    const size_t fixed = sizeof(double) * ((size_t)AP * S + (glg ? 0 : (size_t)nmax * S) +
+                                           (size_t)kCmixWarps * NZ * AP * cmix_tld(AP)) +
                          sizeof(int) * 2 * (size_t)max_rows;
     const size_t per = sizeof(double) * (size_t)NZ * AP * S + sizeof(int) * (size_t)nmax;
     if (fixed + per > budget) return 0;
     return (int)std::min<size_t>(nmax, (budget - fixed) / per);
 }
-static int cmix_chunk_size(int AT, bool sym, int S, int nmax, int max_rows) {
-    // prefer two CTAs per SM (~110 KB each); long radial grids need the whole 220 KB for one CTA
-    const int nc = cmix_chunk_size_for(110 * 1024, AT, sym, S, nmax, max_rows);
-    return nc >= 1 ? nc : cmix_chunk_size_for(220 * 1024, AT, sym, S, nmax, max_rows);
+static int cmix_chunk_size(int AT, bool sym, int S, int nmax, int max_rows, bool* glg) {
+    // prefer two CTAs per SM (~110 KB each); long radial grids need the whole 220 KB for one CTA, and beyond that the
+    // G_L rows stay in global memory (e.g. cfg4's modes on the reference's recommended nr = 8(n+N) = 384 grid)
+    *glg = false;
+    int nc = cmix_chunk_size_for(110 * 1024, AT, sym, S, nmax, max_rows);
+    if (nc >= 1) return nc;
+    nc = cmix_chunk_size_for(220 * 1024, AT, sym, S, nmax, max_rows);
+    if (nc >= 1) return nc;
+    *glg = true;
+    return cmix_chunk_size_for(220 * 1024, AT, sym, S, nmax, max_rows, true);
 }
 
 // =============================================================================================
@@ -744,12 +755,7 @@ int cmix_plan_create(CmixPlan** out, const int64_t* lnn, int64_t lnnsize, int64_
         }
     }
     p->nl = (int)nl_L.size();
-    p->amax_tiles = (amax + 7) / 8;
-    if (p->amax_tiles > 4) {
-        delete p;
-        set_error("cmix_plan_create: nmax_l > 32 is not supported by this build");
-        return 2;
-    }
+    p->amax_tiles = (amax + 7) / 8;   // > 4 (nmax_l > 32): only the tiled block kernels are unavailable (checked in cmix_run)
 
     // --- G: [nr][nmax][lmax+1] column-major -> [ell][n][nrp], NaN / padding -> 0 where unused ---
     std::vector<double> Gh((size_t)(lmax + 1) * nmax * p->nrp, 0.0);
@@ -833,6 +839,8 @@ int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp
     SFB_REQUIRE(0 <= row_lo && row_lo <= row_hi && row_hi <= p->nout, "cmix_run: bad row range");
     SFB_REQUIRE(0 <= col_lo && col_lo <= col_hi && col_hi <= p->nout, "cmix_run: bad column range");
     SFB_REQUIRE(ldM >= row_hi - row_lo, "cmix_run: ldM smaller than the row shard");
+    SFB_REQUIRE(p->amax_tiles <= 4, "power_win_mix (dense window): nmax_l > 32 is not supported by the tiled block kernels of "
+                                    "this build (the separable-window path and win_lnn are)");
     p->t_wl = p->t_what = p->t_block = 0;
     p->flops_executed = 0;
     p->launches = 0;
@@ -931,6 +939,7 @@ int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp
     args.col_lo = (int)col_lo;
     args.col_hi = (int)col_hi;
     args.mirror = mirror ? 1 : 0;
+    args.gl_global = 0;
     args.dbg = getenv("SFB_CMIX_DBG") ? atoi(getenv("SFB_CMIX_DBG")) : 0;
 
     double flops = 0.0;
@@ -999,8 +1008,11 @@ int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp
             int max_rows = 0;
             for (int l : ells) max_rows = std::max(max_rows, p->ell_ptr[l + 1] - p->ell_ptr[l]);
             // chunk list (L, N0, N1) for this tile class
-            const int NC = cmix_chunk_size(AT, sym, p->S, p->nmax, max_rows);
-            SFB_REQUIRE(NC >= 1, "cmix: nr * nmax too large for the shared-memory tiling of this build");
+            bool glg = false;
+            const int NC = cmix_chunk_size(AT, sym, p->S, p->nmax, max_rows, &glg);
+            SFB_REQUIRE(NC >= 1, "cmix: nr too large for the shared-memory tiling of this build (nr * 8 * ceil(nmax_l/8) "
+                                 "doubles must fit twice in 220 KB)");
+            args.gl_global = glg ? 1 : 0;
             std::vector<int> chL, chN0, chN1;
             for (int L = 0; L <= lmax; ++L)
                 for (int n0 = 0; L_used[L] && n0 < p->a_of_ell[L]; n0 += NC) {

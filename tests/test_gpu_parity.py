@@ -121,7 +121,9 @@ def test_cmix_from_wrlm_matches_oracle(kw):
 
 # every tile class of the block kernels: nmax_l = 5 / 12 / 20 / 26 / 32 (1..4 row tiles of 8), 24 / 40 / 64 shells
 # (register-Z kernel with 4 or 8 radial tiles) and 72 shells (shared-memory-Z kernel), dense lnn tables
-@pytest.mark.parametrize("nmax,lmax,nr", [(5, 3, 24), (12, 3, 40), (20, 2, 64), (26, 2, 40), (32, 1, 64), (26, 1, 72)])
+# (20, 1, 400): long radial grid (the reference's recommended nr >= 8(n+N)): G_L rows stay in global memory
+@pytest.mark.parametrize("nmax,lmax,nr", [(5, 3, 24), (12, 3, 40), (20, 2, 64), (26, 2, 40), (32, 1, 64), (26, 1, 72),
+                                          (20, 1, 400), (9, 2, 200)])
 @pytest.mark.parametrize("kw", [dict(), dict(div2Lp1=True, interchange_NN=True)])
 def test_cmix_tile_classes(nmax, lmax, nr, kw):
     import warnings
@@ -324,3 +326,22 @@ def test_stage1_ring_space_variants(monkeypatch, flag, nside, lmax, nr):
     if ref is not None:
         assert relerr(base, ref) < RTOL and relerr(got, ref) < RTOL
     assert relerr(got, base) < 1e-12
+
+
+def test_nmax_l_above_32_separable_and_win_lnn_still_work():
+    """tables with nmax_l > 32 are only unsupported by the tiled dense-window kernels; the separable-window
+    coupling matrix and win_lnn go through the same plan and must work (the dense call fails with a clear message)."""
+    import warnings
+    from sfb_b200 import _lib
+    sfb, oa, a, owm, wm, oc, c, rng = _setup(nmax=34, lmax=1, nr=40, dnmax=None)
+    assert max(oa.nmax_l) == 34
+    win, phi, mask = _random_window(rng, owm)
+    swin = sfb.SeparableArray(phi, mask)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        M = sfb.power_win_mix(swin, swin, wm, c)
+        ref = ow.power_win_mix(swin.dense(), swin.dense(), owm, oc)
+        assert relerr(M, ref) < RTOL
+        assert relerr(sfb.win_lnn(swin.dense(), wm, c), ow.win_lnn(swin.dense(), owm, oc)) < RTOL
+        with pytest.raises(_lib.SFBError, match="nmax_l > 32"):
+            sfb.power_win_mix(swin.dense(), wm, c)
