@@ -109,6 +109,21 @@ int32_t sfb_power_win_mix_binned(const double* win1, int64_t nr, int64_t npix_in
                                  const int64_t* v_rowval, const double* v_nzval, int64_t LNN2, int32_t div2Lp1,
                                  int32_t interchange_NN, double* N_out);
 
+/* On-device window deconvolution.  The reference finishes on the host with
+ *   C = bcmix \ (w̃mat * Cobs)   (docs/src/tutorial_catalog.md:93-97)   and   wmat = inv(Nmix) * w̃M   (test/test_windows.jl:583-584);
+ * Julia's `\` on a square matrix is an LU factorisation with partial pivoting.  Here the same factorisation runs on the
+ * device (blocked LU, trailing updates on DMMA), so only LNN x nrhs numbers cross PCIe instead of the matrix.
+ *   sfb_solve: X = N \ B for host arrays N (n x n) and B (n x nrhs), column-major.
+ *   sfb_power_win_mix_binned_solve: N = w̃ M v exactly as sfb_power_win_mix_binned, kept on the device, then X = N \ B
+ *     (B: LNN x nrhs); N_out (LNN x LNN) is filled too unless NULL.  A singular matrix is an error (SingularException). */
+int32_t sfb_solve(const double* N, int64_t n, const double* B, int64_t nrhs, double* X_out);
+int32_t sfb_power_win_mix_binned_solve(const double* win1, int64_t nr, int64_t npix_in, int64_t ld_win, int64_t nside,
+                                       const double* G, int64_t nmax, int64_t lmax, const int64_t* lnn, int64_t lnnsize,
+                                       const int64_t* wt_colptr, const int64_t* wt_rowval, const double* wt_nzval,
+                                       int64_t LNN1, const int64_t* v_colptr, const int64_t* v_rowval,
+                                       const double* v_nzval, int64_t LNN2, int32_t div2Lp1, int32_t interchange_NN,
+                                       const double* B, int64_t nrhs, double* X_out, double* N_out);
+
 /* win_lnn(win, wmodes, cmodes) (src/windows.jl:382-391, calc_intr_gg_fn :394-418): the shot-noise
  * window W_lnn' = sum_r r^2 dr g_nl(r) g_n'l(r) Wr_00(r)/sqrt(4 pi), with Wr_00 = calc_Wr_lm(win, 2 lmax, nside)[:,1]
  * ("need to be consistent", :386).  G = rsdrgnlr as for power_win_mix; Wlnn_out has lnnsize entries.  A negative

@@ -17,12 +17,12 @@ from .modes import (AnlmModes, ClnnBinnedModes, ClnnModes, bandpower_binning_wei
 from .separable import SeparableArray
 from .cat2anlm import amln2clnn, anlm2field, cat2amln, field2anlm, win_rhat_ln
 from .windows import (ConfigurationSpaceModes, calc_Wr_lm, calc_wmix, calc_wmix_all, check_nsamp, get_devices, optimize_Wr_lm_layout, pinned_empty,
-                      power_win_mix, power_win_mix_from_wrlm, precompute_gnlr, rsdrgnlr, set_devices, win_lnn, window_r)
+                      power_win_mix, power_win_mix_from_wrlm, power_win_mix_solve, solve, precompute_gnlr, rsdrgnlr, set_devices, win_lnn, window_r)
 
 __all__ = [
     "AnlmModes", "ClnnModes", "ClnnBinnedModes", "bandpower_binning_weights", "estimate_nside", "getidx", "getlkk",
     "getlmsize", "getlnn", "getlnnsize", "getnlm", "getnlmsize", "SeparableArray", "ConfigurationSpaceModes",
     "calc_Wr_lm", "check_nsamp", "optimize_Wr_lm_layout", "power_win_mix", "power_win_mix_from_wrlm",
     "precompute_gnlr", "rsdrgnlr", "win_lnn", "window_r", "set_devices", "get_devices", "pinned_empty", "calc_wmix", "calc_wmix_all",
-    "field2anlm", "anlm2field", "win_rhat_ln", "cat2amln", "amln2clnn",
+    "solve", "power_win_mix_solve", "field2anlm", "anlm2field", "win_rhat_ln", "cat2amln", "amln2clnn",
 ]

@@ -37,6 +37,10 @@ SIGNATURES = {
                                         _i64p, _i64p, _f64p, _i64, _i64p, _i64p, _f64p, _i64, _i32, _i32, _f64p]),
     "sfb_power_win_mix_separable": (_i32, [_f64p, _f64p, _i64, _i64, _i64, _f64p, _i64, _i64, _i64p, _i64,
                                            _i64p, _i64p, _f64p, _i64, _i64p, _i64p, _f64p, _i64, _i32, _i32, _f64p]),
+    "sfb_solve": (_i32, [_f64p, _i64, _f64p, _i64, _f64p]),
+    "sfb_power_win_mix_binned_solve": (_i32, [_f64p, _i64, _i64, _i64, _i64, _f64p, _i64, _i64, _i64p, _i64,
+                                              _i64p, _i64p, _f64p, _i64, _i64p, _i64p, _f64p, _i64, _i32, _i32,
+                                              _f64p, _i64, _f64p, _f64p]),
     "sfb_win_lnn": (_i32, [_f64p, _i64, _i64, _i64, _i64, _f64p, _i64, _i64, _i64p, _i64, _f64p]),
     "sfb_calc_wmix": (_i32, [_f64p, _i64, _i64, _i64, _i64, _f64p, _i64, _i64, _i64p, _i64p, _i32, _f64p]),
     "sfb_field2anlm": (_i32, [_f64p, _i64, _i64, _i64, _f64p, _i64, _i64, _i64p, _i64p, _f64p]),

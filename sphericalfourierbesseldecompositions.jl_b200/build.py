@@ -7,7 +7,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["capi.cu", "cmix.cu", "cmix_regz.cu", "sht.cu", "binned.cu", "wmix.cu", "sfbt.cu"]
+SOURCES = ["capi.cu", "cmix.cu", "cmix_regz.cu", "sht.cu", "binned.cu", "wmix.cu", "sfbt.cu", "lusolve.cu"]
 OUT = os.path.join(HERE, "libsfb_b200.so")
 
 

@@ -10,7 +10,7 @@ namespace sfb {
 __global__ void binned_product_kernel(const double* __restrict__ M, long long n, const int* __restrict__ wptr,
                                       const int* __restrict__ wcol, const double* __restrict__ wval, int LNN1,
                                       const int* __restrict__ vptr, const int* __restrict__ vrow,
-                                      const double* __restrict__ vval, int LNN2, double* __restrict__ N) {
+                                      const double* __restrict__ vval, int LNN2, double* __restrict__ N, long long ldN) {
     const int I = blockIdx.x * blockDim.x + threadIdx.x;
     const int m = blockIdx.y;
     if (I >= LNN1) return;
@@ -28,13 +28,22 @@ __global__ void binned_product_kernel(const double* __restrict__ M, long long n,
             c += wv * vv * M[i + ip * n];
         }
     }
-    N[I + (size_t)m * LNN1] = c;
+    N[I + (size_t)m * ldN] = c;
 }
 
 __global__ void nonfinite_flag_kernel(const double* __restrict__ x, size_t n, int* flag) {
     int bad = 0;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         bad |= !isfinite(x[i]);
+    if (bad) atomicOr(flag, 1);
+}
+
+__global__ void nonfinite_flag_2d_kernel(const double* __restrict__ x, long long rows, long long cols, long long ld,
+                                         int* flag) {
+    int bad = 0;
+    const long long n = rows * cols;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        bad |= !isfinite(x[(i % rows) + (i / rows) * ld]);
     if (bad) atomicOr(flag, 1);
 }
 
@@ -49,8 +58,30 @@ int binned_product_to_host(const double* d_M, int64_t n, const int64_t* wt_colpt
         if (ms) *ms = 0;
         return 0;
     }
+    DevBuf<double> d_N;
+    SFB_TRY(d_N.alloc((size_t)LNN1 * LNN2));
+    SFB_TRY(binned_product_device(d_M, n, wt_colptr, wt_rowval, wt_nzval, LNN1, v_colptr, v_rowval, v_nzval, LNN2, d_N.p,
+                                  LNN1, ms));
+    SFB_CUDA_OK(cudaMemcpy(N_out, d_N.p, (size_t)LNN1 * LNN2 * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// N = w̃ M v left on the device: d_N is LNN1 x LNN2 column-major with leading dimension ldN (the non-finite check of
+// src/windows.jl:1013 included).  w̃ = v = I copies M.
+int binned_product_device(const double* d_M, int64_t n, const int64_t* wt_colptr, const int64_t* wt_rowval,
+                          const double* wt_nzval, int64_t LNN1, const int64_t* v_colptr, const int64_t* v_rowval,
+                          const double* v_nzval, int64_t LNN2, double* d_Nout, int64_t ldN, float* ms) {
+    SFB_REQUIRE(d_M && d_Nout && ldN >= LNN1, "binned_product: bad arguments");
+    if (!wt_colptr) SFB_REQUIRE(LNN1 == n, "w̃ = I requires LNN1 == lnnsize");
+    if (!v_colptr) SFB_REQUIRE(LNN2 == n, "v = I requires LNN2 == lnnsize");
+    if (!wt_colptr && !v_colptr) {
+        SFB_CUDA_OK(cudaMemcpy2D(d_Nout, ldN * sizeof(double), d_M, n * sizeof(double), n * sizeof(double), (size_t)n,
+                                 cudaMemcpyDeviceToDevice));
+        if (ms) *ms = 0;
+        return 0;
+    }
     DevBuf<int> d_wptr, d_wcol, d_vptr, d_vrow;
-    DevBuf<double> d_wval, d_vval, d_N;
+    DevBuf<double> d_wval, d_vval;
     if (wt_colptr) {
         // CSC (columns i) -> CSR (rows I), keeping ascending i within a row like the reference's nzind order
         SFB_REQUIRE(wt_rowval && wt_nzval, "w̃: null rowval/nzval");
@@ -93,7 +124,6 @@ int binned_product_to_host(const double* d_M, int64_t n, const int64_t* wt_colpt
         SFB_CUDA_OK(cudaMemcpy(d_vrow.p, row.data(), row.size() * sizeof(int), cudaMemcpyHostToDevice));
         SFB_CUDA_OK(cudaMemcpy(d_vval.p, v_nzval, nnz * sizeof(double), cudaMemcpyHostToDevice));
     }
-    SFB_TRY(d_N.alloc((size_t)LNN1 * LNN2));
     cudaEvent_t e0, e1;
     SFB_CUDA_OK(cudaEventCreate(&e0));
     SFB_CUDA_OK(cudaEventCreate(&e1));
@@ -104,7 +134,7 @@ int binned_product_to_host(const double* d_M, int64_t n, const int64_t* wt_colpt
         const int64_t mc = std::min<int64_t>(65535, LNN2 - m0);
         binned_product_kernel<<<dim3((unsigned)ceil_div(LNN1, 128), (unsigned)mc), 128>>>(
             d_M, n, wt_colptr ? d_wptr.p : nullptr, d_wcol.p, d_wval.p, (int)LNN1,
-            v_colptr ? d_vptr.p + m0 : nullptr, d_vrow.p, d_vval.p, (int)LNN2, d_N.p + (size_t)m0 * LNN1);
+            v_colptr ? d_vptr.p + m0 : nullptr, d_vrow.p, d_vval.p, (int)LNN2, d_Nout + (size_t)m0 * ldN, ldN);
         SFB_CUDA_OK(cudaGetLastError());
         SFB_REQUIRE(v_colptr || m0 == 0, "v = I with LNN2 > 65535 is not supported");
     }
@@ -115,18 +145,17 @@ int binned_product_to_host(const double* d_M, int64_t n, const int64_t* wt_colpt
     if (ms) *ms = t;
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    {  // @assert all(isfinite.(mix))  src/windows.jl:1013 — checked on the device before the copy back
+    {  // @assert all(isfinite.(mix))  src/windows.jl:1013 — checked on the device
         DevBuf<int> flag;
         SFB_TRY(flag.alloc(1));
         SFB_CUDA_OK(cudaMemset(flag.p, 0, sizeof(int)));
-        nonfinite_flag_kernel<<<512, 256>>>(d_N.p, (size_t)LNN1 * LNN2, flag.p);
+        nonfinite_flag_2d_kernel<<<512, 256>>>(d_Nout, LNN1, LNN2, ldN, flag.p);
         int h = 0;
         SFB_CUDA_OK(cudaMemcpy(&h, flag.p, sizeof(int), cudaMemcpyDeviceToHost));
         if (h) {
             set_error("AssertionError: all(isfinite.(mix))");
             return 4;
         }
-        SFB_CUDA_OK(cudaMemcpy(N_out, d_N.p, (size_t)LNN1 * LNN2 * sizeof(double), cudaMemcpyDeviceToHost));
     }
     return 0;
 }

@@ -18,6 +18,10 @@ int binned_product_to_host(const double* d_M, int64_t n, const int64_t* wt_colpt
                            const double* wt_nzval, int64_t LNN1, const int64_t* v_colptr, const int64_t* v_rowval,
                            const double* v_nzval, int64_t LNN2, double* N_out, float* ms);
 
+int binned_product_device(const double* d_M, int64_t n, const int64_t* wt_colptr, const int64_t* wt_rowval,
+                          const double* wt_nzval, int64_t LNN1, const int64_t* v_colptr, const int64_t* v_rowval,
+                          const double* v_nzval, int64_t LNN2, double* d_N, int64_t ldN, float* ms);
+
 // Coupling matrix of a separable window W(r, n̂) = phi(r) mask(n̂): d_wlm planar alm of the mask (1 shell,
 // padded to nrp_s), phi host vector of length nr.  Writes the full nout x nout matrix to d_M.
 int separable_cmix(CmixPlan* p, const double* d_wlm, int nrp_s, const double* phi, int div2Lp1, int interchange,

@@ -4,6 +4,7 @@
 #include "binned.cuh"
 #include "cmix.cuh"
 #include "common.cuh"
+#include "lusolve.cuh"
 #include "sfbt.cuh"
 #include "sht.cuh"
 #include "wmix.cuh"
@@ -859,6 +860,62 @@ int32_t sfb_power_win_mix_binned(const double* win1, int64_t nr, int64_t npix_in
                                    N_out, &t_bin));
     g_times[7] = t_bin;
     tr.mark("binned: w~ M v + D2H");
+    return 0;
+}
+
+// ---- on-device deconvolution ----
+int32_t sfb_solve(const double* N, int64_t n, const double* B, int64_t nrhs, double* X_out) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    SFB_REQUIRE(N && B && X_out && n >= 1 && nrhs >= 1, "sfb_solve: bad arguments");
+    Workspace* ws = nullptr;
+    SFB_TRY(get_ws(&ws));
+    DevBuf<double> A;
+    SFB_TRY(A.alloc((size_t)n * (n + nrhs)));
+    SFB_CUDA_OK(cudaMemcpyAsync(A.p, N, (size_t)n * n * sizeof(double), cudaMemcpyHostToDevice, ws->main));
+    SFB_CUDA_OK(cudaMemcpyAsync(A.p + (size_t)n * n, B, (size_t)n * nrhs * sizeof(double), cudaMemcpyHostToDevice, ws->main));
+    int info = 0;
+    SFB_TRY(lu_solve_inplace(A.p, n, n, nrhs, &info, ws->main));
+    SFB_TRY(check_finite(A.p + (size_t)n * n, (size_t)n * nrhs, "solution"));
+    SFB_CUDA_OK(cudaMemcpy(X_out, A.p + (size_t)n * n, (size_t)n * nrhs * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int32_t sfb_power_win_mix_binned_solve(const double* win1, int64_t nr, int64_t npix_in, int64_t ld_win, int64_t nside,
+                                       const double* G, int64_t nmax, int64_t lmax, const int64_t* lnn, int64_t lnnsize,
+                                       const int64_t* wt_colptr, const int64_t* wt_rowval, const double* wt_nzval,
+                                       int64_t LNN1, const int64_t* v_colptr, const int64_t* v_rowval,
+                                       const double* v_nzval, int64_t LNN2, int32_t div2Lp1, int32_t interchange_NN,
+                                       const double* B, int64_t nrhs, double* X_out, double* N_out) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    SFB_REQUIRE(win1 && B && X_out && nrhs >= 1, "null pointer");
+    SFB_REQUIRE(LNN1 == LNN2, "the binned coupling matrix must be square to be inverted");
+    Trace tr;
+    PlanGuard pg;
+    SFB_TRY(get_cmix_plan(&pg.p, lnn, lnnsize, 1, G, nr, nmax, lmax));
+    Workspace* ws = nullptr;
+    SFB_TRY(get_ws(&ws));
+    bool same = true;
+    SFB_TRY(windows_to_alm(*ws, win1, nullptr, nr, npix_in, ld_win, nside, 2 * lmax, &same));
+    const int64_t n = pg.p->nout, L = LNN1;
+    SFB_TRY(ws->M.alloc((size_t)n * n));
+    SFB_TRY(cmix_run(pg.p, ws->alm1.p, ws->alm1.p, div2Lp1, interchange_NN, 0, n, 0, n, ws->M.p, n, 0, nullptr, 0, false,
+                     mirror_enabled()));
+    record_cmix_times(pg.p);
+    tr.mark("solve: stage 1-3");
+    DevBuf<double> A;                         // [N | B], L x (L + nrhs)
+    SFB_TRY(A.alloc((size_t)L * (L + nrhs)));
+    float t_bin = 0;
+    SFB_TRY(binned_product_device(ws->M.p, n, wt_colptr, wt_rowval, wt_nzval, LNN1, v_colptr, v_rowval, v_nzval, LNN2, A.p, L,
+                                  &t_bin));
+    g_times[7] = t_bin;
+    if (N_out) SFB_CUDA_OK(cudaMemcpy(N_out, A.p, (size_t)L * L * sizeof(double), cudaMemcpyDeviceToHost));
+    SFB_CUDA_OK(cudaMemcpy(A.p + (size_t)L * L, B, (size_t)L * nrhs * sizeof(double), cudaMemcpyHostToDevice));
+    tr.mark("solve: N = w~ M v");
+    int info = 0;
+    SFB_TRY(lu_solve_inplace(A.p, L, L, nrhs, &info, 0));
+    SFB_TRY(check_finite(A.p + (size_t)L * L, (size_t)L * nrhs, "solution"));
+    SFB_CUDA_OK(cudaMemcpy(X_out, A.p + (size_t)L * L, (size_t)L * nrhs * sizeof(double), cudaMemcpyDeviceToHost));
+    tr.mark("solve: LU + substitution + D2H");
     return 0;
 }
 

@@ -29,7 +29,7 @@ from .separable import SeparableArray
 
 __all__ = ["ConfigurationSpaceModes", "window_r", "calc_Wr_lm", "optimize_Wr_lm_layout", "precompute_gnlr",
            "check_nsamp", "power_win_mix", "rsdrgnlr", "set_devices", "get_devices", "pinned_empty", "calc_wmix",
-           "calc_wmix_all"]
+           "calc_wmix_all", "solve", "power_win_mix_solve"]
 
 LAYOUT_MMAJOR, LAYOUT_MFAST = 0, 1
 
@@ -277,6 +277,49 @@ def _power_win_mix_binned(win1, win2, wt, v, wmodes, bcmodes, div2Lp1, interchan
         _lib.check(lib.sfb_power_win_mix_binned(_lib.ptr(w1), w1.shape[0], w1.shape[1], w1.shape[0], amodes.nside,
                                                 *common))
     return N
+
+
+def solve(N, B):
+    """X = N \\ B on the device (LU with partial pivoting, like Julia's `\\` for a square matrix): the deconvolution step
+    `bcmix \\ (w̃mat * Cobs)` of docs/src/tutorial_catalog.md:93-97."""
+    lib = _lib.load()
+    N = np.asfortranarray(N, dtype=np.float64)
+    if N.ndim != 2 or N.shape[0] != N.shape[1]:
+        raise ValueError("N must be square")
+    B = np.asarray(B, dtype=np.float64)
+    vec = B.ndim == 1
+    B2 = np.asfortranarray(B.reshape(N.shape[0], -1))
+    X = np.empty_like(B2, order="F")
+    _lib.check(lib.sfb_solve(_lib.ptr(N), N.shape[0], _lib.ptr(B2), B2.shape[1], _lib.ptr(X)))
+    return X[:, 0] if vec else X
+
+
+def power_win_mix_solve(win, wt, v, wmodes, bcmodes, B, div2Lp1=False, interchange_NN=False, return_N=False):
+    """`power_win_mix(win, w̃, v, wmodes, bcmodes) \\ B` without bringing the binned coupling matrix to the host
+    (docs/src/tutorial_catalog.md:93-97, test/test_windows.jl:583-584).  B: LNN or LNN x nrhs.  Not in the reference as
+    one call; returns X (and N with return_N)."""
+    lib = _lib.load()
+    cmodes = bcmodes.cmodes
+    amodes, G, lnn = _mode_tables(cmodes, wmodes)
+    lnnsize = lnn.shape[1]
+    wc, wr, wv, LNN1, _ = _csc_args(wt, n_cols_expected=lnnsize)
+    vc, vr, vv, _, LNN2 = _csc_args(v, n_rows_expected=lnnsize)
+    LNN1 = lnnsize if LNN1 is None else LNN1
+    LNN2 = lnnsize if LNN2 is None else LNN2
+    if LNN1 != LNN2:
+        raise ValueError("the binned coupling matrix must be square")
+    B = np.asarray(B, dtype=np.float64)
+    vec = B.ndim == 1
+    B2 = np.asfortranarray(B.reshape(LNN1, -1))
+    X = np.empty_like(B2, order="F")
+    N = np.empty((LNN1, LNN2), order="F") if return_N else None
+    w1 = _as_julia_matrix(win)
+    _lib.check(lib.sfb_power_win_mix_binned_solve(
+        _lib.ptr(w1), w1.shape[0], w1.shape[1], w1.shape[0], amodes.nside, _lib.ptr(G), amodes.nmax, amodes.lmax,
+        _lib.ptr(lnn), lnnsize, _lib.ptr(wc), _lib.ptr(wr), _lib.ptr(wv), LNN1, _lib.ptr(vc), _lib.ptr(vr), _lib.ptr(vv),
+        LNN2, int(bool(div2Lp1)), int(bool(interchange_NN)), _lib.ptr(B2), B2.shape[1], _lib.ptr(X), _lib.ptr(N)))
+    X = X[:, 0] if vec else X
+    return (X, N) if return_N else X
 
 
 def win_lnn(win, wmodes, cmodes):
