@@ -6,7 +6,8 @@
 // so that only the band powers (LNN x nrhs) cross PCIe instead of the matrix.
 //
 // Blocked right-looking LU with partial pivoting on the augmented matrix [N | B] (column-major, in place), block size 64:
-//   panel      one CTA per panel: pivot search (block reduction), row swap inside the panel, scaling, rank-1 updates
+//   panel      one CTA per 8-column sub-panel: pivot search (block reduction), row swap inside it, scaling, rank-1 updates;
+//              the other columns of the 64-column panel are updated by the parallel kernels below (two-level blocking)
 //   swap       the panel's row interchanges applied to all other columns (left of the panel and right of it, B included)
 //   trsm_l     U12 = L11^{-1} A12 (unit lower 64 x 64 in shared memory, one thread per column)
 //   gemm       A22 -= L21 U12: the O(n³) part, FP64 tensor cores (DMMA), 64 x 64 tiles, K = 64
@@ -227,11 +228,31 @@ int lu_solve_inplace(double* d_A, int64_t lda, int64_t n, int64_t nrhs, int* inf
     SFB_TRY(d_info.alloc(1));
     SFB_CUDA_OK(cudaMemsetAsync(d_info.p, 0, sizeof(int), st));
     const int N = (int)n, NC = (int)(n + nrhs);
+    // two-level blocking: the 64-column outer panel is factored in sub-panels of kNBi columns by the single-CTA kernel (whose
+    // traffic is what one SM can pull from L2), the rest of the outer panel is updated by the parallel kernels; the O(n³)
+    // trailing update outside the panel then runs with K = 64.
+    constexpr int kNBi = 8;
     for (int k0 = 0; k0 < N; k0 += kNB) {
         const int nb = std::min(kNB, N - k0);
-        lu_panel_kernel<<<1, 1024, 0, st>>>(d_A, lda, N, k0, nb, d_piv.p, d_info.p);
+        const int pend = k0 + nb;                                  // end of the outer panel
+        for (int i0 = k0; i0 < pend; i0 += kNBi) {
+            const int ib = std::min(kNBi, pend - i0);
+            lu_panel_kernel<<<1, 1024, 0, st>>>(d_A, lda, N, i0, ib, d_piv.p, d_info.p);
+            // interchanges + updates on the other columns of the outer panel
+            if (i0 > k0) lu_swap_kernel<<<(unsigned)ceil_div(i0 - k0, 64), 64, 0, st>>>(d_A, lda, d_piv.p, i0, ib, k0, i0);
+            const int c1 = i0 + ib;
+            if (c1 < pend) {
+                lu_swap_kernel<<<(unsigned)ceil_div(pend - c1, 64), 64, 0, st>>>(d_A, lda, d_piv.p, i0, ib, c1, pend);
+                lu_trsm_lower_kernel<<<(unsigned)ceil_div(pend - c1, 128), 128, 0, st>>>(d_A, lda, i0, ib, c1, pend);
+                const int m = N - c1;
+                if (m > 0)
+                    lu_gemm_kernel<<<dim3((unsigned)ceil_div(m, 64), (unsigned)ceil_div(pend - c1, 64)), 256, 0, st>>>(
+                        d_A + c1 + (size_t)i0 * lda, lda, d_A + i0 + (size_t)c1 * lda, lda, d_A + c1 + (size_t)c1 * lda, lda, m,
+                        pend - c1, ib);
+            }
+        }
         if (k0 > 0) lu_swap_kernel<<<(unsigned)ceil_div(k0, 256), 256, 0, st>>>(d_A, lda, d_piv.p, k0, nb, 0, k0);
-        const int c_lo = k0 + nb;
+        const int c_lo = pend;
         if (c_lo < NC) {
             lu_swap_kernel<<<(unsigned)ceil_div(NC - c_lo, 256), 256, 0, st>>>(d_A, lda, d_piv.p, k0, nb, c_lo, NC);
             lu_trsm_lower_kernel<<<(unsigned)ceil_div(NC - c_lo, 128), 128, 0, st>>>(d_A, lda, k0, nb, c_lo, NC);
