@@ -511,9 +511,8 @@ def run_e2e(sfb, wl, ndev, args):
             del pout, Mp
         except Exception as exc:  # noqa: BLE001
             res["pageable"] = {"error": str(exc)}
-        # the binned call of cfg4 (BASELINE.json: "binned ClnnBinnedModes output"): N = w̃ M v, Δl = 4 (single device)
+        # the binned call of cfg4 (BASELINE.json: "binned ClnnBinnedModes output"): N = w̃ M v, Δl = 4, on the same devices
         try:
-            sfb.set_devices(1)
             wt, vv = sfb.bandpower_binning_weights(wl.cmodes, dl=4)
             bc = sfb.ClnnBinnedModes(wt, vv, wl.cmodes)
             outN = sfb.pinned_empty((wt.shape[0], vv.shape[1]))
@@ -532,11 +531,14 @@ def run_e2e(sfb, wl, ndev, args):
                 pass
             bms = tb["binned_ms"]
             res["binned"] = {"ms_per_step": dtb * 1e3, "value": n * n / dtb, "unit": UNIT, "LNN": int(wt.shape[0]),
-                             "d2h_bytes_per_step": int(8 * wt.shape[0] * vv.shape[1]), "n_gpus": 1, "binned_ms": bms,
+                             "d2h_bytes_per_step": int(8 * wt.shape[0] * vv.shape[1]), "n_gpus": ndev, "binned_ms": bms,
+                             "checksum": float(outN[::53, ::47].sum()),
                              "roofline": {"kernel": "binned_product_kernel", "bound": "hbm", "unit": "GB/s",
-                                          "achieved": 8.0 * n * n / (bms * 1e-3) / 1e9 if bms > 0 else None, "peak": hbm,
-                                          "frac": (8.0 * n * n / (bms * 1e-3) / 1e9 / hbm) if (hbm and bms > 0) else None,
-                                          "algorithmic_bytes": 8.0 * n * n},
+                                          "achieved": 8.0 * n * n / ndev / (bms * 1e-3) / 1e9 if bms > 0 else None,
+                                          "peak": hbm,
+                                          "frac": (8.0 * n * n / ndev / (bms * 1e-3) / 1e9 / hbm) if (hbm and bms > 0) else None,
+                                          "algorithmic_bytes": 8.0 * n * n / ndev,
+                                          "note": "per device: every element of its column slab of M is read once"},
                              "note": "power_win_mix(win, w̃, v, wmodes, bcmodes) with Δl=4: all lnnsize² elements of M are "
                                      "formed on the device, only N = w̃Mv returns to the host"}
         except Exception as exc:  # noqa: BLE001

@@ -1,6 +1,7 @@
 // See binned.cuh for the reference functions replaced.
 #include "binned.cuh"
 
+#include <algorithm>
 #include <vector>
 
 namespace sfb {
@@ -156,6 +157,107 @@ int binned_product_device(const double* d_M, int64_t n, const int64_t* wt_colptr
             set_error("AssertionError: all(isfinite.(mix))");
             return 4;
         }
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// column-restricted form (multi-device runs: every device bins the column slab of M it formed)
+
+int bin_tables_build(BinTables* t, int64_t n, const int64_t* wt_colptr, const int64_t* wt_rowval, const double* wt_nzval,
+                     int64_t LNN1, const int64_t* v_colptr, const int64_t* v_rowval, const double* v_nzval, int64_t LNN2) {
+    t->n = n;
+    t->LNN1 = LNN1;
+    t->LNN2 = LNN2;
+    t->has_w = wt_colptr != nullptr;
+    t->has_v = v_colptr != nullptr;
+    if (!t->has_w) SFB_REQUIRE(LNN1 == n, "w̃ = I requires LNN1 == lnnsize");
+    if (!t->has_v) SFB_REQUIRE(LNN2 == n, "v = I requires LNN2 == lnnsize");
+    if (t->has_w) {
+        SFB_REQUIRE(wt_rowval && wt_nzval, "w̃: null rowval/nzval");
+        const int64_t nnz = wt_colptr[n] - 1;
+        t->wptr.assign(LNN1 + 1, 0);
+        t->wcol.resize(nnz);
+        t->wval.resize(nnz);
+        for (int64_t k = 0; k < nnz; ++k) {
+            const int64_t I = wt_rowval[k] - 1;
+            SFB_REQUIRE(I >= 0 && I < LNN1, "w̃: row index out of range");
+            t->wptr[I + 1]++;
+        }
+        for (int64_t I = 0; I < LNN1; ++I) t->wptr[I + 1] += t->wptr[I];
+        std::vector<int> fill(t->wptr.begin(), t->wptr.end() - 1);
+        for (int64_t i = 0; i < n; ++i)
+            for (int64_t k = wt_colptr[i] - 1; k < wt_colptr[i + 1] - 1; ++k) {
+                const int slot = fill[wt_rowval[k] - 1]++;
+                t->wcol[slot] = (int)i;
+                t->wval[slot] = wt_nzval[k];
+            }
+    }
+    if (t->has_v) {
+        SFB_REQUIRE(v_rowval && v_nzval, "v: null rowval/nzval");
+        const int64_t nnz = v_colptr[LNN2] - 1;
+        t->vptr.resize(LNN2 + 1);
+        t->vrow.resize(nnz);
+        t->vval.assign(v_nzval, v_nzval + nnz);
+        for (int64_t m = 0; m <= LNN2; ++m) t->vptr[m] = (int)(v_colptr[m] - 1);
+        for (int64_t k = 0; k < nnz; ++k) {
+            SFB_REQUIRE(v_rowval[k] >= 1 && v_rowval[k] <= n, "v: row index out of range");
+            t->vrow[k] = (int)(v_rowval[k] - 1);
+        }
+    }
+    return 0;
+}
+
+template <typename T>
+static int up_async(DevBuf<T>& d, const std::vector<T>& h, cudaStream_t st) {
+    SFB_TRY(d.alloc(std::max<size_t>(1, h.size())));
+    if (!h.empty()) SFB_CUDA_OK(cudaMemcpyAsync(d.p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+    return 0;
+}
+
+int bin_tables_upload(const BinTables& t, BinDev& d, cudaStream_t st) {
+    SFB_TRY(up_async(d.wptr, t.wptr, st));
+    SFB_TRY(up_async(d.wcol, t.wcol, st));
+    SFB_TRY(up_async(d.wval, t.wval, st));
+    SFB_TRY(up_async(d.vptr, t.vptr, st));
+    SFB_TRY(up_async(d.vrow, t.vrow, st));
+    SFB_TRY(up_async(d.vval, t.vval, st));
+    return 0;
+}
+
+void bin_needed_cols(const BinTables& t, int64_t J0, int64_t J1, int64_t* c0, int64_t* c1) {
+    if (!t.has_v) {
+        *c0 = J0;
+        *c1 = J1;
+        return;
+    }
+    int64_t lo = t.n, hi = 0;
+    for (int k = t.vptr[J0]; k < t.vptr[J1]; ++k) {
+        lo = std::min<int64_t>(lo, t.vrow[k]);
+        hi = std::max<int64_t>(hi, t.vrow[k] + 1);
+    }
+    if (hi <= lo) lo = hi = 0;
+    *c0 = lo;
+    *c1 = hi;
+}
+
+int binned_product_range(const double* d_Mslab, int64_t c0, const BinTables& t, const BinDev& d, int64_t J0, int64_t J1,
+                         double* d_N, int64_t ldN, cudaStream_t st) {
+    if (J1 <= J0) return 0;
+    SFB_REQUIRE(d_Mslab && d_N && ldN >= t.LNN1, "binned_product_range: bad arguments");
+    const double* Mbase = d_Mslab - c0 * t.n;      // virtual base of the full matrix: only columns >= c0 are dereferenced
+    for (int64_t m0 = J0; m0 < J1; m0 += 65535) {
+        const int64_t mc = std::min<int64_t>(65535, J1 - m0);
+        if (t.has_v) {
+            binned_product_kernel<<<dim3((unsigned)ceil_div(t.LNN1, 128), (unsigned)mc), 128, 0, st>>>(
+                Mbase, t.n, t.has_w ? d.wptr.p : nullptr, d.wcol.p, d.wval.p, (int)t.LNN1, d.vptr.p + m0, d.vrow.p, d.vval.p,
+                (int)t.LNN2, d_N + (size_t)(m0 - J0) * ldN, ldN);
+        } else {   // v = I: output column J reads M column J
+            binned_product_kernel<<<dim3((unsigned)ceil_div(t.LNN1, 128), (unsigned)mc), 128, 0, st>>>(
+                Mbase + m0 * t.n, t.n, t.has_w ? d.wptr.p : nullptr, d.wcol.p, d.wval.p, (int)t.LNN1, nullptr, nullptr, nullptr,
+                (int)t.LNN2, d_N + (size_t)(m0 - J0) * ldN, ldN);
+        }
+        SFB_CUDA_OK(cudaGetLastError());
     }
     return 0;
 }

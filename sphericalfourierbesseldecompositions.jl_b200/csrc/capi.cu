@@ -441,6 +441,12 @@ struct MdJob {
     const int64_t* lnn = nullptr;
     int div2Lp1 = 0, interchange = 0;
     double* M_out = nullptr;
+    // binned output N = w̃ M v (every device bins the column slab of M it forms and returns its columns of N)
+    const BinTables* bin = nullptr;
+    double* N_out = nullptr;
+    int64_t J[kMaxDev + 1] = {0};                          // output-column bounds per device
+    int64_t bcol0[kMaxDev] = {0}, bcol1[kMaxDev] = {0};   // M columns each device needs for them (may overlap)
+    double t_bin[kMaxDev] = {0};
     // calc_Wr_lm output (device 0 gathers and converts)
     double* wr_out = nullptr;
     int layout = 0;
@@ -542,6 +548,40 @@ static int md_phase_cmix(MdJob& J, int d) {
     if (J.nwin == 2) SFB_TRY(md_gather_alm(J, d, 1, ws.alm2, p->nrp));
     const double* a1 = ws.alm1.p;
     const double* a2 = J.nwin == 2 ? ws.alm2.p : a1;
+    if (J.bin) {   // N[:, J0:J1) = w̃ · M[:, c0:c1) · v[c0:c1, J0:J1): the slab of M never leaves the device
+        const int64_t J0 = J.J[d], J1 = J.J[d + 1], c0 = J.bcol0[d], c1 = J.bcol1[d], n = p->nout, L1 = J.bin->LNN1;
+        if (J1 <= J0) return 0;
+        BinDev bd;
+        SFB_TRY(bin_tables_upload(*J.bin, bd, ws.main));
+        SFB_TRY(ws.slab[0].alloc((size_t)std::max<int64_t>(1, c1 - c0) * n));
+        if (c1 > c0)
+            SFB_TRY(cmix_run(p, a1, a2, J.div2Lp1, J.interchange, 0, n, c0, c1, ws.slab[0].p, n, ws.main));   // synchronous
+        SFB_TRY(ws.slab[1].alloc((size_t)L1 * (J1 - J0)));
+        cudaEvent_t e0, e1;
+        SFB_CUDA_OK(cudaEventCreate(&e0));
+        SFB_CUDA_OK(cudaEventCreate(&e1));
+        SFB_CUDA_OK(cudaEventRecord(e0, ws.main));
+        SFB_TRY(binned_product_range(ws.slab[0].p, c0, *J.bin, bd, J0, J1, ws.slab[1].p, L1, ws.main));
+        SFB_CUDA_OK(cudaEventRecord(e1, ws.main));
+        SFB_TRY(ws.flag.alloc(1));
+        SFB_CUDA_OK(cudaMemsetAsync(ws.flag.p, 0, sizeof(int), ws.main));
+        finite_check_kernel<<<256, 256, 0, ws.main>>>(ws.slab[1].p, (size_t)L1 * (J1 - J0), ws.flag.p);
+        SFB_CUDA_OK(cudaMemcpyAsync(J.N_out + J0 * L1, ws.slab[1].p, (size_t)L1 * (J1 - J0) * sizeof(double),
+                                    cudaMemcpyDeviceToHost, ws.main));
+        int h = 0;
+        SFB_CUDA_OK(cudaMemcpyAsync(&h, ws.flag.p, sizeof(int), cudaMemcpyDeviceToHost, ws.main));
+        SFB_CUDA_OK(cudaStreamSynchronize(ws.main));
+        float t = 0;
+        cudaEventElapsedTime(&t, e0, e1);
+        J.t_bin[d] = t;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        if (h) {   // @assert all(isfinite.(mix))  src/windows.jl:1013
+            set_error("AssertionError: all(isfinite.(mix))");
+            return 4;
+        }
+        return 0;
+    }
     SFB_TRY(cmix_cols_to_host(p, ws, a1, a2, J.div2Lp1, J.interchange, J.col[d], J.col[d + 1], 4, J.M_out));
     return 0;
 }
@@ -595,7 +635,7 @@ static int md_run(MdJob& J) {
         double t[5] = {0, 0, 0, 0, 0}, launches = 0;
         for (int d = 0; d < n; ++d) {
             const CmixPlan* p = J.cplan[d];
-            if (!p || J.col[d + 1] <= J.col[d]) continue;
+            if (!p || (J.bin ? J.bcol1[d] <= J.bcol0[d] : J.col[d + 1] <= J.col[d])) continue;
             t[0] = std::max<double>(t[0], p->t_wl);
             t[1] = std::max<double>(t[1], p->t_fill);
             t[2] = std::max<double>(t[2], p->t_what);
@@ -609,6 +649,8 @@ static int md_run(MdJob& J) {
         g_times[4] = t[3];
         g_times[5] = t[4];
         g_times[6] += launches;
+        g_times[7] = 0;
+        for (int d = 0; d < n; ++d) g_times[7] = std::max(g_times[7], J.t_bin[d]);
     }
     return 0;
 }
@@ -840,6 +882,34 @@ int32_t sfb_power_win_mix_binned(const double* win1, int64_t nr, int64_t npix_in
     std::lock_guard<std::mutex> lk(g_mutex);
     SFB_REQUIRE(win1 && N_out, "null pointer");
     Trace tr;
+    if (md_devices_for(nr) > 1) {   // sfb_set_devices(n): output columns of N, hence column slabs of M, sharded over n GPUs
+        MdJob J;
+        SFB_TRY(make_plan_key(&J.key, lnn, lnnsize, 1, G, nr, nmax, lmax));
+        SFB_REQUIRE(ld_win >= nr, "ld_win < nr");
+        BinTables bt;
+        SFB_TRY(bin_tables_build(&bt, lnnsize, wt_colptr, wt_rowval, wt_nzval, LNN1, v_colptr, v_rowval, v_nzval, LNN2));
+        J.win[0] = win1;      // like the reference, W2r_lm is computed from win1 as well (src/windows.jl:1005-1006)
+        J.nr = nr, J.npix_in = npix_in, J.ld_win = ld_win, J.nside = nside, J.LMAX = 2 * lmax;
+        SFB_TRY(npix2nside(npix_in, &J.nside_in));
+        J.want_cmix = true;
+        J.G = G, J.nmax = nmax, J.lmax = lmax, J.lnn = lnn, J.lnnsize = lnnsize, J.lnn_min = 1;
+        J.div2Lp1 = div2Lp1, J.interchange = interchange_NN;
+        J.bin = &bt, J.N_out = N_out;
+        J.ndev = md_devices_for(nr);
+        // output columns in ndev contiguous ranges of equal v-nonzero count (a proxy for the M columns behind them)
+        const int64_t total = bt.has_v ? (int64_t)bt.vptr[LNN2] : LNN2;
+        J.J[0] = 0;
+        for (int g = 1; g <= J.ndev; ++g) {
+            int64_t j = J.J[g - 1];
+            const int64_t target = total * g / J.ndev;
+            while (j < LNN2 && (bt.has_v ? (int64_t)bt.vptr[j] : j) < target) ++j;
+            J.J[g] = (g == J.ndev) ? LNN2 : j;
+        }
+        for (int g = 0; g < J.ndev; ++g) bin_needed_cols(bt, J.J[g], J.J[g + 1], &J.bcol0[g], &J.bcol1[g]);
+        SFB_TRY(md_run(J));
+        tr.mark("multi-device binned power_win_mix");
+        return 0;
+    }
     PlanGuard pg;
     SFB_TRY(get_cmix_plan(&pg.p, lnn, lnnsize, 1, G, nr, nmax, lmax));
     tr.mark("binned: plan");

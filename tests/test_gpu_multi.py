@@ -97,6 +97,11 @@ def _set_devices_case(sfb, ndev, nr=21):
             res["Wr"] = sfb.calc_Wr_lm(win, 2 * a.lmax, a.nside)
             res["Wr_fast"] = sfb.calc_Wr_lm(win, 2 * a.lmax, a.nside, layout=1)
             res["Wr_up"] = sfb.calc_Wr_lm(np.asfortranarray(win2[:, :12 * 8 * 8]), 2 * a.lmax, a.nside)  # nside 8 -> udgrade
+            wt, v = sfb.bandpower_binning_weights(c, dl=3)
+            bc = sfb.ClnnBinnedModes(wt, v, c)
+            res["N"] = sfb.power_win_mix(win, wt, v, wm, bc)
+            res["wM"] = sfb.power_win_mix(win, wt, None, wm, bc)
+            res["Mv"] = sfb.power_win_mix(win, None, v, wm, bc, div2Lp1=True)
             out = sfb.pinned_empty(res["M"].shape)
             res["M_pinned"] = sfb.power_win_mix(win, wm, c, out=out).copy()
         finally:
