@@ -226,8 +226,12 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the CUDA arm has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # host-side barrier for the e2e leg: an NCCL barrier would keep a spinning kernel on every idle rank's GPU while
+        # rank 0 drives all GPUs through the C ABI
+        cpu_group = dist.new_group(backend="gloo")
     lib = _lib.load()
     _lib.check(lib.sfb_set_device(local_rank))
 
@@ -433,10 +437,13 @@ def run_b200(args):
     e2e = None
     if not args.no_e2e:
         del full
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(group=cpu_group)
         if rank == 0:
             e2e = run_e2e(sfb, wl, world, args)
         if world > 1:
-            dist.barrier()
+            dist.barrier(group=cpu_group)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

@@ -589,12 +589,21 @@ static int md_phase_cmix(MdJob& J, int d) {
 static void md_worker(MdJob* Jp, int d) {
     MdJob& J = *Jp;
     int (*phases[3])(MdJob&, int) = {md_phase_upload, md_phase_stage1, md_phase_cmix};
+    static const char* names[3] = {"md: plans + H2D enqueue", "md: shell gather + stage 1", "md: alm gather + stage 2/3 + D2H"};
+    const bool trace = (d == 0) && getenv("SFB_TRACE") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
     for (int ph = 0; ph < 3; ++ph) {
         if (!J.gang.failed.load()) {
             const int rc = phases[ph](J, d);
             if (rc) J.gang.fail(d, rc);
         }
         J.gang.sync();   // every worker arrives at every barrier, failed or not
+        if (trace) {
+            const auto t1 = std::chrono::steady_clock::now();
+            fprintf(stderr, "[sfb] %-36s %8.3f ms (device 0 + barrier)\n", names[ph],
+                    std::chrono::duration<double, std::milli>(t1 - t0).count());
+            t0 = t1;
+        }
     }
     // nobody may reuse a slice / alm shard while a peer still reads it: drain this device before the call returns
     if (J.ws[d]) {
