@@ -274,7 +274,7 @@ def test_device_pipeline_row_shards():
 # the kernels behind the environment switches are exercised here (the switches are read at call
 # time), each against the oracle, so none of them is dead code on the GPU box.
 
-@pytest.mark.parametrize("flag", ["SFB_NO_MIRROR", "SFB_CMIX_OLD", "SFB_WHAT_FMA", "SFB_WL_FMA"])
+@pytest.mark.parametrize("flag", ["SFB_NO_MIRROR", "SFB_CMIX_OLD", "SFB_WHAT_FMA", "SFB_WL_FMA", "SFB_REGZ_CPASYNC"])
 @pytest.mark.parametrize("nr", [24, 64])
 def test_stage23_alternative_paths(monkeypatch, flag, nr):
     import warnings
@@ -283,6 +283,7 @@ def test_stage23_alternative_paths(monkeypatch, flag, nr):
     ref = ow.power_win_mix(win, win, owm, oc)
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
+        monkeypatch.setenv("SFB_REGZ_TMA_STRICT", "1")          # the default TMA staging must not silently fall back
         base = sfb.power_win_mix(win, wm, c)
         monkeypatch.setenv(flag, "1")
         got = sfb.power_win_mix(win, wm, c)
