@@ -161,4 +161,88 @@ function power_win_mix(win1, win2, w̃mat, vmat, wmodes::ConfigurationSpaceModes
     return mix
 end
 
+############################## §8f rows: calc_wmix, SFB transforms, deconvolution ##############################
+
+# src/windows.jl:299-364
+function calc_wmix(win::AbstractMatrix{Float64}, wmodes::ConfigurationSpaceModes, amodes::AnlmModes; neg_m=false)
+    win = win isa Matrix{Float64} ? win : Matrix{Float64}(win)
+    G = rsdrgnlr(amodes, wmodes)
+    nr, npix = size(win)
+    nlmsize = SFB.getnlmsize(amodes)
+    wmix = pinned_matrix(ComplexF64, nlmsize, nlmsize)
+    nmax_l = Vector{Int64}(amodes.nmax_l); lmax_n = Vector{Int64}(amodes.lmax_n)
+    GC.@preserve win G nmax_l lmax_n wmix check(ccall((:sfb_calc_wmix, libsfb), Int32,
+        (Ptr{Float64}, Int64, Int64, Int64, Int64, Ptr{Float64}, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Int32, Ptr{ComplexF64}),
+        win, nr, npix, stride(win, 2), amodes.nside, G, amodes.nmax, amodes.lmax, nmax_l, lmax_n, neg_m, wmix))
+    return wmix
+end
+calc_wmix_all(win::AbstractMatrix{Float64}, wmodes, amodes) =                      # src/window_chains.jl:578-582
+    (calc_wmix(win, wmodes, amodes), calc_wmix(win, wmodes, amodes, neg_m=true))
+
+# radial tables trimmed like rsdrgnlr: g_nl(r) and g_nl(r) r² Δr
+function gnlr_tables(amodes, wmodes)
+    r, Δr = window_r(wmodes)
+    g = Array(SFB.Windows.precompute_gnlr(amodes, wmodes)[:, 1:amodes.nmax, 1:amodes.lmax+1])
+    return g, g .* (r .^ 2 .* Δr)
+end
+
+# src/cat2anlm.jl:326-373
+function field2anlm(f_xyz::AbstractMatrix{Float64}, wmodes::ConfigurationSpaceModes, amodes::AnlmModes)
+    f = f_xyz isa Matrix{Float64} ? f_xyz : Matrix{Float64}(f_xyz)
+    _, T = gnlr_tables(amodes, wmodes)
+    out = Vector{ComplexF64}(undef, SFB.getnlmsize(amodes))
+    nmax_l = Vector{Int64}(amodes.nmax_l); lmax_n = Vector{Int64}(amodes.lmax_n)
+    GC.@preserve f T nmax_l lmax_n out check(ccall((:sfb_field2anlm, libsfb), Int32,
+        (Ptr{Float64}, Int64, Int64, Int64, Ptr{Float64}, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{ComplexF64}),
+        f, size(f, 1), size(f, 2), stride(f, 2), T, amodes.nmax, amodes.lmax, nmax_l, lmax_n, out))
+    return out
+end
+
+# src/cat2anlm.jl:385-422
+function anlm2field(f_nlm::AbstractVector{ComplexF64}, wmodes::ConfigurationSpaceModes, amodes::AnlmModes)
+    g, _ = gnlr_tables(amodes, wmodes)
+    f = Vector{ComplexF64}(f_nlm)
+    out = pinned_matrix(Float64, wmodes.nr, wmodes.npix)
+    nmax_l = Vector{Int64}(amodes.nmax_l); lmax_n = Vector{Int64}(amodes.lmax_n)
+    GC.@preserve f g nmax_l lmax_n out check(ccall((:sfb_anlm2field, libsfb), Int32,
+        (Ptr{ComplexF64}, Ptr{Float64}, Int64, Int64, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Int64),
+        f, g, wmodes.nr, amodes.nside, amodes.nmax, amodes.lmax, nmax_l, lmax_n, out, wmodes.nr))
+    return out
+end
+
+# src/windows.jl:244-256 (the SeparableArray method :259-270 stays in Julia)
+function win_rhat_ln(win::AbstractMatrix{Float64}, wmodes::ConfigurationSpaceModes, amodes::AnlmModes)
+    w = win isa Matrix{Float64} ? win : Matrix{Float64}(win)
+    _, T = gnlr_tables(amodes, wmodes)
+    out = pinned_matrix(Float64, size(w, 2) * (amodes.lmax + 1) * amodes.nmax)
+    nmax_l = Vector{Int64}(amodes.nmax_l); lmax_n = Vector{Int64}(amodes.lmax_n)
+    GC.@preserve w T nmax_l lmax_n out check(ccall((:sfb_win_rhat_ln, libsfb), Int32,
+        (Ptr{Float64}, Int64, Int64, Int64, Ptr{Float64}, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}),
+        w, size(w, 1), size(w, 2), stride(w, 2), T, amodes.nmax, amodes.lmax, nmax_l, lmax_n, out))
+    return reshape(out, size(w, 2), amodes.lmax + 1, amodes.nmax)
+end
+
+# C = bcmix \ (w̃mat * Cobs) without bringing bcmix to the host  (docs/src/tutorial_catalog.md:93-97)
+function power_win_mix_solve(win::AbstractMatrix{Float64}, w̃mat, vmat, wmodes::ConfigurationSpaceModes,
+                             bcmodes::ClnnBinnedModes, B::AbstractVecOrMat{Float64}; div2Lp1=false, interchange_NN′=false)
+    cmodes = bcmodes.cmodes
+    amodes = cmodes.amodes
+    G = rsdrgnlr(amodes, wmodes)
+    lnn = cmodes.lnn
+    lnnsize = getlnnsize(cmodes)
+    wc, wr, wv, LNN1, wkeep = csc(w̃mat, lnnsize, 1)
+    vc, vr, vv, LNN2, vkeep = csc(vmat, lnnsize, 2)
+    w1 = win isa Matrix{Float64} ? win : Matrix{Float64}(win)
+    Bm = Matrix{Float64}(reshape(B, LNN1, :))
+    X = similar(Bm)
+    nr, npix = size(w1)
+    GC.@preserve w1 G lnn wkeep vkeep Bm X check(ccall((:sfb_power_win_mix_binned_solve, libsfb), Int32,
+        (Ptr{Float64}, Int64, Int64, Int64, Int64, Ptr{Float64}, Int64, Int64, Ptr{Int64}, Int64,
+         Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Int64, Int32, Int32,
+         Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}),
+        w1, nr, npix, stride(w1, 2), amodes.nside, G, amodes.nmax, amodes.lmax, lnn, lnnsize,
+        wc, wr, wv, LNN1, vc, vr, vv, LNN2, div2Lp1, interchange_NN′, Bm, size(Bm, 2), X, C_NULL))
+    return B isa AbstractVector ? vec(X) : X
+end
+
 end # module

@@ -1074,7 +1074,7 @@ __global__ void __launch_bounds__(kT) gram_apply_kernel(const double* __restrict
 // F'_m = nφ G_m; short polar rings pick up their exact aliases.  So map - S(alm) is never formed in the iterations:
 //   alm <- alm + A f - LegendreAnalysis(F'(LegendreSynthesis(alm))).
 // thread = (ring, m, column c of the re plane); G and F2 are [m][ring][re/im][nrp].
-// Class-sum form (DESIGN §9.1; identity checked on CPU: tests/test_oracle_sht.py::test_alias_operator_class_sum_form).
+// Class-sum form (identity checked on CPU: tests/test_oracle_sht.py::test_alias_operator_class_sum_form).
 // F'_m depends on m only through ρ = m mod nφ and q = m div nφ: with the alternating class sums
 //   Q[ρ] = Σ_j σ^j c_{ρ+j nφ} G_{ρ+j nφ}      (c_0 = 1/2, c_{m'} = 1 otherwise; σ = -1 on shifted rings)
 //   F'_m = nφ σ^q ( Q[ρ] + σ^{[ρ≠0]} conj Q[(nφ-ρ) mod nφ] ).

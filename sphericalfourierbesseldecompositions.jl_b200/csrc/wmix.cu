@@ -49,7 +49,7 @@ __device__ __forceinline__ double warp_max(double v) {
 }
 
 // (j j2 j3; m1 m2 m3), j = jmin..jmax, m1 = -m2-m3, into f[0..n) (warp-private shared memory; Aj, Bj, fw, bw scratch of
-// the same capacity).  Restates oracle/wigner.py::wigner3j_family (the WignerFamilies algorithm) step for step.
+// the same capacity).  The WignerFamilies algorithm (Schulten-Gordon / Luscombe-Luban two-sided recursion): same steps as the CPU checker.
 __device__ void w3j_family_warp(int j2, int j3, int m2, int m3, double* Aj, double* Bj, double* fw, double* bw, double* f,
                                 int* jmin_out, int* n_out) {
     const int lane = threadIdx.x & 31;
