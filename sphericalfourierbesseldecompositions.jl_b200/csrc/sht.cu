@@ -72,6 +72,18 @@ __global__ void lambda_table_kernel(double* __restrict__ lam, int nside, int lma
     }
 }
 
+// max_l |λ_lm(θ_k)| per (north ring k, m): input of the m-cutoff tables (libsharp's `mlim` idea, but read off the table the
+// kernels actually use, so the cutoff is rigorous): beyond mlim[k] every λ_lm(θ_k), l <= lmax, is below 1e-30 and the
+// (ring, m) pair contributes nothing at FP64 precision.
+__global__ void lambda_absmax_kernel(const double* __restrict__ lam, int lmax, int nhalf, double* __restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int m = blockIdx.y;
+    if (k >= nhalf) return;
+    double mx = 0.0;
+    for (int l = m; l <= lmax; ++l) mx = fmax(mx, fabs(lam[lm_mmajor(lmax, l, m) * nhalf + k]));
+    out[(size_t)m * nhalf + k] = mx;
+}
+
 // ---------------------------------------------------------------------------------------------
 // udgrade via the NESTED scheme
 
@@ -557,14 +569,17 @@ struct ColTile {
 template <int NI>
 __global__ void __launch_bounds__(kT) cap_analysis_kernel(const double* __restrict__ map, long long ldw, int nr, int nrp,
                                                           RingTabs rt, const int* __restrict__ ring_list, int nrings,
-                                                          int lmax, double* __restrict__ F) {
+                                                          int lmax, double* __restrict__ F,
+                                                          const int* __restrict__ mlim_ring) {
     constexpr int BW = ColTile<NI>::BW, LD = ColTile<NI>::LD;
     __shared__ double As[64 * kLdF];
     __shared__ double Bs[4][kFK * LD];
     // m-chunk index fastest: the CTAs that re-read the same ring of the map are co-scheduled (L2 reuse)
     const int ring = ring_list[blockIdx.y], m0 = blockIdx.x * 32, sh0 = blockIdx.z * BW;
     const int nphi = rt.nphi[ring], start = rt.start[ring];
-    const int nq = nphi >> 2;
+    // m beyond the ring's cutoff meet only λ_lm < 1e-30 in the Legendre step: their F_m are written as zeros, not computed
+    const bool skip = mlim_ring && m0 > mlim_ring[min(ring, nrings - 1 - ring)];
+    const int nq = skip ? 0 : (nphi >> 2);
     const double2* tw = rt.tw + rt.twoff[ring];
     const unsigned two_nphi = 2u * nphi;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
@@ -769,7 +784,8 @@ __global__ void __launch_bounds__(kT) legendre_analysis_kernel(const double* __r
                                                                const double* __restrict__ lam, int nrings, int nhalf,
                                                                int kend, int lmax, int nrp, double w, int accumulate,
                                                                const double* __restrict__ add,
-                                                               double* __restrict__ alm) {
+                                                               double* __restrict__ alm,
+                                                               const int* __restrict__ kbeg_of_m) {
     // kend: only the north rings [0, kend) (and their southern mirrors) contribute (kend = nhalf: all rings)
     constexpr int BW = ColTile<NI>::BW, LD = ColTile<NI>::LD;
     extern __shared__ double la_smem[];
@@ -815,8 +831,10 @@ __global__ void __launch_bounds__(kT) legendre_analysis_kernel(const double* __r
             }
         }
     };
-    prefetch(0);
-    for (int k0 = 0; k0 < kend; k0 += 32) {
+    // rings [0, kbeg) see only λ_lm < 1e-30 for this m (the cutoff grows towards the equator): start at the first live chunk
+    const int kbeg = kbeg_of_m ? min(kbeg_of_m[m], kend) : 0;
+    prefetch(kbeg);
+    for (int k0 = kbeg; k0 < kend; k0 += 32) {
         {
             const int kk = tid & 31;
 #pragma unroll
@@ -866,7 +884,8 @@ __global__ void __launch_bounds__(kT, 2) legendre_synthesis_kernel(const double*
                                                                 const double* __restrict__ lam, int nrings, int nhalf,
                                                                 int kend, int lmax, int nrp, double* __restrict__ G,
                                                                 double* __restrict__ F2,
-                                                                const int* __restrict__ nphi_tab) {
+                                                                const int* __restrict__ nphi_tab,
+                                                                const int* __restrict__ mlim_tile) {
     // kend: only the north rings [0, kend) and their mirrors are synthesised (the grid covers ceil(kend/64) tiles)
     // F2 (optional): rings with nφ > 2 lmax have no aliases, their re-analysed Fourier coefficients are F'_m = nφ G_m
     // (imaginary part of m = 0 dropped; see ring_alias_kernel), so they are written there directly and the alias pass
@@ -875,6 +894,9 @@ __global__ void __launch_bounds__(kT, 2) legendre_synthesis_kernel(const double*
     __shared__ double Ls[32 * kLdB];  // [l (16 even-parity, 16 odd-parity)][ring]
     __shared__ double Bs[32 * LD];
     const int m = blockIdx.x, k0 = blockIdx.y * 64, c0 = blockIdx.z * BW;
+    // every ring of this tile is beyond the cutoff of m: its G_m would be < 1e-30 |alm|; the consumers (alias pass with the
+    // same cutoff, Legendre analysis) never use it.  Only passed in the ring-space Jacobi passes (alm2map needs every G).
+    if (mlim_tile && m > mlim_tile[blockIdx.y]) return;
     const int ncol = 2 * nrp;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int wm = warp >> 1, wn = warp & 1;
@@ -1085,7 +1107,7 @@ __global__ void __launch_bounds__(256) ring_alias_smem_kernel(const double* __re
                                                               const int* __restrict__ ring_list,
                                                               const int* __restrict__ nphi_tab,
                                                               const int* __restrict__ shift_tab, int nrings, int lmax,
-                                                              int nrp) {
+                                                              int nrp, const int* __restrict__ mlim_ring) {
     extern __shared__ double Qs[];   // [ρ < min(nφ, lmax+1)][re/im][kAliasCW]
     constexpr int CW = kAliasCW;
     const int ring = ring_list[blockIdx.x], c0 = blockIdx.y * CW;
@@ -1099,7 +1121,8 @@ __global__ void __launch_bounds__(256) ring_alias_smem_kernel(const double* __re
         double q = 0.0;
         if (c0 + c < nrp) {
             double s = (rho == 0) ? 0.5 : 1.0;
-            for (int mp = rho; mp <= lmax; mp += n) {
+            const int mcap = mlim_ring ? min(lmax, mlim_ring[min(ring, nrings - 1 - ring)]) : lmax;   // G beyond: not synthesised
+            for (int mp = rho; mp <= mcap; mp += n) {
                 q = fma(s, g[(size_t)mp * stride_m + (size_t)comp * nrp + c], q);
                 s = (mp == 0) ? sig : s * sig;           // c_0 = 1/2 applies to m' = 0 only
             }
@@ -1283,6 +1306,45 @@ int sht_plan_create(ShtPlan** out, int64_t nside_in, int64_t nside_out, int64_t 
     twiddle_table_kernel<<<ns, 256>>>(p->d_tw.p, ns);
     lambda_table_kernel<<<dim3((unsigned)ceil_div(p->nhalf, 128), (unsigned)(lmax + 1)), 128>>>(p->d_lam.p, ns, (int)lmax,
                                                                                               p->nhalf);
+    if (!getenv("SFB_SHT_NO_MLIM")) {
+        // m-cutoff tables from the λ table itself: mlim_ring[k] = largest m with max_l |λ_lm(θ_k)| >= 1e-30
+        DevBuf<double> d_mx;
+        rc = d_mx.alloc((size_t)(lmax + 1) * p->nhalf);
+        if (!rc) {
+            lambda_absmax_kernel<<<dim3((unsigned)ceil_div(p->nhalf, 128), (unsigned)(lmax + 1)), 128>>>(p->d_lam.p, (int)lmax,
+                                                                                                         p->nhalf, d_mx.p);
+            std::vector<double> mx((size_t)(lmax + 1) * p->nhalf);
+            if (cudaMemcpy(mx.data(), d_mx.p, mx.size() * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) rc = 1;
+            if (!rc) {
+                std::vector<int> mlim(p->nhalf, 0);
+                for (int k = 0; k < p->nhalf; ++k)
+                    for (int m = 0; m <= lmax; ++m)
+                        if (mx[(size_t)m * p->nhalf + k] >= 1e-30) mlim[k] = m;
+                for (int k = 1; k < p->nhalf; ++k) mlim[k] = std::max(mlim[k], mlim[k - 1]);   // monotone towards the equator
+                std::vector<int> tile((p->nhalf + 63) / 64, 0), kbeg(lmax + 1, 0);
+                for (int k = 0; k < p->nhalf; ++k) tile[k / 64] = std::max(tile[k / 64], mlim[k]);
+                for (int m = 0; m <= lmax; ++m) {
+                    int k = 0;
+                    while (k < p->nhalf && mlim[k] < m) ++k;       // first ring that sees m
+                    kbeg[m] = (k / 32) * 32;                        // chunk of 32 rings it lives in
+                }
+                rc = rc ? rc : up(p->d_mlim_ring, mlim);
+                rc = rc ? rc : up(p->d_mlim_tile, tile);
+                rc = rc ? rc : up(p->d_kbeg_of_m, kbeg);
+            }
+        }
+        if (rc) {
+            set_error("sht_plan_create: m-cutoff tables");
+            delete p;
+            return rc;
+        }
+    }
+    // skipped (ring, m) pairs leave their slots untouched: the buffers must hold finite numbers from the start
+    if (cudaMemset(p->d_FG.p, 0, p->d_FG.n * sizeof(double)) != cudaSuccess) {
+        set_error("sht_plan_create: cudaMemset");
+        delete p;
+        return 1;
+    }
     {
         // rings [0, kpolar) keep synthesis -> alias -> analysis in a Jacobi pass; the alias-free rings beyond go through
         // the Gram matrices.  kpolar = the aliased north rings (nφ <= 2 lmax) rounded up to the synthesis tile of 64.
@@ -1356,11 +1418,14 @@ static int run_ring_analysis(ShtPlan* p, const double* map, int64_t ldw, cudaStr
         const int ni = pick_ni(nrp);
         dim3 gc((unsigned)ceil_div(lmax + 1, 32), p->n_cap_rings, (unsigned)ceil_div(nrp, 16 * ni));
         if (ni == 4)
-            cap_analysis_kernel<4><<<gc, kT, 0, st>>>(map, ldw, p->nr, nrp, rt, p->d_cap_rings.p, p->nrings, lmax, p->d_FG.p);
+            cap_analysis_kernel<4><<<gc, kT, 0, st>>>(map, ldw, p->nr, nrp, rt, p->d_cap_rings.p, p->nrings, lmax, p->d_FG.p,
+                                                      p->d_mlim_ring.p);
         else if (ni == 2)
-            cap_analysis_kernel<2><<<gc, kT, 0, st>>>(map, ldw, p->nr, nrp, rt, p->d_cap_rings.p, p->nrings, lmax, p->d_FG.p);
+            cap_analysis_kernel<2><<<gc, kT, 0, st>>>(map, ldw, p->nr, nrp, rt, p->d_cap_rings.p, p->nrings, lmax, p->d_FG.p,
+                                                      p->d_mlim_ring.p);
         else
-            cap_analysis_kernel<1><<<gc, kT, 0, st>>>(map, ldw, p->nr, nrp, rt, p->d_cap_rings.p, p->nrings, lmax, p->d_FG.p);
+            cap_analysis_kernel<1><<<gc, kT, 0, st>>>(map, ldw, p->nr, nrp, rt, p->d_cap_rings.p, p->nrings, lmax, p->d_FG.p,
+                                                      p->d_mlim_ring.p);
         SFB_CUDA_OK(cudaGetLastError());
         p->launches++;
     }
@@ -1390,7 +1455,8 @@ static int run_legendre_analysis(ShtPlan* p, const double* Fsrc, double w, int a
         SFB_CUDA_OK(cudaFuncSetAttribute(legendre_analysis_kernel<NI_>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                          la_smem_bytes));                                                             \
         legendre_analysis_kernel<NI_><<<g2, kT, la_smem_bytes, st>>>(Fsrc, p->d_lam.p, p->nrings, p->nhalf, kend, lmax,  \
-                                                                     nrp, w, accumulate, add, d_alm);                \
+                                                                     nrp, w, accumulate, add, d_alm,                 \
+                                                                     p->d_kbeg_of_m.p);                              \
     } while (0)
     if (nil == 4)
         SFB_LAUNCH_LA(4);
@@ -1479,17 +1545,18 @@ int sht_map2alm(ShtPlan* p, const double* d_win, int64_t ldw, int niter, double*
     const bool pixel_iter = getenv("SFB_SHT_PIXEL_ITER") != nullptr;  // cross-check: refine through pixel space
     auto legendre_synthesis = [&](bool ring_iter, int kend) -> int {
         double* f2 = ring_iter ? p->d_F2.p : nullptr;
+        const int* mt = ring_iter ? p->d_mlim_tile.p : nullptr;
         const int nil = pick_ni(2 * p->nrp);
         dim3 gs(p->lmax + 1, (unsigned)ceil_div(kend, 64), (unsigned)ceil_div(2 * p->nrp, 16 * nil));
         if (nil == 4)
             legendre_synthesis_kernel<4><<<gs, kT, 0, st>>>(d_alm, p->d_lam.p, p->nrings, p->nhalf, kend, p->lmax, p->nrp,
-                                                            p->d_FG.p, f2, p->d_nphi.p);
+                                                            p->d_FG.p, f2, p->d_nphi.p, mt);
         else if (nil == 2)
             legendre_synthesis_kernel<2><<<gs, kT, 0, st>>>(d_alm, p->d_lam.p, p->nrings, p->nhalf, kend, p->lmax, p->nrp,
-                                                            p->d_FG.p, f2, p->d_nphi.p);
+                                                            p->d_FG.p, f2, p->d_nphi.p, mt);
         else
             legendre_synthesis_kernel<1><<<gs, kT, 0, st>>>(d_alm, p->d_lam.p, p->nrings, p->nhalf, kend, p->lmax, p->nrp,
-                                                            p->d_FG.p, f2, p->d_nphi.p);
+                                                            p->d_FG.p, f2, p->d_nphi.p, mt);
         SFB_CUDA_OK(cudaGetLastError());
         p->launches += 1;
         return 0;
@@ -1497,7 +1564,10 @@ int sht_map2alm(ShtPlan* p, const double* d_win, int64_t ldw, int niter, double*
     if (niter > 0 && !pixel_iter) {
         // alm <- alm + A f - Λ F'(Λᵀ alm): the refinement never leaves ring-Fourier space (ring_alias_kernel)
         const size_t nalm = p->lmsize * 2 * p->nrp;
-        SFB_TRY(p->d_F2.alloc((size_t)(p->lmax + 1) * p->nrings * 2 * p->nrp));
+        if (!p->d_F2.p) {
+            SFB_TRY(p->d_F2.alloc((size_t)(p->lmax + 1) * p->nrings * 2 * p->nrp));
+            SFB_CUDA_OK(cudaMemsetAsync(p->d_F2.p, 0, p->d_F2.n * sizeof(double), st));   // see the m-cutoff: finite from the start
+        }
         SFB_TRY(p->d_a0.alloc(nalm));
         SFB_TRY(run_ring_analysis(p, map, ldm, st));
         SFB_TRY(run_legendre_analysis(p, p->d_FG.p, w, 0, nullptr, p->d_a0.p, st));
@@ -1531,7 +1601,7 @@ int sht_map2alm(ShtPlan* p, const double* d_win, int64_t ldw, int niter, double*
                                                      alias_smem));
                     ring_alias_smem_kernel<<<dim3(p->n_alias_rings, (unsigned)ceil_div(p->nrp, kAliasCW)), 256, alias_smem,
                                              st>>>(p->d_FG.p, p->d_F2.p, p->d_alias_rings.p, p->d_nphi.p, p->d_shift.p,
-                                                   p->nrings, p->lmax, p->nrp);
+                                                   p->nrings, p->lmax, p->nrp, p->d_mlim_ring.p);
                 } else if (p->n_alias_rings > 0) {
                     ring_alias_kernel<<<dim3(p->nrings, p->lmax + 1), 64, 0, st>>>(p->d_FG.p, p->d_F2.p, p->d_nphi.p,
                                                                                   p->d_shift.p, p->nrings, p->lmax, p->nrp);
@@ -1568,13 +1638,13 @@ int sht_alm2map(ShtPlan* p, const double* d_alm, double* d_out, cudaStream_t st)
     dim3 gs(p->lmax + 1, (unsigned)ceil_div(p->nhalf, 64), (unsigned)ceil_div(2 * p->nrp, 16 * nil));
     if (nil == 4)
         legendre_synthesis_kernel<4><<<gs, kT, 0, st>>>(d_alm, p->d_lam.p, p->nrings, p->nhalf, p->nhalf, p->lmax, p->nrp,
-                                                        p->d_FG.p, nullptr, p->d_nphi.p);
+                                                        p->d_FG.p, nullptr, p->d_nphi.p, nullptr);
     else if (nil == 2)
         legendre_synthesis_kernel<2><<<gs, kT, 0, st>>>(d_alm, p->d_lam.p, p->nrings, p->nhalf, p->nhalf, p->lmax, p->nrp,
-                                                        p->d_FG.p, nullptr, p->d_nphi.p);
+                                                        p->d_FG.p, nullptr, p->d_nphi.p, nullptr);
     else
         legendre_synthesis_kernel<1><<<gs, kT, 0, st>>>(d_alm, p->d_lam.p, p->nrings, p->nhalf, p->nhalf, p->lmax, p->nrp,
-                                                        p->d_FG.p, nullptr, p->d_nphi.p);
+                                                        p->d_FG.p, nullptr, p->d_nphi.p, nullptr);
     SFB_CUDA_OK(cudaGetLastError());
     p->launches = 1;
     return run_ring_synthesis(p, d_out, p->nrp, 0, d_out, st);

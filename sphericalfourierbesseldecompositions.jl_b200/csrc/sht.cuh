@@ -34,6 +34,10 @@ struct ShtPlan {
     DevBuf<double> d_a0;     // A f, the first-pass alm
     DevBuf<int> d_alias_rings;   // rings with nφ <= 2 lmax (both hemispheres): the alias pass visits only these
     int n_alias_rings = 0;
+    // m-cutoff (SFB_SHT_NO_MLIM disables): beyond mlim_ring[k] every λ_lm(θ_k) is < 1e-30
+    DevBuf<int> d_mlim_ring;     // [nhalf] north rings, monotone towards the equator
+    DevBuf<int> d_mlim_tile;     // [ceil(nhalf/64)] max over a synthesis tile of 64 rings
+    DevBuf<int> d_kbeg_of_m;     // [lmax+1] first ring chunk (multiple of 32) the Legendre analysis of m has to visit
     int kpolar = 0;          // north rings [0, kpolar) keep synthesis -> alias -> analysis in a Jacobi pass ...
     DevBuf<double> d_gram;   // ... the alias-free rings beyond act through Gram matrices K_m (see sht.cu)
     DevBuf<long long> d_gram_off;

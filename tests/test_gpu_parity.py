@@ -307,7 +307,7 @@ def test_stage1_pixel_space_refinement_path(monkeypatch, nside, lmax, nr):
     assert relerr(got, base) < 1e-11
 
 
-@pytest.mark.parametrize("flag", ["SFB_SHT_NO_GRAM", "SFB_ALIAS_OLD"])
+@pytest.mark.parametrize("flag", ["SFB_SHT_NO_GRAM", "SFB_ALIAS_OLD", "SFB_SHT_NO_MLIM"])
 @pytest.mark.parametrize("nside,lmax,nr", [(16, 24, 9), (32, 40, 3), (64, 100, 2)])
 def test_stage1_ring_space_variants(monkeypatch, flag, nside, lmax, nr):
     """The ring-Fourier Jacobi pass in its three forms must agree: Gram matrices for the alias-free rings + shared-memory
