@@ -389,7 +389,7 @@ def run_b200(args):
     except OSError:
         pass
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["kernels"]
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))["kernels"]
     except (OSError, KeyError):
         pass
     nl = np.asarray(wl.amodes.nmax_l, dtype=np.float64)
@@ -422,7 +422,12 @@ def run_b200(args):
     shells_here = -(-wl.nr // world)
     lmsize = (wl.LMAX + 1) * (wl.LMAX + 2) // 2
     s1_exec = 7 * 2.0 * lmsize * (2 * wl.amodes.nside) * 2 * shells_here
-    roofline_stage1 = {"ms": s1_ms, "bound": "tensor",
+    s1_traffic = None
+    if world == 1 and str(args.config) == "4" and traffic:
+        s1_traffic = sum(v["traffic_bytes"] for k, v in traffic.items()
+                         if k.startswith(("cap_analysis", "belt_analysis", "legendre_", "gram_apply", "ring_alias"))
+                         and not (k.startswith(("cap_analysis", "belt_analysis")) and "#" in k)) or None
+    roofline_stage1 = {"ms": s1_ms, "bound": "tensor", "traffic": s1_traffic,
                        "executed_flops": s1_exec, "achieved": s1_exec / (s1_ms * 1e-3) / 1e12 if s1_ms > 0 else None,
                        "peak": float(dmma[0]), "unit": "TFLOP/s",
                        "frac": s1_exec / (s1_ms * 1e-3) / 1e12 / float(dmma[0]) if s1_ms > 0 else None,
