@@ -48,6 +48,7 @@ struct CmixPlan {
     DevBuf<int> d_jt_order;           // column-tile visiting order of the fused pull (cmix_unpack_mirror)
     std::vector<int> h_jt_key;        // (column bounds, nranks, rank) the order was built for
     DevBuf<int> d_regz_blocks;        // per-launch block descriptors of the register-Z kernel (cmix_regz.cu)
+    DevBuf<int> d_regz_queue;         // block-queue heads of the persistent register-Z launches (one int per launch)
     size_t what_budget_bytes = size_t(2) << 30;
 
     // last-run stage times (ms): wl, w3j, what, block

@@ -85,12 +85,14 @@ struct RegzArgs {
     int col_lo, col_hi;
     int div2Lp1, interchange;
     int dbg;
+    int force_rowtab;      // SFB_REGZ_FULLDIAG: form all sub-tiles of the N' = N tiles
 };
 
-constexpr int kRegzU = 8;              // rows per lane per epilogue iteration
 constexpr int kRegzNoRow = 0x3FFFFF;   // packed row-table marker: row not in the shard
 
-__host__ __device__ constexpr int regz_tld(int AP) { return (AP % 16 == 8) ? AP : AP + 8; }  // ≡ 8 (mod 16)
+// per-warp tile staging stride ≡ 8 (mod 16): conflict-free 16-byte tile stores; the epilogue reads run along the diagonals
+// of the tile (the reference orders an l-block by n'-n, then n: src/modes.jl getidx), i.e. with stride TLD + 1 (odd)
+__host__ __device__ constexpr int regz_tld(int AP) { return (AP % 16 == 8) ? AP : AP + 8; }
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -98,95 +100,73 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
-template <int AT, int NT, int NW, int MINB, bool TMA>
-__global__ void __launch_bounds__(NW * 32, MINB) cmix_regz_kernel(RegzArgs p, const __grid_constant__ RegzTmaps tm) {
-    extern __shared__ __align__(128) double sm[];
+// Epilogue rows idx0 + 32u, u < U, of the current tile: M[row] = T[n][n'] (+ T[n'][n] off the N diagonal) read from the
+// warp's staged tile through the packed row table (the tile is already scaled: the factor c_L sits in Z)
+template <int U, int TLD>
+__device__ __forceinline__ void regz_store_rows(const double* Tw, const int* rowtab, int idx0, int nrows, double* Mc,
+                                                bool offdiag, int interchange) {
+    int pk[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int idx = idx0 + 32 * u;
+        pk[u] = (idx < nrows) ? rowtab[idx] : kRegzNoRow;
+    }
+    double v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int n = (pk[u] >> 22) & 31, n2 = (pk[u] >> 27) & 31;
+        const double A = Tw[n * TLD + n2], B = Tw[n2 * TLD + n];
+        v[u] = interchange ? B : (offdiag ? A + B : A);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int orow = pk[u] & kRegzNoRow;
+        if (orow != kRegzNoRow) Mc[orow] = v[u];
+    }
+}
+
+// T phase of one (N, N') tile: acc[i][j] = Σ_r' Z[i][.][r'] G_LN'[r'] G_l(8j+.)[r'].  UPPER: only the sub-tiles with i <= j
+// (T_NN is symmetric, so the N' = N tile needs no more)
+template <int AT, int NT, int S, bool UPPER>
+__device__ __forceinline__ void regz_tile(double (&acc)[AT][AT][2], const double (&Z)[AT][NT][2], const double* glS,
+                                          const double* glB) {
+#pragma unroll
+    for (int i = 0; i < AT; ++i)
+#pragma unroll
+        for (int j = 0; j < AT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll
+    for (int jt = 0; jt < NT; ++jt) {
+        const double2 s2 = *reinterpret_cast<const double2*>(glS + 8 * jt);
+        double2 gv[AT];
+#pragma unroll
+        for (int j = 0; j < AT; ++j) gv[j] = *reinterpret_cast<const double2*>(glB + j * 8 * S + 8 * jt);
+#pragma unroll
+        for (int i = 0; i < AT; ++i) {
+            const double a0 = Z[i][jt][0] * s2.x, a1 = Z[i][jt][1] * s2.y;
+#pragma unroll
+            for (int j = UPPER ? i : 0; j < AT; ++j) {
+                dmma884(acc[i][j], a0, gv[j].x);
+                dmma884(acc[i][j], a1, gv[j].y);
+            }
+        }
+    }
+}
+
+// Work of one warp on a staged (l, L) block: grab an N, Z phase, tiles N' >= N with their epilogue; repeat until the block's
+// N counter runs out.  Shared by the one-block-per-CTA kernel and the persistent kernel.
+template <int AT, int NT>
+__device__ __forceinline__ void regz_warp_work(const RegzArgs& p, const double* Gl, const double* GL, const double* Ws,
+                                               double* Tw, const int* rowtab, int* counter, int colell, int a, int b,
+                                               int nrows, bool rows_upper) {
     constexpr int AP = AT * 8;
-    constexpr int K = NT * 8;          // padded radial length
-    constexpr int S = K + 8;           // row stride ≡ 8 (mod 16): conflict-free 16-byte fragment loads
+    constexpr int K = NT * 8;
+    constexpr int S = K + 8;
     constexpr int TLD = regz_tld(AP);
-    constexpr int NTHR = NW * 32;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-
-    const int4 d0 = reinterpret_cast<const int4*>(p.blocks)[2 * blockIdx.x];
-    const int4 d1 = reinterpret_cast<const int4*>(p.blocks)[2 * blockIdx.x + 1];
-    const int rowell = d0.x, colell = d0.y, a = d0.z, b = d0.w;
-    const int r0 = d1.x, nrows = d1.y, widx = d1.z;
-    const int nrp = p.nrp, nmax = p.nmax;
-
-    const int nmaxe = nmax + (nmax & 1);   // even row count: every tile starts 128-byte aligned (TMA destination)
-    double* Gl = sm;                       // [AP][S]   G_ln[r], rows >= a zero
-    double* GL = Gl + AP * S;              // [nmaxe][S] G_LN[r]
-    double* Ws = GL + nmaxe * S;           // [K][S]    Ŵ_lL (symmetric)
-    double* Ts = Ws + K * S;               // [NW][AP][TLD]
-    int* rowtab = reinterpret_cast<int*>(Ts + NW * AP * TLD);  // [nrows] orow | n << 22 | n' << 27
-    int* counter = rowtab + nrows;
-
-    if (TMA) {
-        // ---- stage operands with three tensor copies (one elected thread), completion on an mbarrier -------------
-        __shared__ __align__(8) unsigned long long bar;
-        if (tid == 0) mbar_init(&bar, 1);
-        __syncthreads();
-        if (tid == 0) {
-            mbar_expect_tx(&bar, (unsigned)((AP + nmax + nrp) * S * sizeof(double)));
-            tma_load_2d(Gl, &tm.gl, 0, rowell * nmax, &bar);
-            tma_load_2d(GL, &tm.gL, 0, colell * nmax, &bar);
-            tma_load_2d(Ws, &tm.w, 0, widx * nrp, &bar);
-        }
-        if (nrp < K) {   // rows of Ŵ beyond nrp (the columns beyond nrp are zero-filled by the copy engine)
-            const int padc = K - nrp;
-            for (int x = tid; x < padc * K; x += NTHR) Ws[(nrp + x / K) * S + x % K] = 0.0;
-        }
-        for (int x = tid; x < nrows; x += NTHR) {
-            const int o = p.row_out[r0 + x];
-            rowtab[x] = (o < 0 ? kRegzNoRow : o) | (p.row_n[r0 + x] << 22) | (p.row_n2[r0 + x] << 27);
-        }
-        if (tid == 0) *counter = 0;
-        mbar_wait(&bar, 0);
-        __syncthreads();
-    } else {
-    // ---- stage operands: one round of 16-byte async copies, zero fill of the padding --------------------------
-    const int cpr = nrp / 2;  // 16-byte chunks per row
-    {
-        const double* src = p.G + (size_t)rowell * nmax * nrp;
-        for (int x = tid; x < a * cpr; x += NTHR) {
-            const int n = x / cpr, c = x - n * cpr;
-            cp_async16(Gl + n * S + 2 * c, src + (size_t)n * nrp + 2 * c);
-        }
-        src = p.G + (size_t)colell * nmax * nrp;
-        for (int x = tid; x < b * cpr; x += NTHR) {
-            const int n = x / cpr, c = x - n * cpr;
-            cp_async16(GL + n * S + 2 * c, src + (size_t)n * nrp + 2 * c);
-        }
-        src = p.What + (size_t)widx * nrp * nrp;
-        for (int x = tid; x < nrp * cpr; x += NTHR) {
-            const int r = x / cpr, c = x - r * cpr;
-            cp_async16(Ws + r * S + 2 * c, src + (size_t)r * nrp + 2 * c);
-        }
-    }
-    for (int x = tid; x < (AP - a) * K; x += NTHR) {
-        const int n = a + x / K, c = x % K;
-        Gl[n * S + c] = 0.0;
-    }
-    if (nrp < K) {
-        const int padc = K - nrp;
-        for (int x = tid; x < a * padc; x += NTHR) Gl[(x / padc) * S + nrp + x % padc] = 0.0;
-        for (int x = tid; x < b * padc; x += NTHR) GL[(x / padc) * S + nrp + x % padc] = 0.0;
-        for (int x = tid; x < nrp * padc; x += NTHR) Ws[(x / padc) * S + nrp + x % padc] = 0.0;
-        for (int x = tid; x < padc * K; x += NTHR) Ws[(nrp + x / K) * S + x % K] = 0.0;
-    }
-    for (int x = tid; x < nrows; x += NTHR) {
-        const int o = p.row_out[r0 + x];
-        rowtab[x] = (o < 0 ? kRegzNoRow : o) | (p.row_n[r0 + x] << 22) | (p.row_n2[r0 + x] << 27);
-    }
-    if (tid == 0) *counter = 0;
-    cp_async_wait_all();
-    __syncthreads();
-
-    }
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int nmax = p.nmax;
+    (void)a;
     const double inv4pi = 0.07957747154594767;
     const double scale = (p.div2Lp1 ? 1.0 : (2.0 * colell + 1.0)) * inv4pi;
-    double* Tw = Ts + warp * AP * TLD;
 
     for (;;) {
         int N = 0;
@@ -233,37 +213,36 @@ __global__ void __launch_bounds__(NW * 32, MINB) cmix_regz_kernel(RegzArgs p, co
             }
         }
 
+        // the factor c_L = (2L+1)/(4π) of the output rides on Z (once per N instead of once per stored element)
+#pragma unroll
+        for (int i = 0; i < AT; ++i)
+#pragma unroll
+            for (int jt = 0; jt < NT; ++jt) Z[i][jt][0] *= scale, Z[i][jt][1] *= scale;
+
         // ---- T phase over N' >= N -------------------------------------------------------------------------
         for (int N2 = N; N2 < b; ++N2) {
             const int col = __shfl_sync(0xffffffffu, mycol, N2 - N);
             if (col < 0) continue;  // warp-uniform
+            const bool offdiag = (N2 != N);
+            const bool upper_only = rows_upper && !offdiag && !p.interchange;
             double acc[AT][AT][2];
-#pragma unroll
-            for (int i = 0; i < AT; ++i)
-#pragma unroll
-                for (int j = 0; j < AT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
             const double* glS = GL + N2 * S + 2 * t;
             const double* glB = Gl + g * S + 2 * t;
-            if (!(p.dbg & 4)) {
+            if (p.dbg & 4) {
 #pragma unroll
-                for (int jt = 0; jt < NT; ++jt) {
-                    const double2 s2 = *reinterpret_cast<const double2*>(glS + 8 * jt);
-                    double2 gv[AT];
+                for (int i = 0; i < AT; ++i)
 #pragma unroll
-                    for (int j = 0; j < AT; ++j) gv[j] = *reinterpret_cast<const double2*>(glB + j * 8 * S + 8 * jt);
-#pragma unroll
-                    for (int i = 0; i < AT; ++i) {
-                        const double a0 = Z[i][jt][0] * s2.x, a1 = Z[i][jt][1] * s2.y;
-#pragma unroll
-                        for (int j = 0; j < AT; ++j) {
-                            dmma884(acc[i][j], a0, gv[j].x);
-                            dmma884(acc[i][j], a1, gv[j].y);
-                        }
-                    }
-                }
+                    for (int j = 0; j < AT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+            } else if (upper_only) {
+                regz_tile<AT, NT, S, true>(acc, Z, glS, glB);
+            } else {
+                regz_tile<AT, NT, S, false>(acc, Z, glS, glB);
             }
             if (p.dbg & 1) continue;
+            const size_t coff = p.colbase ? (size_t)p.colbase[col] : (size_t)col * p.ldM;
             // ---- epilogue: tile -> per-warp shared staging -> rows of this l-block ----------------------------
+            // (software-pipelining these row stores into the next tile's DMMA stream was tried: the extra live values spill
+            //  at the 168-register cap and the block kernel slows from 2.73 to 2.95 ms at cfg4)
 #pragma unroll
             for (int i = 0; i < AT; ++i)
 #pragma unroll
@@ -271,27 +250,23 @@ __global__ void __launch_bounds__(NW * 32, MINB) cmix_regz_kernel(RegzArgs p, co
                     *reinterpret_cast<double2*>(Tw + (i * 8 + g) * TLD + j * 8 + 2 * t) =
                         make_double2(acc[i][j][0], acc[i][j][1]);
             __syncwarp();
-            const size_t coff = p.colbase ? (size_t)p.colbase[col] : (size_t)col * p.ldM;
-            const bool offdiag = (N2 != N);
-            // eight rows per lane per iteration: all table and tile loads of an iteration are independent
-            for (int idx0 = lane; idx0 < nrows; idx0 += 32 * kRegzU) {
-                int pk[kRegzU];
-#pragma unroll
-                for (int u = 0; u < kRegzU; ++u) {
-                    const int idx = idx0 + 32 * u;
-                    pk[u] = (idx < nrows) ? rowtab[idx] : kRegzNoRow;
-                }
-                double v[kRegzU];
-#pragma unroll
-                for (int u = 0; u < kRegzU; ++u) {
-                    const int n = (pk[u] >> 22) & 31, n2 = (pk[u] >> 27) & 31;
-                    const double A = Tw[n * TLD + n2], B = Tw[n2 * TLD + n];
-                    v[u] = p.interchange ? B : (offdiag ? A + B : A);
-                }
-#pragma unroll
-                for (int u = 0; u < kRegzU; ++u) {
-                    const int orow = pk[u] & kRegzNoRow;
-                    if (orow != kRegzNoRow) p.M[coff + orow] = v[u] * scale;
+            // U rows per lane per pass, all table and tile loads of a pass independent; U follows the rows that are left
+            double* Mc = p.M + coff;
+            int idx0 = lane;
+            for (int left = nrows; left > 0;) {
+                const int per = (left + 31) >> 5;
+                if (per >= 7) {
+                    regz_store_rows<8, TLD>(Tw, rowtab, idx0, nrows, Mc, offdiag, p.interchange);
+                    idx0 += 256, left -= 256;
+                } else if (per >= 5) {
+                    regz_store_rows<6, TLD>(Tw, rowtab, idx0, nrows, Mc, offdiag, p.interchange);
+                    idx0 += 192, left -= 192;
+                } else if (per >= 3) {
+                    regz_store_rows<4, TLD>(Tw, rowtab, idx0, nrows, Mc, offdiag, p.interchange);
+                    idx0 += 128, left -= 128;
+                } else {
+                    regz_store_rows<2, TLD>(Tw, rowtab, idx0, nrows, Mc, offdiag, p.interchange);
+                    idx0 += 64, left -= 64;
                 }
             }
             __syncwarp();
@@ -299,6 +274,216 @@ __global__ void __launch_bounds__(NW * 32, MINB) cmix_regz_kernel(RegzArgs p, co
     }
 }
 
+template <int AT, int NT, int NW, int MINB, bool TMA>
+__global__ void __launch_bounds__(NW * 32, MINB) cmix_regz_kernel(RegzArgs p, const __grid_constant__ RegzTmaps tm) {
+    extern __shared__ __align__(128) double sm[];
+    constexpr int AP = AT * 8;
+    constexpr int K = NT * 8;          // padded radial length
+    constexpr int S = K + 8;           // row stride ≡ 8 (mod 16): conflict-free 16-byte fragment loads
+    constexpr int TLD = regz_tld(AP);
+    constexpr int NTHR = NW * 32;
+    const int tid = threadIdx.x, warp = tid >> 5;
+
+    const int4 d0 = reinterpret_cast<const int4*>(p.blocks)[2 * blockIdx.x];
+    const int4 d1 = reinterpret_cast<const int4*>(p.blocks)[2 * blockIdx.x + 1];
+    const int rowell = d0.x, colell = d0.y, a = d0.z, b = d0.w;
+    const int r0 = d1.x, nrows = d1.y, widx = d1.z;
+    const int nrp = p.nrp, nmax = p.nmax;
+
+    const int nmaxe = nmax + (nmax & 1);   // even row count: every tile starts 128-byte aligned (TMA destination)
+    double* Gl = sm;                       // [AP][S]   G_ln[r], rows >= a zero
+    double* GL = Gl + AP * S;              // [nmaxe][S] G_LN[r]
+    double* Ws = GL + nmaxe * S;           // [K][S]    Ŵ_lL (symmetric)
+    double* Ts = Ws + K * S;               // [NW][AP][TLD]
+    int* counter = reinterpret_cast<int*>(Ts + NW * AP * TLD);
+    int* rowtab = counter + 2;                                    // [nrows] orow | n << 22 | n' << 27
+
+    // every row (n, n') of this l-block has n <= n' (true of every table ClnnModes builds): the N' = N tile, which is symmetric
+    // and enters the output as is, then needs only its sub-tiles on and above the diagonal
+    bool rows_upper = !p.force_rowtab;
+    if (TMA) {
+        // ---- stage operands with three tensor copies (one elected thread), completion on an mbarrier -------------
+        __shared__ __align__(8) unsigned long long bar;
+        if (tid == 0) mbar_init(&bar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(&bar, (unsigned)((AP + nmax + nrp) * S * sizeof(double)));
+            tma_load_2d(Gl, &tm.gl, 0, rowell * nmax, &bar);
+            tma_load_2d(GL, &tm.gL, 0, colell * nmax, &bar);
+            tma_load_2d(Ws, &tm.w, 0, widx * nrp, &bar);
+        }
+        if (nrp < K) {   // rows of Ŵ beyond nrp (the columns beyond nrp are zero-filled by the copy engine)
+            const int padc = K - nrp;
+            for (int x = tid; x < padc * K; x += NTHR) Ws[(nrp + x / K) * S + x % K] = 0.0;
+        }
+        for (int x = tid; x < nrows; x += NTHR) {
+            const int o = p.row_out[r0 + x], n = p.row_n[r0 + x], n2 = p.row_n2[r0 + x];
+            rowtab[x] = (o < 0 ? kRegzNoRow : o) | (n << 22) | (n2 << 27);
+            rows_upper = rows_upper && (n <= n2);
+        }
+        if (tid == 0) *counter = 0;
+        mbar_wait(&bar, 0);
+        rows_upper = __syncthreads_and(rows_upper) != 0;
+    } else {
+    // ---- stage operands: one round of 16-byte async copies, zero fill of the padding --------------------------
+    const int cpr = nrp / 2;  // 16-byte chunks per row
+    {
+        const double* src = p.G + (size_t)rowell * nmax * nrp;
+        for (int x = tid; x < a * cpr; x += NTHR) {
+            const int n = x / cpr, c = x - n * cpr;
+            cp_async16(Gl + n * S + 2 * c, src + (size_t)n * nrp + 2 * c);
+        }
+        src = p.G + (size_t)colell * nmax * nrp;
+        for (int x = tid; x < b * cpr; x += NTHR) {
+            const int n = x / cpr, c = x - n * cpr;
+            cp_async16(GL + n * S + 2 * c, src + (size_t)n * nrp + 2 * c);
+        }
+        src = p.What + (size_t)widx * nrp * nrp;
+        for (int x = tid; x < nrp * cpr; x += NTHR) {
+            const int r = x / cpr, c = x - r * cpr;
+            cp_async16(Ws + r * S + 2 * c, src + (size_t)r * nrp + 2 * c);
+        }
+    }
+    for (int x = tid; x < (AP - a) * K; x += NTHR) {
+        const int n = a + x / K, c = x % K;
+        Gl[n * S + c] = 0.0;
+    }
+    if (nrp < K) {
+        const int padc = K - nrp;
+        for (int x = tid; x < a * padc; x += NTHR) Gl[(x / padc) * S + nrp + x % padc] = 0.0;
+        for (int x = tid; x < b * padc; x += NTHR) GL[(x / padc) * S + nrp + x % padc] = 0.0;
+        for (int x = tid; x < nrp * padc; x += NTHR) Ws[(x / padc) * S + nrp + x % padc] = 0.0;
+        for (int x = tid; x < padc * K; x += NTHR) Ws[(nrp + x / K) * S + x % K] = 0.0;
+    }
+    for (int x = tid; x < nrows; x += NTHR) {
+        const int o = p.row_out[r0 + x], n = p.row_n[r0 + x], n2 = p.row_n2[r0 + x];
+        rowtab[x] = (o < 0 ? kRegzNoRow : o) | (n << 22) | (n2 << 27);
+        rows_upper = rows_upper && (n <= n2);
+    }
+    if (tid == 0) *counter = 0;
+    cp_async_wait_all();
+    rows_upper = __syncthreads_and(rows_upper) != 0;
+    }
+    regz_warp_work<AT, NT>(p, Gl, GL, Ws, Ts + warp * AP * TLD, rowtab, counter, colell, a, b, nrows, rows_upper);
+}
+
+// ---- Persistent variant (default when the tensor maps encode and two operand stages fit in shared memory) ----------------
+// One CTA per SM walks a global queue of (l, L) blocks (heaviest first).  The operands of the NEXT block are staged by TMA
+// into the second buffer while the warps still work on the current one, and a warp that finds the current block's N
+// counter exhausted moves straight on to the next block: neither the staging latency nor the end-of-block imbalance
+// (N is a coarse work item: 9 % of the warp time at cfg4 with one block per CTA) idles a warp.  The last warp to leave a
+// stage refills it (row table by the warp, tiles by TMA); completion is an mbarrier per stage.
+struct RegzStage {
+    int desc[8];       // rowell, colell, a, b, r0, nrows, what_index, valid
+    int counter;       // next N of the block
+    int done;          // warps that have left the stage
+    int rows_upper;
+    int pad;
+};
+
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(a) : "memory");
+}
+
+template <int AT, int NT, int NW>
+__global__ void __launch_bounds__(NW * 32, 1) cmix_regz_persist_kernel(RegzArgs p, const __grid_constant__ RegzTmaps tm,
+                                                                       int nblocks, int max_rows, int* queue) {
+    extern __shared__ __align__(128) double sm[];
+    constexpr int AP = AT * 8;
+    constexpr int K = NT * 8;
+    constexpr int S = K + 8;
+    constexpr int TLD = regz_tld(AP);
+    constexpr int NTHR = NW * 32;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nrp = p.nrp, nmax = p.nmax;
+    const int nmaxe = nmax + (nmax & 1);
+    const int stage_doubles = (AP + nmaxe + K) * S;          // Gl | GL | Ws, every tile 128-byte aligned
+    double* Ts = sm + 2 * stage_doubles;                      // [NW][AP][TLD]
+    int* rowtabs = reinterpret_cast<int*>(Ts + NW * AP * TLD);   // [2][max_rows]
+    RegzStage* st = reinterpret_cast<RegzStage*>(rowtabs + 2 * max_rows + ((2 * max_rows) & 1));
+    __shared__ __align__(8) unsigned long long full[2];
+
+    auto tiles = [&](int s) { return sm + s * stage_doubles; };
+    // refill stage s with the next block of the queue (one warp; every other warp has left the stage)
+    auto produce = [&](int s) {
+        int idx = 0;
+        if (lane == 0) idx = atomicAdd(queue, 1);
+        idx = __shfl_sync(0xffffffffu, idx, 0);
+        if (idx >= nblocks) {
+            if (lane == 0) {
+                st[s].desc[7] = 0;
+                st[s].done = 0;
+                __threadfence_block();
+                mbar_arrive(&full[s]);
+            }
+            return;
+        }
+        const int4 d0 = reinterpret_cast<const int4*>(p.blocks)[2 * idx];
+        const int4 d1 = reinterpret_cast<const int4*>(p.blocks)[2 * idx + 1];
+        const int r0 = d1.x, nrows = d1.y;
+        int* rowtab = rowtabs + s * max_rows;
+        bool up = !p.force_rowtab;
+        for (int x = lane; x < nrows; x += 32) {
+            const int o = p.row_out[r0 + x], n = p.row_n[r0 + x], n2 = p.row_n2[r0 + x];
+            rowtab[x] = (o < 0 ? kRegzNoRow : o) | (n << 22) | (n2 << 27);
+            up = up && (n <= n2);
+        }
+        up = __all_sync(0xffffffffu, up);
+        __syncwarp();
+        if (lane == 0) {
+            st[s].desc[0] = d0.x, st[s].desc[1] = d0.y, st[s].desc[2] = d0.z, st[s].desc[3] = d0.w;
+            st[s].desc[4] = d1.x, st[s].desc[5] = d1.y, st[s].desc[6] = d1.z, st[s].desc[7] = 1;
+            st[s].counter = 0;
+            st[s].done = 0;
+            st[s].rows_upper = up ? 1 : 0;
+            __threadfence_block();
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+            double* T0 = tiles(s);
+            mbar_expect_tx(&full[s], (unsigned)((AP + nmax + nrp) * S * sizeof(double)));
+            tma_load_2d(T0, &tm.gl, 0, d0.x * nmax, &full[s]);
+            tma_load_2d(T0 + AP * S, &tm.gL, 0, d0.y * nmax, &full[s]);
+            tma_load_2d(T0 + (AP + nmaxe) * S, &tm.w, 0, d1.z * nrp, &full[s]);
+        }
+    };
+
+    if (tid == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+    }
+    // rows of Ŵ beyond nrp are never written by the copy engine (box = nrp rows): zero them once in both stages; so is the odd
+    // padding row of GL
+    for (int s = 0; s < 2; ++s) {
+        double* Ws = tiles(s) + (AP + nmaxe) * S;
+        for (int x = tid; x < (K - nrp) * S; x += NTHR) Ws[nrp * S + x] = 0.0;
+        double* GLp = tiles(s) + AP * S;
+        for (int x = tid; x < (nmaxe - nmax) * S; x += NTHR) GLp[nmax * S + x] = 0.0;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        produce(0);
+        produce(1);
+    }
+    for (int k = 0;; ++k) {
+        const int s = k & 1;
+        mbar_wait(&full[s], (unsigned)((k >> 1) & 1));
+        if (!st[s].desc[7]) break;
+        const int colell = st[s].desc[1], a = st[s].desc[2], b = st[s].desc[3], nrows = st[s].desc[5];
+        const bool rows_upper = st[s].rows_upper != 0;
+        double* T0 = tiles(s);
+        regz_warp_work<AT, NT>(p, T0, T0 + AP * S, T0 + (AP + nmaxe) * S, Ts + warp * AP * TLD, rowtabs + s * max_rows,
+                               &st[s].counter, colell, a, b, nrows, rows_upper);
+        __syncwarp();
+        int last = 0;
+        if (lane == 0) {
+            __threadfence_block();
+            last = (atomicAdd(&st[s].done, 1) == NW - 1) ? 1 : 0;
+            __threadfence_block();
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) produce(s);
+    }
+}
 
 // =============================================================================================
 // Mirror fill: for the output columns c in [c0, c1) (an l-aligned range) write every element below the block diagonal,
@@ -604,9 +789,20 @@ struct RegzLaunchCtx {
     const double* What;
     long long w_rows;      // rows of the Ŵ chunk buffer
     bool want_tma;
+    bool want_persist;
+    int* queue;            // zeroed head of this launch's block queue (persistent kernel)
+    int num_sms;
 };
 
-template <int AT, int NT, int NW, int MINB>
+template <int AT, int NT, int NW>
+static size_t regz_persist_smem_bytes(int nmax, int max_rows) {
+    constexpr int AP = AT * 8, K = NT * 8, S = K + 8;
+    const int nmaxe = nmax + (nmax & 1);
+    return sizeof(double) * (2 * (size_t)(AP + nmaxe + K) * S + (size_t)NW * AP * regz_tld(AP)) +
+           sizeof(int) * (2 * (size_t)max_rows + 2) + 2 * sizeof(RegzStage) + 64;
+}
+
+template <int AT, int NT, int NW, int MINB, int NWP>
 static int launch_regz(const RegzArgs& args, const RegzLaunchCtx& ctx, int nblocks, int nmax, int max_rows,
                        cudaStream_t stream) {
     constexpr int AP = AT * 8, S = NT * 8 + 8;
@@ -618,6 +814,15 @@ static int launch_regz(const RegzArgs& args, const RegzLaunchCtx& ctx, int nbloc
     if (tma)
         tma = encode_2d(&tm.gl, ctx.G, args.nrp, ctx.g_rows, S, AP) && encode_2d(&tm.gL, ctx.G, args.nrp, ctx.g_rows, S, nmax) &&
               encode_2d(&tm.w, ctx.What, args.nrp, ctx.w_rows, S, args.nrp);
+    const size_t psmem = regz_persist_smem_bytes<AT, NT, NWP>(nmax, max_rows);
+    if (tma && ctx.want_persist && ctx.queue && psmem <= 227 * 1024) {
+        SFB_CUDA_OK(cudaFuncSetAttribute(cmix_regz_persist_kernel<AT, NT, NWP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)psmem));
+        const int grid = std::min(nblocks, ctx.num_sms);
+        cmix_regz_persist_kernel<AT, NT, NWP><<<grid, NWP * 32, psmem, stream>>>(args, tm, nblocks, max_rows, ctx.queue);
+        SFB_CUDA_OK(cudaGetLastError());
+        return 0;
+    }
     if (tma) {
         SFB_CUDA_OK(cudaFuncSetAttribute(cmix_regz_kernel<AT, NT, NW, MINB, true>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -636,10 +841,10 @@ template <int NT>
 static int launch_regz_at(int AT, const RegzArgs& args, const RegzLaunchCtx& ctx, int nblocks, int nmax, int max_rows,
                           cudaStream_t stream) {
     switch (AT) {
-        case 1: return launch_regz<1, NT, 4, 4>(args, ctx, nblocks, nmax, max_rows, stream);
-        case 2: return launch_regz<2, NT, 6, 2>(args, ctx, nblocks, nmax, max_rows, stream);
-        case 3: return launch_regz<3, NT, 6, 2>(args, ctx, nblocks, nmax, max_rows, stream);
-        case 4: return launch_regz<4, NT, 8, 1>(args, ctx, nblocks, nmax, max_rows, stream);
+        case 1: return launch_regz<1, NT, 4, 4, 12>(args, ctx, nblocks, nmax, max_rows, stream);
+        case 2: return launch_regz<2, NT, 6, 2, 12>(args, ctx, nblocks, nmax, max_rows, stream);
+        case 3: return launch_regz<3, NT, 6, 2, 12>(args, ctx, nblocks, nmax, max_rows, stream);
+        case 4: return launch_regz<4, NT, 8, 1, 8>(args, ctx, nblocks, nmax, max_rows, stream);
         default: break;
     }
     set_error("cmix: nmax_l > 32 is not supported by this build");
@@ -694,6 +899,20 @@ int cmix_regz_run(CmixPlan* p, const std::vector<int>& blocks, const double* d_W
     args.div2Lp1 = div2Lp1;
     args.interchange = interchange;
     args.dbg = getenv("SFB_CMIX_DBG") ? atoi(getenv("SFB_CMIX_DBG")) : 0;
+    args.force_rowtab = getenv("SFB_REGZ_FULLDIAG") ? 1 : 0;
+    // persistent launches pull their blocks from a queue head each (zeroed here, in stream order)
+    const bool want_persist = getenv("SFB_REGZ_ONEBLOCK") == nullptr;
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        SFB_CUDA_OK(cudaGetDevice(&dev));
+        SFB_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    if (want_persist) {
+        SFB_TRY(p->d_regz_queue.alloc(8));
+        SFB_CUDA_OK(cudaMemsetAsync(p->d_regz_queue.p, 0, 8 * sizeof(int), stream));
+    }
+    int nlaunch = 0;
     int i0 = 0;
     while (i0 < nb) {
         const int AT = (sorted[8 * (size_t)i0 + 2] + 7) / 8;
@@ -701,8 +920,10 @@ int cmix_regz_run(CmixPlan* p, const std::vector<int>& blocks, const double* d_W
         while (i1 < nb && (sorted[8 * (size_t)i1 + 2] + 7) / 8 == AT) {
             max_rows = std::max(max_rows, sorted[8 * (size_t)i1 + 5]);
             const double b = sorted[8 * (size_t)i1 + 3];
-            // executed DMMA flops: Z = AT*NT*2NT DMMAs per N, T = AT*AT*2NT DMMAs per (N <= N') tile
-            *flops += 512.0 * (AT * NT * 2.0 * NT * b + AT * AT * 2.0 * NT * b * (b + 1) / 2);
+            // executed DMMA flops: Z = AT*NT*2NT DMMAs per N, T = 2NT DMMAs per sub-tile: AT*AT per (N < N') tile,
+            // AT(AT+1)/2 per N' = N tile
+            const double diag_sub = (interchange || args.force_rowtab) ? AT * AT : AT * (AT + 1) / 2;
+            *flops += 512.0 * (AT * NT * 2.0 * NT * b + 2.0 * NT * (AT * AT * b * (b - 1) / 2 + diag_sub * b));
             ++i1;
         }
         args.blocks = p->d_regz_blocks.p + 8 * (size_t)i0;
@@ -712,6 +933,10 @@ int cmix_regz_run(CmixPlan* p, const std::vector<int>& blocks, const double* d_W
         ctx.What = d_What;
         ctx.w_rows = (long long)(p->d_What.n / (size_t)p->nrp);
         ctx.want_tma = getenv("SFB_REGZ_CPASYNC") == nullptr;
+        ctx.want_persist = want_persist && nlaunch < 8;
+        ctx.queue = want_persist ? p->d_regz_queue.p + nlaunch : nullptr;
+        ctx.num_sms = num_sms;
+        ++nlaunch;
         if (NT == 4)
             SFB_TRY(launch_regz_at<4>(AT, args, ctx, i1 - i0, p->nmax, max_rows, stream));
         else

@@ -40,9 +40,43 @@ void run(int blocks_per_sm, int warps, int sms, double* d) {
     printf("acc=%2d mul=%d blocks/SM=%d warps/blk=%d (warps/SMSP=%.1f): %6.2f TFLOP/s\n", NACC, (int)MUL, blocks_per_sm, warps,
            blocks_per_sm * warps / 4.0, fl / (best * 1e-3) / 1e12);
 }
+// which hardware warp slot (%warpid; slot % 4 = SM sub-partition) the warps of co-resident CTAs get
+__global__ void slot_map(int* out, int warps) {
+    extern __shared__ double pad[];
+    unsigned sm, wid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+    asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+    if ((threadIdx.x & 31) == 0) {
+        int* o = out + 3 * (blockIdx.x * warps + (threadIdx.x >> 5));
+        o[0] = sm; o[1] = wid; o[2] = blockIdx.x;
+    }
+    long long t0 = clock64();
+    while (clock64() - t0 < 2000000) {}
+}
+static void report_slots(int sms, int warps, int regs_smem_kb) {
+    int* d; int n = sms * 2 * warps;
+    cudaMalloc(&d, n * 3 * sizeof(int));
+    cudaFuncSetAttribute(slot_map, cudaFuncAttributeMaxDynamicSharedMemorySize, regs_smem_kb * 1024);
+    slot_map<<<sms * 2, warps * 32, regs_smem_kb * 1024>>>(d, warps);
+    int* h = new int[n * 3];
+    cudaMemcpy(h, d, n * 3 * sizeof(int), cudaMemcpyDeviceToHost);
+    int sm0 = h[0];
+    printf("warp slots on SM %d (2 CTAs x %d warps, %d KB smem each):", sm0, warps, regs_smem_kb);
+    int cnt[4] = {0, 0, 0, 0};
+    for (int i = 0; i < n; ++i) if (h[3 * i] == sm0) { printf(" cta%d:%d", h[3 * i + 2], h[3 * i + 1]); cnt[h[3 * i + 1] & 3]++; }
+    printf("\n  warps per sub-partition: %d %d %d %d\n", cnt[0], cnt[1], cnt[2], cnt[3]);
+    cudaFree(d); delete[] h;
+}
 int main() {
     int sms; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     double* d; cudaMalloc(&d, 8);
+    report_slots(sms, 6, 93);
+    report_slots(sms, 4, 60);
+    // K3's shape (6 warps x 2 CTAs: 4/4/2/2 warps per sub-partition) against balanced shapes with 12 warps per SM
+    for (int w : {6, 12, 3}) for (int b : {1, 2, 4}) {
+        if (w * b > 16) continue;
+        run<9, false>(b, w, sms, d); run<9, true>(b, w, sms, d);
+    }
     for (int w : {4, 8}) for (int b : {1, 2, 4}) {
         run<1, false>(b, w, sms, d); run<2, false>(b, w, sms, d); run<4, false>(b, w, sms, d);
         run<9, false>(b, w, sms, d); run<18, false>(b, w, sms, d); run<18, true>(b, w, sms, d);
