@@ -293,12 +293,13 @@ def run_b200(args):
     for _ in range(args.warmup):
         step()
     barrier()
-    stage_ms = {"stage1": [], "wl": [], "what": [], "block": [], "fill": [], "stage1_incl_gather": [], "stage23": []}
+    stage_ms = {"stage1": [], "wl": [], "what": [], "block": [], "fill": [], "k3": [], "stage1_incl_gather": [], "stage23": []}
     launches = [0]
 
     def collect():
         tim = _lib.timings()
-        for k, key in (("stage1", "stage1_ms"), ("wl", "wl_ms"), ("what", "what_ms"), ("block", "block_ms"), ("fill", "fill_ms")):
+        for k, key in (("stage1", "stage1_ms"), ("wl", "wl_ms"), ("what", "what_ms"), ("block", "block_ms"), ("fill", "fill_ms"),
+                       ("k3", "k3_ms")):
             stage_ms[k].append(tim[key])
         torch.cuda.synchronize()
         stage_ms["stage1_incl_gather"].append(evs[0].elapsed_time(evs[1]))
@@ -380,7 +381,9 @@ def run_b200(args):
         pb.close()
 
     # ---- roofline of the dominant kernel (measured live: CUDA events on the launching stream, inside the lib) ----
-    kern_ms = sm["block"] - sm["fill"]     # the DMMA block kernel(s) alone; block_ms includes the mirror-fill pass
+    # the DMMA block kernel launches alone (block_ms adds the part of the mirror fill that is not hidden under them; at N = 1
+    # the fill of an l-chunk runs on a second stream under the block kernel of the next chunk, and its launches sum to fill_ms)
+    kern_ms = sm["k3"]
     dmma = np.zeros(1)
     _lib.check(lib.sfb_probe_dmma_tflops(_lib.ptr(dmma)))
     peaks, traffic = {}, {}
@@ -416,7 +419,10 @@ def run_b200(args):
     fill_ms, s1_ms = sm["fill"], sm["stage1"]
     roofline_fill = {"kernel": "cmix_mirror_fill_kernel", "ms": fill_ms, "bound": "hbm",
                      "achieved": (8.0 * n * n / (fill_ms * 1e-3) / 1e9) if fill_ms > 0 else None, "peak": hbm, "unit": "GB/s",
-                     "frac": (8.0 * n * n / (fill_ms * 1e-3) / 1e9 / hbm) if (fill_ms > 0 and hbm) else None}
+                     "frac": (8.0 * n * n / (fill_ms * 1e-3) / 1e9 / hbm) if (fill_ms > 0 and hbm) else None,
+                     "exposed_ms": sm["block"] - sm["k3"],
+                     "note": "ms = sum of the fill launches (second stream, each under the block kernel of the next l-chunk, "
+                             "so slower than alone); exposed_ms = what the step still waits for after its last block kernel"}
     # useful Legendre-GEMM flops of one map2alm(niter=3) on this rank's shells: 7 passes (4 analyses + 3 syntheses) of
     # Σ_m [l x ring] x [ring x 2 shells] with north/south rings folded: 2 · lmsize · 2nside · 2·shells per pass
     shells_here = -(-wl.nr // world)

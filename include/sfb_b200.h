@@ -56,8 +56,10 @@ int32_t sfb_host_free(void* ptr);
 int32_t sfb_host_register(void* ptr, int64_t bytes);
 int32_t sfb_host_unregister(void* ptr);
 /* times (ms, CUDA events) of the last call on this thread's plans:
- *   [0] stage 1 total, [1] W_{L1} build, [2] 3j table, [3] Ŵ_{ℓL} build, [4] block kernel,
- *   [5] executed DMMA flops of [4], [6] kernel launches of the last power_win_mix, [7] binned products */
+ *   [0] stage 1 total, [1] W_{L1} build, [2] mirror fill, [3] Ŵ_{ℓL} build, [4] block kernel + exposed fill,
+ *   [5] executed DMMA flops of [4], [6] kernel launches of the last power_win_mix, [7] binned products,
+ *   [8] block-kernel launches alone ([4] = [8] + the mirror-fill time not hidden under block kernels; [2] = the mirror
+ *       fill launches, which run on a second stream under the block kernels of the next l-chunk) */
 int32_t sfb_get_timings(double* out, int32_t n);
 
 /* FP64 tensor-pipe (DMMA) throughput of the current device in TFLOP/s, measured by an in-register probe:

@@ -108,7 +108,7 @@ def ptr(a):
 
 def timings():
     import numpy as np
-    out = np.zeros(8)
-    check(load().sfb_get_timings(ptr(out), 8))
-    keys = ["stage1_ms", "wl_ms", "fill_ms", "what_ms", "block_ms", "block_flops", "launches", "binned_ms"]
+    out = np.zeros(9)
+    check(load().sfb_get_timings(ptr(out), 9))
+    keys = ["stage1_ms", "wl_ms", "fill_ms", "what_ms", "block_ms", "block_flops", "launches", "binned_ms", "k3_ms"]
     return dict(zip(keys, out.tolist()))

@@ -48,6 +48,21 @@ __global__ void nonfinite_flag_2d_kernel(const double* __restrict__ x, long long
     if (bad) atomicOr(flag, 1);
 }
 
+// Device scratch of the binned products, kept per device across calls: cudaMalloc / cudaFree of the 246 MB result and the
+// binning tables on every call made the host-pointer binned call erratic (10 - 700 ms for the same work at cfg4).
+struct BinScratch {
+    DevBuf<double> d_N, d_wval, d_vval;
+    DevBuf<int> d_wptr, d_wcol, d_vptr, d_vrow;
+};
+static int bin_scratch(BinScratch** out) {
+    static BinScratch scratch[64];
+    int dev = 0;
+    SFB_CUDA_OK(cudaGetDevice(&dev));
+    SFB_REQUIRE(dev >= 0 && dev < 64, "binned_product: device index out of range");
+    *out = &scratch[dev];
+    return 0;
+}
+
 int binned_product_to_host(const double* d_M, int64_t n, const int64_t* wt_colptr, const int64_t* wt_rowval,
                            const double* wt_nzval, int64_t LNN1, const int64_t* v_colptr, const int64_t* v_rowval,
                            const double* v_nzval, int64_t LNN2, double* N_out, float* ms) {
@@ -59,7 +74,9 @@ int binned_product_to_host(const double* d_M, int64_t n, const int64_t* wt_colpt
         if (ms) *ms = 0;
         return 0;
     }
-    DevBuf<double> d_N;
+    BinScratch* bs = nullptr;
+    SFB_TRY(bin_scratch(&bs));
+    DevBuf<double>& d_N = bs->d_N;
     SFB_TRY(d_N.alloc((size_t)LNN1 * LNN2));
     SFB_TRY(binned_product_device(d_M, n, wt_colptr, wt_rowval, wt_nzval, LNN1, v_colptr, v_rowval, v_nzval, LNN2, d_N.p,
                                   LNN1, ms));
@@ -81,8 +98,10 @@ int binned_product_device(const double* d_M, int64_t n, const int64_t* wt_colptr
         if (ms) *ms = 0;
         return 0;
     }
-    DevBuf<int> d_wptr, d_wcol, d_vptr, d_vrow;
-    DevBuf<double> d_wval, d_vval;
+    BinScratch* bs = nullptr;
+    SFB_TRY(bin_scratch(&bs));
+    DevBuf<int>&d_wptr = bs->d_wptr, &d_wcol = bs->d_wcol, &d_vptr = bs->d_vptr, &d_vrow = bs->d_vrow;
+    DevBuf<double>&d_wval = bs->d_wval, &d_vval = bs->d_vval;
     if (wt_colptr) {
         // CSC (columns i) -> CSR (rows I), keeping ascending i within a row like the reference's nzind order
         SFB_REQUIRE(wt_rowval && wt_nzval, "w̃: null rowval/nzval");

@@ -36,7 +36,7 @@ struct Trace {
 };
 
 static std::mutex g_mutex;  // one call at a time (the Julia side calls from one task and blocks)
-static double g_times[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+static double g_times[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 // plans whose last (device-resident, asynchronous) run has unread timing events: resolved by sfb_get_timings
 static ShtPlan* g_pend_sht = nullptr;
 static CmixPlan* g_pend_cmix = nullptr;
@@ -143,6 +143,7 @@ static void record_cmix_times(const CmixPlan* p) {
     g_times[4] = p->t_block;
     g_times[5] = p->flops_executed;
     g_times[6] += p->launches;
+    g_times[8] = p->t_k3;
 }
 
 // Device-resident entry points: run without a host sync and leave the timing events to sfb_get_timings.
@@ -194,7 +195,7 @@ static int get_ws(Workspace** out) {
 static bool mirror_enabled() { return getenv("SFB_NO_MIRROR") == nullptr; }
 
 struct CmixTimes {
-    float wl = 0, what = 0, block = 0, fill = 0;
+    float wl = 0, what = 0, block = 0, fill = 0, k3 = 0;
     double flops = 0;
     int launches = 0;
     void add(const CmixPlan* p) {
@@ -202,6 +203,7 @@ struct CmixTimes {
         what += p->t_what;
         block += p->t_block;
         fill += p->t_fill;
+        k3 += p->t_k3;
         flops += p->flops_executed;
         launches += p->launches;
     }
@@ -210,6 +212,7 @@ struct CmixTimes {
         p->t_what = what;
         p->t_block = block;
         p->t_fill = fill;
+        p->t_k3 = k3;
         p->flops_executed = flops;
         p->launches = launches;
     }
@@ -641,7 +644,7 @@ static int md_run(MdJob& J) {
         g_times[6] = std::max(g_times[6], (double)J.launches1[d]);
     }
     if (J.want_cmix) {
-        double t[5] = {0, 0, 0, 0, 0}, launches = 0;
+        double t[6] = {0, 0, 0, 0, 0, 0}, launches = 0;
         for (int d = 0; d < n; ++d) {
             const CmixPlan* p = J.cplan[d];
             if (!p || (J.bin ? J.bcol1[d] <= J.bcol0[d] : J.col[d + 1] <= J.col[d])) continue;
@@ -650,6 +653,7 @@ static int md_run(MdJob& J) {
             t[2] = std::max<double>(t[2], p->t_what);
             t[3] = std::max<double>(t[3], p->t_block);
             t[4] += p->flops_executed;
+            t[5] = std::max<double>(t[5], p->t_k3);
             launches = std::max<double>(launches, p->launches);
         }
         g_times[1] = t[0];
@@ -657,6 +661,7 @@ static int md_run(MdJob& J) {
         g_times[3] = t[2];
         g_times[4] = t[3];
         g_times[5] = t[4];
+        g_times[8] = t[5];
         g_times[6] += launches;
         g_times[7] = 0;
         for (int d = 0; d < n; ++d) g_times[7] = std::max(g_times[7], J.t_bin[d]);
@@ -768,7 +773,7 @@ int32_t sfb_get_timings(double* out, int32_t n) {
         g_times[6] = launches;
         g_pend_cmix = nullptr;
     }
-    for (int i = 0; i < n && i < 8; ++i) out[i] = g_times[i];
+    for (int i = 0; i < n && i < 9; ++i) out[i] = g_times[i];
     return 0;
 }
 

@@ -275,12 +275,18 @@ __global__ void __launch_bounds__(128, 3) what_build_dmma_kernel(const double* _
     const int n2 = nrp * nrp;
     const int hlo = (L1lo - par) >> 1, hhi = (L1hi - par) >> 1;
     const int nks = (hhi - hlo + 4) / 4;   // k-steps of four L1 values (h, h+1, h+2, h+3)
-    // row tiles that hold at least one wanted L
+    // row tiles that hold at least one wanted L, and the k-steps that meet their band: the eight rows of a tile span
+    // L1 in [min |l-L|, max l+L], l + 8 values of the right parity, against l + 32 for the union over the CTA's rows
     bool live[4];
+    int kslo[4], kshi[4];
 #pragma unroll
     for (int mt = 0; mt < 4; ++mt) {
         const int Lf = base + 2 * (mt * 8), Ll = min(base + 2 * (mt * 8 + 7), lmax - ((lmax - base) & 1));
         live[mt] = (Lf <= lmax) && !(mirror && Ll < ell) && !(Ll < Llo || Lf > Lhi);
+        const int dmin = (ell >= Lf && ell <= Ll) ? ((ell - Lf) & 1) : min(abs(ell - Lf), abs(ell - Ll));
+        const int h0 = (dmin - par) >> 1, h1 = (ell + Ll - par) >> 1;      // wsm columns of the tile's band
+        kslo[mt] = max(0, (h0 - hlo) / 4);
+        kshi[mt] = min(nks - 1, (h1 - hlo) / 4);
     }
     // each warp sweeps kWhatEPW column tiles of 64 e's: the 3j tile in shared memory is built once per 1024 e's
     for (int ep = 0; ep < kWhatEPW; ++ep) {
@@ -306,7 +312,7 @@ __global__ void __launch_bounds__(128, 3) what_build_dmma_kernel(const double* _
             const double* arow = wsm + g * SW + hlo + 4 * ks + t;
 #pragma unroll
             for (int mt = 0; mt < 4; ++mt) {
-                if (!live[mt]) continue;
+                if (!live[mt] || ks < kslo[mt] || ks > kshi[mt]) continue;
                 const double a = arow[mt * 8 * SW];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) dmma884(acc[mt][j], a, bcur[j]);
@@ -827,6 +833,8 @@ int cmix_plan_create(CmixPlan** out, const int64_t* lnn, int64_t lnnsize, int64_
 void cmix_plan_destroy(CmixPlan* p) {
     if (p) {
         for (auto& e : p->pend_ev) cudaEventDestroy(e);
+        for (auto& e : p->pend_fill_ev) cudaEventDestroy(e);
+        if (p->side_stream) cudaStreamDestroy(p->side_stream);
     }
     delete p;
 }
@@ -945,8 +953,51 @@ int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp
     double flops = 0.0;
     const int ngroups = 2 * (int)ceil_div(lmax + 1, 2 * kWhatGroup);
     std::vector<int> ell_list_all;  // device ell_list is filled per launch at distinct offsets
-    for (int ell0 = 0; ell0 <= lmax; ell0 += chunk) {
-        const int ell1 = std::min(lmax + 1, ell0 + chunk);
+    // l-chunks of the Ŵ memory budget.  SFB_FILL_OVERLAP=1 (mirror mode with the register-Z kernel; an ablation that LOST, off
+    // by default): the block kernel of a chunk runs in a few sub-chunks of equal cost and the mirror fill of sub-chunk i
+    // (HBM-bound, on a second stream) runs under the block kernel of sub-chunk i+1 — the fill of the columns of sub-chunk i
+    // reads only blocks (l in sub-chunk i, L >= l) and writes below the block diagonal, where no block kernel writes.
+    // Measured at cfg4: the fill disappears from the critical path (0.78 -> 0.15 ms exposed) but the block kernels, whose
+    // operand tiles stream from HBM, slow from 2.73 to 3.5 ms under the fill's traffic: 5.96 -> 6.09 ms per step.
+    const bool overlap_fill = regz && mirror && getenv("SFB_FILL_OVERLAP") != nullptr;
+    std::vector<std::pair<int, int>> lchunks;
+    for (int ell0 = 0; ell0 <= lmax; ell0 += chunk) lchunks.emplace_back(ell0, std::min(lmax + 1, ell0 + chunk));
+    std::vector<char> sub_end(lmax + 1, 0);   // 1: a block-kernel sub-chunk ends after this l
+    if (overlap_fill) {
+        int K = getenv("SFB_FILL_CHUNKS") ? atoi(getenv("SFB_FILL_CHUNKS")) : 4;
+        K = std::max(1, std::min(K, 16));
+        std::vector<double> cl(lmax + 1, 0.0);
+        double total = 0;
+        for (int l = 0; l <= lmax; ++l) {
+            if (!ell_used[l] || p->a_of_ell[l] == 0) continue;
+            const double ap = 8.0 * ((p->a_of_ell[l] + 7) / 8);
+            for (int L = l; L <= lmax; ++L) {
+                if (!L_used[L]) continue;
+                const double b = p->a_of_ell[L];
+                cl[l] += 2.0 * ap * nrp * nrp * b + ap * ap * nrp * b * (b + 1);
+            }
+            total += cl[l];
+        }
+        double acc = 0;
+        int made = 0;
+        for (int l = 0; l < lmax; ++l) {
+            acc += cl[l];
+            if (made < K - 1 && acc >= total * (made + 1) / K) sub_end[l] = 1, ++made;
+        }
+    }
+    // output index range of every l (mirror mode: the table is l-sorted, the rows of an l are consecutive)
+    std::vector<int> out_lo(lmax + 1, 1 << 30), out_hi(lmax + 1, -1);
+    if (overlap_fill)
+        for (int l = 0; l <= lmax; ++l)
+            for (int s = p->ell_ptr[l]; s < p->ell_ptr[l + 1]; ++s)
+                if (row_out[s] >= 0) {
+                    out_lo[l] = std::min(out_lo[l], row_out[s]);
+                    out_hi[l] = std::max(out_hi[l], row_out[s] + 1);
+                }
+    if (overlap_fill && !p->side_stream) SFB_CUDA_OK(cudaStreamCreateWithFlags(&p->side_stream, cudaStreamNonBlocking));
+    std::vector<cudaEvent_t> fill_ev;
+    for (const auto& lc : lchunks) {
+        const int ell0 = lc.first, ell1 = lc.second;
         bool any = false;
         for (int l = ell0; l < ell1; ++l) any = any || (ell_used[l] && p->a_of_ell[l] > 0);
         if (!any) continue;
@@ -983,16 +1034,50 @@ int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp
         args.ell0 = ell0;
         chunk_fill = 0;  // the previous l-chunk's kernels have completed (event sync below)
         if (regz) {
-            std::vector<int> blocks;
-            for (int l : wells)
-                for (int L = upper ? l : 0; L <= lmax; ++L) {
-                    if (!L_used[L] || p->a_of_ell[L] == 0) continue;
-                    const int desc[8] = {l, L, p->a_of_ell[l], p->a_of_ell[L], p->ell_ptr[l],
-                                         p->ell_ptr[l + 1] - p->ell_ptr[l], (l - ell0) * (lmax + 1) + L, 0};
-                    blocks.insert(blocks.end(), desc, desc + 8);
+            // sub-chunks of this memory chunk (one, unless the fill is overlapped)
+            size_t w0 = 0;
+            while (w0 < wells.size()) {
+                size_t w1 = w0;
+                while (w1 < wells.size()) {
+                    const int l = wells[w1++];
+                    bool cut = false;
+                    for (int q = l; q < (w1 < wells.size() ? wells[w1] : l + 1) && !cut; ++q) cut = sub_end[q] != 0;
+                    if (cut) break;
                 }
-            SFB_TRY(cmix_regz_run(p, blocks, p->d_What.p, div2Lp1, interchange, col_lo, col_hi, d_M, ldM,
-                                  upper_packed ? p->d_colbase.p + col_lo : nullptr, stream, &flops, &p->launches));
+                std::vector<int> blocks;
+                for (size_t wi = w0; wi < w1; ++wi) {
+                    const int l = wells[wi];
+                    for (int L = upper ? l : 0; L <= lmax; ++L) {
+                        if (!L_used[L] || p->a_of_ell[L] == 0) continue;
+                        const int desc[8] = {l, L, p->a_of_ell[l], p->a_of_ell[L], p->ell_ptr[l],
+                                             p->ell_ptr[l + 1] - p->ell_ptr[l], (l - ell0) * (lmax + 1) + L, 0};
+                        blocks.insert(blocks.end(), desc, desc + 8);
+                    }
+                }
+                SFB_TRY(cmix_regz_run(p, blocks, p->d_What.p, div2Lp1, interchange, col_lo, col_hi, d_M, ldM,
+                                      upper_packed ? p->d_colbase.p + col_lo : nullptr, stream, &flops, &p->launches));
+                if (overlap_fill) {
+                    int c0 = 1 << 30, c1 = -1;
+                    for (size_t wi = w0; wi < w1; ++wi)
+                        c0 = std::min(c0, out_lo[wells[wi]]), c1 = std::max(c1, out_hi[wells[wi]]);
+                    if (c1 > c0) {
+                        cudaEvent_t kd, f0, f1;
+                        SFB_CUDA_OK(cudaEventCreateWithFlags(&kd, cudaEventDisableTiming));
+                        SFB_CUDA_OK(cudaEventCreate(&f0));
+                        SFB_CUDA_OK(cudaEventCreate(&f1));
+                        SFB_CUDA_OK(cudaEventRecord(kd, stream));
+                        SFB_CUDA_OK(cudaStreamWaitEvent(p->side_stream, kd, 0));
+                        SFB_CUDA_OK(cudaEventDestroy(kd));   // released once the wait has been satisfied
+                        SFB_CUDA_OK(cudaEventRecord(f0, p->side_stream));
+                        SFB_TRY(cmix_mirror_fill(p, c0, c1, div2Lp1, interchange, d_M, ldM, p->side_stream));
+                        p->launches++;
+                        SFB_CUDA_OK(cudaEventRecord(f1, p->side_stream));
+                        fill_ev.push_back(f0);
+                        fill_ev.push_back(f1);
+                    }
+                }
+                w0 = w1;
+            }
         }
         for (int AT = regz ? 0 : p->amax_tiles; AT >= 1; --AT) {
             std::vector<int> ells;
@@ -1054,10 +1139,16 @@ int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp
     p->t_fill = 0;
     if (regz && mirror) {
         SFB_CUDA_OK(cudaEventRecord(ev[2], stream));
-        SFB_TRY(cmix_mirror_fill(p, row_lo, row_hi, div2Lp1, interchange, d_M, ldM, stream));
-        p->launches++;
+        if (overlap_fill) {
+            if (!fill_ev.empty()) SFB_CUDA_OK(cudaStreamWaitEvent(stream, fill_ev.back(), 0));   // join the fill stream
+        } else {
+            SFB_TRY(cmix_mirror_fill(p, row_lo, row_hi, div2Lp1, interchange, d_M, ldM, stream));
+            p->launches++;
+        }
         SFB_CUDA_OK(cudaEventRecord(ev[3], stream));
     }
+    for (auto& e : p->pend_fill_ev) cudaEventDestroy(e);
+    p->pend_fill_ev = fill_ev;
     p->flops_executed = flops;
     p->pend_ev.clear();
     p->pend_ev.push_back(ev[0]);
@@ -1095,14 +1186,29 @@ int cmix_resolve_times(CmixPlan* p) {
                 t_what += a_ms;
                 t_block += b_ms;
             }
+            p->t_k3 = t_block;
             if (p->pend_fill) {
-                cudaEventElapsedTime(&p->t_fill, ev[n - 2], ev[n - 1]);
-                t_block += p->t_fill;
+                // serial fill: the span between the last two events; overlapped fill: that span is only the exposed tail
+                // (block kernels done, fill stream still draining) and t_fill sums the fill launches of the side stream
+                float tail = 0;
+                cudaEventElapsedTime(&tail, ev[n - 2], ev[n - 1]);
+                t_block += tail;
+                p->t_fill = tail;
+                if (!p->pend_fill_ev.empty()) {
+                    p->t_fill = 0;
+                    for (size_t i = 0; i + 1 < p->pend_fill_ev.size(); i += 2) {
+                        float f = 0;
+                        cudaEventElapsedTime(&f, p->pend_fill_ev[i], p->pend_fill_ev[i + 1]);
+                        p->t_fill += f;
+                    }
+                }
             }
         }
     }
     for (auto& e : ev) cudaEventDestroy(e);
     ev.clear();
+    for (auto& e : p->pend_fill_ev) cudaEventDestroy(e);
+    p->pend_fill_ev.clear();
     p->pending = false;
     p->t_what = t_what;
     p->t_block = t_block;

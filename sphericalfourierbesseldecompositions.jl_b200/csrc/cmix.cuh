@@ -52,7 +52,10 @@ struct CmixPlan {
     size_t what_budget_bytes = size_t(2) << 30;
 
     // last-run stage times (ms): wl, w3j, what, block
-    float t_wl = 0, t_fill = 0, t_what = 0, t_block = 0;  // t_block includes t_fill
+    float t_wl = 0, t_fill = 0, t_what = 0, t_block = 0;  // t_block = t_k3 + the fill time not hidden under block kernels
+    float t_k3 = 0;                                        // block-kernel launches alone
+    cudaStream_t side_stream = nullptr;                    // mirror fills of finished l-chunks run here
+    std::vector<cudaEvent_t> pend_fill_ev;                 // (begin, end) per fill launch of the side stream
     double flops_executed = 0;
     int launches = 0;
     // async_times: cmix_run records its timing events and returns without a host sync; cmix_resolve_times fills t_*.

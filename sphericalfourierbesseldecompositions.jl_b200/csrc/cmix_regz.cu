@@ -497,10 +497,18 @@ constexpr int kFillT = 64;  // tile edge: 16 independent 8-byte loads in flight 
 template <bool VEC>
 __global__ void __launch_bounds__(256) cmix_mirror_fill_kernel(double* __restrict__ M, long long ld, int n, int c0,
                                                                int c1, int rbase, const int* __restrict__ es,
-                                                               int div2Lp1, int interchange, int sorted) {
+                                                               int div2Lp1, int interchange, int sorted, int tri) {
     __shared__ double tile[kFillT][kFillT + 1];
     __shared__ int esr[kFillT], esc[kFillT];
-    const int cb = c0 + blockIdx.x * kFillT, rb = rbase + blockIdx.y * kFillT;
+    int bx = blockIdx.x, by = blockIdx.y;
+    if (tri) {   // 1-D grid over the tiles on and below the tile diagonal only (by >= bx): no empty CTAs
+        const unsigned k = blockIdx.x;
+        by = (int)((sqrtf(8.0f * (float)k + 1.0f) - 1.0f) * 0.5f);
+        while ((unsigned)(by + 1) * (unsigned)(by + 2) / 2 <= k) ++by;
+        while ((unsigned)by * (unsigned)(by + 1) / 2 > k) --by;
+        bx = (int)(k - (unsigned)by * (unsigned)(by + 1) / 2);
+    }
+    const int cb = c0 + bx * kFillT, rb = rbase + by * kFillT;
     if (sorted && rb + kFillT - 1 <= cb) return;
     const int x = threadIdx.x & 31, y0 = threadIdx.x >> 5;
     if (threadIdx.x < kFillT) esr[threadIdx.x] = (rb + threadIdx.x < n) ? es[rb + threadIdx.x] : -1;
@@ -577,13 +585,16 @@ int cmix_mirror_fill(CmixPlan* p, int64_t c0, int64_t c1, int div2Lp1, int inter
     const int n = (int)p->nout;
     const int rbase = p->ell_sorted ? (int)(c0 / kFillT) * kFillT : 0;
     dim3 grid((unsigned)ceil_div(c1 - c0, kFillT), (unsigned)ceil_div(n - rbase, kFillT));
+    // whole sorted matrix: the tiles above the tile diagonal hold nothing to fill, so only the others are launched
+    const int tri = (p->ell_sorted && c0 == 0 && c1 == n && !getenv("SFB_FILL_2D")) ? 1 : 0;
+    if (tri) grid = dim3((unsigned)((size_t)grid.y * (grid.y + 1) / 2), 1);
     const bool vec = p->ell_sorted && (ldM % 2 == 0) && (c0 % 2 == 0) && (reinterpret_cast<uintptr_t>(d_M) % 16 == 0);
     if (vec)
         cmix_mirror_fill_kernel<true><<<grid, 256, 0, stream>>>(d_M, ldM, n, (int)c0, (int)c1, rbase, p->d_es.p, div2Lp1,
-                                                                interchange, 1);
+                                                                interchange, 1, tri);
     else
         cmix_mirror_fill_kernel<false><<<grid, 256, 0, stream>>>(d_M, ldM, n, (int)c0, (int)c1, rbase, p->d_es.p,
-                                                                 div2Lp1, interchange, p->ell_sorted ? 1 : 0);
+                                                                 div2Lp1, interchange, p->ell_sorted ? 1 : 0, tri);
     SFB_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -816,9 +827,9 @@ static int launch_regz(const RegzArgs& args, const RegzLaunchCtx& ctx, int nbloc
               encode_2d(&tm.w, ctx.What, args.nrp, ctx.w_rows, S, args.nrp);
     const size_t psmem = regz_persist_smem_bytes<AT, NT, NWP>(nmax, max_rows);
     if (tma && ctx.want_persist && ctx.queue && psmem <= 227 * 1024) {
+        const int grid = std::min(nblocks, ctx.num_sms);
         SFB_CUDA_OK(cudaFuncSetAttribute(cmix_regz_persist_kernel<AT, NT, NWP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)psmem));
-        const int grid = std::min(nblocks, ctx.num_sms);
         cmix_regz_persist_kernel<AT, NT, NWP><<<grid, NWP * 32, psmem, stream>>>(args, tm, nblocks, max_rows, ctx.queue);
         SFB_CUDA_OK(cudaGetLastError());
         return 0;

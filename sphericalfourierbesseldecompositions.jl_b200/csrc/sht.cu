@@ -1401,13 +1401,38 @@ void sht_plan_destroy(ShtPlan* p) {
         cudaEventDestroy(p->tev0);
         cudaEventDestroy(p->tev1);
     }
+    if (p && p->side) {
+        cudaStreamDestroy(p->side);
+        cudaEventDestroy(p->fork_ev);
+        cudaEventDestroy(p->join_ev);
+    }
     delete p;
+}
+
+// fork: work enqueued on p->side after this call starts once everything enqueued on `st` so far has finished;
+// join: `st` continues once the side stream has drained.  Returns false (and does nothing) in serial mode.
+static bool sht_fork(ShtPlan* p, cudaStream_t st) {
+    if (getenv("SFB_SHT_SERIAL")) return false;
+    if (!p->side) {
+        if (cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking) != cudaSuccess) return false;
+        cudaEventCreateWithFlags(&p->fork_ev, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&p->join_ev, cudaEventDisableTiming);
+    }
+    if (cudaEventRecord(p->fork_ev, st) != cudaSuccess) return false;
+    return cudaStreamWaitEvent(p->side, p->fork_ev, 0) == cudaSuccess;
+}
+static int sht_join(ShtPlan* p, cudaStream_t st) {
+    SFB_CUDA_OK(cudaEventRecord(p->join_ev, p->side));
+    SFB_CUDA_OK(cudaStreamWaitEvent(st, p->join_ev, 0));
+    return 0;
 }
 
 // map -> ring-Fourier coefficients F (d_FG)
 static int run_ring_analysis(ShtPlan* p, const double* map, int64_t ldw, cudaStream_t st) {
     const int lmax = p->lmax, nrp = p->nrp;
     RingTabs rt{p->d_nphi.p, p->d_start.p, p->d_shift.p, p->d_twoff.p, p->d_tw.p};
+    // the belt FFT (latency/HBM-bound) and the cap DFT (DMMA) touch disjoint rings: side by side on two streams
+    const bool forked = p->n_fft_rings > 0 && (p->n_cap_rings > 0 || p->n_gemm_rings > 0) && sht_fork(p, st);
     if (p->n_gemm_rings > 0) {
         dim3 g1(p->n_gemm_rings, (unsigned)ceil_div(lmax + 1, 32), (unsigned)ceil_div(nrp, 64));
         ring_analysis_kernel<<<g1, kT, 0, st>>>(map, ldw, p->nr, nrp, rt, p->d_gemm_rings.p, p->nrings, lmax, p->d_FG.p);
@@ -1434,11 +1459,12 @@ static int run_ring_analysis(ShtPlan* p, const double* map, int64_t ldw, cudaStr
         const int smem = n * sch * (int)sizeof(double2);
         SFB_CUDA_OK(cudaFuncSetAttribute(belt_analysis_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         dim3 gf(p->n_fft_rings, (unsigned)ceil_div(nrp, 2 * sch));
-        belt_analysis_fft_kernel<<<gf, kT, smem, st>>>(map, ldw, p->nr, nrp, rt, p->d_fft_rings.p, p->nrings, lmax,
-                                                       p->log2n, sch, p->d_FG.p);
+        belt_analysis_fft_kernel<<<gf, kT, smem, forked ? p->side : st>>>(map, ldw, p->nr, nrp, rt, p->d_fft_rings.p,
+                                                                          p->nrings, lmax, p->log2n, sch, p->d_FG.p);
         SFB_CUDA_OK(cudaGetLastError());
         p->launches++;
     }
+    if (forked) SFB_TRY(sht_join(p, st));
     return 0;
 }
 
@@ -1576,18 +1602,22 @@ int sht_map2alm(ShtPlan* p, const double* d_win, int64_t ldw, int niter, double*
         if (gram) SFB_TRY(p->d_t.alloc(nalm));
         for (int it = 0; it < niter; ++it) {
             const double* add = p->d_a0.p;
+            bool gforked = false;
             if (gram) {   // t = A f - K alm  (alias-free rings), from the alm of the previous pass
+                // independent of the polar synthesis + alias pass below (both read alm, write different buffers): side stream
+                gforked = p->kpolar > 0 && sht_fork(p, st);
+                cudaStream_t gs = gforked ? p->side : st;
                 const int nil = pick_ni(2 * p->nrp);
                 dim3 gg((unsigned)ceil_div(p->lmax / 2 + 1, 64), (unsigned)ceil_div(2 * p->nrp, 16 * nil),
                         2 * (unsigned)(p->lmax + 1));
                 if (nil == 4)
-                    gram_apply_kernel<4><<<gg, kT, 0, st>>>(p->d_gram.p, p->d_gram_off.p, d_alm, p->d_a0.p, p->lmax, p->nrp,
+                    gram_apply_kernel<4><<<gg, kT, 0, gs>>>(p->d_gram.p, p->d_gram_off.p, d_alm, p->d_a0.p, p->lmax, p->nrp,
                                                             p->d_t.p);
                 else if (nil == 2)
-                    gram_apply_kernel<2><<<gg, kT, 0, st>>>(p->d_gram.p, p->d_gram_off.p, d_alm, p->d_a0.p, p->lmax, p->nrp,
+                    gram_apply_kernel<2><<<gg, kT, 0, gs>>>(p->d_gram.p, p->d_gram_off.p, d_alm, p->d_a0.p, p->lmax, p->nrp,
                                                             p->d_t.p);
                 else
-                    gram_apply_kernel<1><<<gg, kT, 0, st>>>(p->d_gram.p, p->d_gram_off.p, d_alm, p->d_a0.p, p->lmax, p->nrp,
+                    gram_apply_kernel<1><<<gg, kT, 0, gs>>>(p->d_gram.p, p->d_gram_off.p, d_alm, p->d_a0.p, p->lmax, p->nrp,
                                                             p->d_t.p);
                 SFB_CUDA_OK(cudaGetLastError());
                 p->launches++;
@@ -1608,6 +1638,7 @@ int sht_map2alm(ShtPlan* p, const double* d_win, int64_t ldw, int niter, double*
                 }
                 SFB_CUDA_OK(cudaGetLastError());
                 p->launches++;
+                if (gforked) SFB_TRY(sht_join(p, st));   // t is complete before the analysis adds it
                 SFB_TRY(run_legendre_analysis(p, p->d_F2.p, -w, 1, add, d_alm, st, p->kpolar));
             }
         }

@@ -49,6 +49,10 @@ struct ShtPlan {
     // sht_resolve_times (the device-resident API uses this so that the host can enqueue stage 2+3 behind stage 1)
     bool async_times = false, pending = false;
     cudaEvent_t tev0 = nullptr, tev1 = nullptr;
+    // independent kernels of one transform run side by side (SFB_SHT_SERIAL=1: one stream): the belt FFT next to the cap
+    // DFT, and the Gram-matrix product next to the polar synthesis + alias pass of a Jacobi iteration
+    cudaStream_t side = nullptr;
+    cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
 };
 
 int sht_plan_create(ShtPlan** out, int64_t nside_in, int64_t nside_out, int64_t lmax, int64_t nr);

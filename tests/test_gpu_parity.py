@@ -275,7 +275,7 @@ def test_device_pipeline_row_shards():
 # time), each against the oracle, so none of them is dead code on the GPU box.
 
 @pytest.mark.parametrize("flag", ["SFB_NO_MIRROR", "SFB_CMIX_OLD", "SFB_WHAT_FMA", "SFB_WL_FMA", "SFB_REGZ_CPASYNC",
-                                  "SFB_REGZ_FULLDIAG", "SFB_REGZ_ONEBLOCK"])
+                                  "SFB_REGZ_FULLDIAG", "SFB_REGZ_ONEBLOCK", "SFB_FILL_OVERLAP", "SFB_FILL_2D"])
 @pytest.mark.parametrize("nr", [24, 64])
 def test_stage23_alternative_paths(monkeypatch, flag, nr):
     import warnings
