@@ -246,15 +246,26 @@ def run_b200(args):
 
     # Output modes of the device-timed step (`value`):
     #   N = 1   : the whole matrix in HBM (mirror mode: L >= l blocks + fill pass)
-    #   N > 1   : "sharded" (default) — rank g forms a full-height column range of M, a contiguous slab of the
-    #             column-major matrix, and leaves it in its HBM (what an on-device consumer or the per-GPU host copy of
-    #             sfb_set_devices wants); stage 1 is shell-sharded + NCCL all-gather of W_lm(r).
-    #             "assembled" (also timed, reported under `assembled`) — the full matrix on EVERY GPU: upper-packed column
-    #             shards pulled from their owners over NVLink inside the unpack+mirror kernel.
-    mode = os.environ.get("SFB_BENCH_MODE", "sharded")
-    ranges = shard_rows(pipe.col_costs, pipe.ell_of_row, world)
+    #   N > 1   : "L-shaped shards" (default) — every element of M is formed exactly once, by the rank whose L range holds
+    #             max(l_i, l_i'): the blocks l <= L of its columns in upper-packed storage plus, mirrored locally from them,
+    #             its rows of the part below the block diagonal.  No redundant flops, no exchange; stage 1 is shell-sharded +
+    #             NCCL all-gather of W_lm(r).
+    #             "column_slabs" (also timed) — rank g forms a full-height column range of M (what the per-GPU host copy of
+    #             sfb_set_devices and the binned product want; twice the block flops).
+    #             "assembled" (also timed) — the full matrix on EVERY GPU: upper-packed column shards pulled from their
+    #             owners over NVLink inside the unpack+mirror kernel.
+    ranges = shard_rows(pipe.col_costs, pipe.ell_of_row, world)          # column slabs
     lo, hi = ranges[rank]
-    out_t = torch.empty((max(1, hi - lo), pipe.nout), dtype=torch.float64, device="cuda")
+    ell = np.asarray(pipe.ell_of_row)
+    if world > 1:
+        off = pipe.packed_offsets()
+        lranges = pipe.packed_shard_ranges(world, balance="lshard")      # L-shaped shards
+        llo, lhi = lranges[rank]
+        slab = torch.zeros(max(1, int(off[lhi] - off[llo])), dtype=torch.float64, device="cuda")
+        rows_t = torch.zeros((max(1, lhi), max(1, lhi - llo)), dtype=torch.float64, device="cuda")
+        out_t = None
+    else:
+        out_t = torch.empty((max(1, hi - lo), pipe.nout), dtype=torch.float64, device="cuda")
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
 
     def step():
@@ -264,9 +275,23 @@ def run_b200(args):
         if world == 1:
             out = pipe.power_win_mix_rows(0, pipe.nout, out=out_t)
         else:
-            out = pipe.power_win_mix_cols(lo, hi, out=out_t) if hi > lo else out_t
+            out = pipe.power_win_mix_lshard(llo, lhi, packed_slab=slab, rows=rows_t) if lhi > llo else (slab, rows_t)
         evs[2].record()
         return out
+
+    def lshard_sample(i_idx, j_idx):
+        """Values M[i, j] of the listed elements this rank owns (others 0), read from its packed slab / mirrored rows."""
+        i_idx, j_idx = np.asarray(i_idx), np.asarray(j_idx)
+        up = (ell[i_idx] <= ell[j_idx]) & (j_idx >= llo) & (j_idx < lhi)
+        dn = (ell[i_idx] > ell[j_idx]) & (i_idx >= llo) & (i_idx < lhi)
+        vals = torch.zeros(i_idx.size, dtype=torch.float64, device="cuda")
+        if up.any():
+            pos = torch.from_numpy((off[j_idx[up]] - off[llo] + i_idx[up]).astype(np.int64)).cuda()
+            vals[torch.from_numpy(np.flatnonzero(up)).cuda()] = slab[pos]
+        if dn.any():
+            pos = torch.from_numpy((j_idx[dn] * (lhi - llo) + (i_idx[dn] - llo)).astype(np.int64)).cuda()
+            vals[torch.from_numpy(np.flatnonzero(dn)).cuda()] = rows_t.view(-1)[pos]
+        return vals, up | dn
 
     def barrier():
         if world > 1:
@@ -319,33 +344,71 @@ def run_b200(args):
     # ---- correctness carried by the bench line: checksum (same formula for every N) and parity against a 1-rank recompute
     full = step()
     torch.cuda.synchronize()
+    column_slabs = None
     if world == 1:
         checksum = strided_checksum_cols(full, 0, n)
         parity = None
     else:
-        cs = torch.tensor([strided_checksum_cols(full, lo, n) if hi > lo else 0.0], device="cuda", dtype=torch.float64)
+        si, sj = max(1, n // 97), max(1, n // 89)
+        ii, jj = np.meshgrid(np.arange(0, n, si), np.arange(0, n, sj), indexing="ij")
+        vals, mine = lshard_sample(ii.ravel(), jj.ravel())
+        cs = torch.stack([vals.sum(), torch.tensor(float(mine.sum()), device="cuda", dtype=torch.float64)])
         dist.all_reduce(cs)
-        checksum = float(cs.item())
-        # every rank recomputes, on its own GPU alone (full stage 1, no collective), a few of its columns
+        checksum = float(cs[0].item())
+        if int(round(float(cs[1].item()))) != ii.size:
+            raise SystemExit("bench.py: the L-shaped shards do not cover every sampled element exactly once")
+        # every rank recomputes, on its own GPU alone (full stage 1, no collective), a few of its columns and rows
         alm_sharded = pipe.alm.clone()
         pipe.calc_wr_lm(d_win)
         torch.cuda.synchronize()
         err = float(((pipe.alm - alm_sharded).norm() / pipe.alm.norm()).item())
-        if hi > lo:
-            for c0 in sorted({lo, (lo + hi) // 2, max(lo, hi - 8)}):
-                c1 = min(hi, c0 + 8)
-                ref = pipe.power_win_mix_cols(c0, c1)
+        if lhi > llo:
+            for c0 in sorted({llo, (llo + lhi) // 2, max(llo, lhi - 8)}):
+                c1 = min(lhi, c0 + 8)
+                ref = pipe.power_win_mix_cols(c0, c1)                 # (c1-c0, nout): ref[j-c0, i] = M[i, j]
+                ref_r = pipe.power_win_mix_rows(c0, c1)               # (nout, c1-c0): ref_r[j, i-c0] = M[i, j]
                 torch.cuda.synchronize()
-                err = max(err, float(((full[c0 - lo:c1 - lo] - ref).norm() / ref.norm()).item()))
+                jc, ic = np.meshgrid(np.arange(c0, c1), np.arange(n), indexing="ij")
+                keep = ell[ic] <= ell[jc]
+                got, own = lshard_sample(ic[keep], jc[keep])
+                assert own.all()
+                want = ref[torch.from_numpy(jc[keep] - c0).cuda(), torch.from_numpy(ic[keep]).cuda()]
+                err = max(err, float(((got - want).norm() / want.norm()).item()))
+                ir, jr = np.meshgrid(np.arange(c0, c1), np.arange(n), indexing="ij")
+                keep = ell[jr] < ell[ir]
+                if keep.any():
+                    got, own = lshard_sample(ir[keep], jr[keep])
+                    assert own.all()
+                    want = ref_r[torch.from_numpy(jr[keep]).cuda(), torch.from_numpy(ir[keep] - c0).cuda()]
+                    err = max(err, float(((got - want).norm() / want.norm()).item()))
         e = torch.tensor([err], device="cuda", dtype=torch.float64)
         dist.all_reduce(e, op=dist.ReduceOp.MAX)
         parity = float(e.item())
         if not parity < 1e-10:
             raise SystemExit(f"bench.py: sharded result differs from the single-GPU recompute (rel err {parity:.3e})")
+        pipe.alm.copy_(alm_sharded)
+
+        # ---- column slabs (full-height column range per rank), timed the same way
+        out_c = torch.empty((max(1, hi - lo), pipe.nout), dtype=torch.float64, device="cuda")
+
+        def step_cols():
+            pipe.calc_wr_lm_sharded(d_win)
+            return pipe.power_win_mix_cols(lo, hi, out=out_c) if hi > lo else out_c
+
+        for _ in range(args.warmup):
+            step_cols()
+        cms = timed(step_cols, max(3, args.steps // 2))
+        ccs = torch.tensor([strided_checksum_cols(out_c, lo, n) if hi > lo else 0.0], device="cuda", dtype=torch.float64)
+        dist.all_reduce(ccs)
+        column_slabs = {"ms_per_step": cms, "value": n * n / (cms * 1e-3), "unit": UNIT, "checksum": float(ccs.item()),
+                        "cols_of_rank": [list(map(int, r)) for r in ranges],
+                        "note": "rank g forms a full-height column range of M (a contiguous slab of the column-major matrix): "
+                                "the form the host copy of sfb_set_devices and the binned product use; twice the block flops"}
+        del out_c
 
     per_rank = None
     if world > 1:
-        mine = {"rank": rank, "cols": [int(lo), int(hi)], **{k: round(v, 3) for k, v in sm.items()}}
+        mine = {"rank": rank, "L_range_cols": [int(llo), int(lhi)], **{k: round(v, 3) for k, v in sm.items()}}
         per_rank = [None] * world
         dist.all_gather_object(per_rank, mine)
 
@@ -370,7 +433,13 @@ def run_b200(args):
             step_assembled()
         ams = timed(step_assembled, max(3, args.steps // 2))
         acs = strided_checksum_cols(full_t, 0, n)
-        aerr = float(((full_t[lo:hi] - full).norm() / full.norm()).item()) if hi > lo else 0.0
+        aerr = 0.0
+        if lhi > llo:   # against this rank's packed columns (full_t[j, i] = M[i, j])
+            jc, ic = np.meshgrid(np.arange(llo, lhi, max(1, (lhi - llo) // 16)), np.arange(0, n, 7), indexing="ij")
+            keep = ell[ic] <= ell[jc]
+            got, _ = lshard_sample(ic[keep], jc[keep])
+            want = full_t[torch.from_numpy(jc[keep]).cuda(), torch.from_numpy(ic[keep]).cuda()]
+            aerr = float(((got - want).norm() / want.norm()).item())
         e = torch.tensor([aerr], device="cuda", dtype=torch.float64)
         dist.all_reduce(e, op=dist.ReduceOp.MAX)
         assembled = {"ms_per_step": ams, "value": n * n / (ams * 1e-3), "unit": UNIT, "checksum": acs,
@@ -396,6 +465,8 @@ def run_b200(args):
     except (OSError, KeyError):
         pass
     nl = np.asarray(wl.amodes.nmax_l, dtype=np.float64)
+    if world > 1:
+        lo, hi = llo, lhi
     ells_mine = np.unique(wl.cmodes.lnn[0, lo:hi])
     nn = nl[ells_mine][:, None] * nl[None, :]
     f_alg_block = float(np.sum(2 * nn * wl.nr ** 2 + 2 * nn * nn * wl.nr))
@@ -470,12 +541,13 @@ def run_b200(args):
             "l2": "working set (win 0.4 GB + ring buffers 0.3 GB + M %.1f GB) exceeds the 126 MB L2, no explicit flush"
                   % (8e-9 * n * n),
             "output_mode": ("full matrix in HBM" if world == 1 else
-                            f"sharded x{world}: stage 1 by shells + NCCL all-gather of W_lm(r); M by full-height column "
-                            "ranges (L,N,N'), each left in its owner's HBM (no assembly); see `assembled` for the "
-                            "all-GPUs-hold-everything variant"),
+                            f"L-shaped shards x{world}: stage 1 by shells + NCCL all-gather of W_lm(r); every element of M formed "
+                            "exactly once, on the rank whose L range holds max(l_i, l_i') (blocks l <= L of its columns in "
+                            "upper-packed storage + its rows below the block diagonal mirrored locally), left in its owner's "
+                            "HBM; see `column_slabs` and `assembled` for the other two forms"),
             "checksum": checksum, "parity_vs_n1": parity,
             "roofline": roofline, "roofline_stage1": roofline_stage1, "roofline_mirror_fill": roofline_fill,
-            "stage_ms": sm, "per_rank": per_rank, "assembled": assembled,
+            "stage_ms": sm, "per_rank": per_rank, "column_slabs": column_slabs, "assembled": assembled,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
         }
         print(json.dumps(line))

@@ -237,6 +237,13 @@ int32_t sfb_cmix_col_costs_upper(const sfb_cmix_plan* plan, double* cost, int64_
 int32_t sfb_power_win_mix_upper_packed_dev(sfb_cmix_plan* plan, const double* d_alm, int32_t div2Lp1,
                                            int32_t interchange_NN, int64_t col_lo, int64_t col_hi, double* d_packed,
                                            void* stream);
+/* "L-shaped" shards (multi-GPU output without redundant work; the reference has no counterpart, its gather is the pmap at
+ * src/windows.jl:841-861): the device that formed the upper-packed columns [col_lo, col_hi) (whole L-blocks) also forms
+ * the rows [col_lo, col_hi) of the part of M below the block diagonal, locally, from the symmetry of the un-symmetrised
+ * kernel: d_rows[r * ld_rows + (j - col_lo)] = M[j, r] for l(r) < l(j).  Every element (i, i') of M then lives on exactly
+ * one device — the one whose L range holds max(l_i, l_i').                                                            */
+int32_t sfb_cmix_mirror_rows_dev(sfb_cmix_plan* plan, const double* d_packed, int64_t col_lo, int64_t col_hi,
+                                 int32_t div2Lp1, int32_t interchange_NN, double* d_rows, int64_t ld_rows, void* stream);
 int32_t sfb_cmix_unpack_mirror_dev(sfb_cmix_plan* plan, const double* d_packed, int32_t div2Lp1, int32_t interchange_NN,
                                    double* d_M, int64_t ldM, void* stream);
 /* Fused exchange: packed_of_rank[g] is rank g's packed buffer (sfb_ipc_alloc / sfb_ipc_open, own buffer included), rank g

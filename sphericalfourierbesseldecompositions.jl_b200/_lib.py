@@ -63,6 +63,7 @@ SIGNATURES = {
     "sfb_cmix_col_costs_upper": (_i32, [_vp, _f64p, _i64]),
     "sfb_cmix_packed_offsets": (_i32, [_vp, _vp, _i64]),
     "sfb_power_win_mix_upper_packed_dev": (_i32, [_vp, _f64p, _i32, _i32, _i64, _i64, _f64p, _vp]),
+    "sfb_cmix_mirror_rows_dev": (_i32, [_vp, _f64p, _i64, _i64, _i32, _i32, _f64p, _i64, _vp]),
     "sfb_cmix_unpack_mirror_dev": (_i32, [_vp, _f64p, _i32, _i32, _f64p, _i64, _vp]),
     "sfb_cmix_unpack_mirror_peers_dev": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _f64p, _i64, _vp]),
     "sfb_power_win_mix_block_dev": (_i32, [_vp, _f64p, _f64p, _i32, _i32, _i64, _i64, _i64, _i64, _f64p, _i64, _vp]),

@@ -1334,6 +1334,14 @@ int32_t sfb_power_win_mix_upper_packed_dev(sfb_cmix_plan* plan, const double* d_
     g_times[6] = t0 + p->launches;
     return 0;
 }
+int32_t sfb_cmix_mirror_rows_dev(sfb_cmix_plan* plan, const double* d_packed, int64_t col_lo, int64_t col_hi,
+                                 int32_t div2Lp1, int32_t interchange_NN, double* d_rows, int64_t ld_rows, void* stream) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    auto* p = reinterpret_cast<CmixPlan*>(plan);
+    SFB_TRY(cmix_mirror_rows(p, d_packed, col_lo, col_hi, div2Lp1, interchange_NN, d_rows, ld_rows, (cudaStream_t)stream));
+    g_times[6] += 1;
+    return 0;
+}
 int32_t sfb_cmix_unpack_mirror_dev(sfb_cmix_plan* plan, const double* d_packed, int32_t div2Lp1, int32_t interchange_NN,
                                    double* d_M, int64_t ldM, void* stream) {
     std::lock_guard<std::mutex> lk(g_mutex);

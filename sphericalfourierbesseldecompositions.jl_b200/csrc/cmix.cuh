@@ -99,6 +99,10 @@ int cmix_unpack_mirror(CmixPlan* p, const double* const* bases, const int64_t* c
                        int div2Lp1, int interchange, double* d_M, int64_t ldM, cudaStream_t stream);
 int cmix_mirror_fill(CmixPlan* p, int64_t c0, int64_t c1, int div2Lp1, int interchange, double* d_M, int64_t ldM,
                      cudaStream_t stream);
+// rows [j_lo, j_hi) of the part of M below the block diagonal, from the upper-packed columns [j_lo, j_hi) of the same
+// device: d_rows[r * ldR + (j - j_lo)] = M[j, r] for l(r) < l(j)  ("L-shaped" multi-GPU shards)
+int cmix_mirror_rows(CmixPlan* p, const double* d_packed, int64_t j_lo, int64_t j_hi, int div2Lp1, int interchange,
+                     double* d_rows, int64_t ldR, cudaStream_t stream);
 // l-block aligned row ranges of roughly equal cost for the mirrored, pipelined host path
 std::vector<std::pair<int64_t, int64_t>> cmix_row_chunks_mirror(const CmixPlan* p, int k);
 // column ranges of roughly equal cost (L-block aligned) for pipelining compute with the D2H of finished slabs

@@ -757,6 +757,86 @@ int cmix_unpack_mirror(CmixPlan* p, const double* const* bases, const int64_t* c
     return 0;
 }
 
+// =============================================================================================
+// Row mirror of an upper-packed column range ("L-shaped" shards, the multi-GPU output without redundant flops): the owner
+// of the columns [j_lo, j_hi) (whole L-blocks, blocks l <= L in packed storage) also owns the ROWS [j_lo, j_hi) of the
+// part below the block diagonal, which it forms locally from its own packed columns,
+//   M[j, r] = M[r, j] · f_r / f_j   for l(r) < l(j),   j in [j_lo, j_hi)
+// (same identity as cmix_mirror_fill_kernel), into the compact row slab R[r * ldR + (j - j_lo)], r in [0, j_hi).
+// Every element of M then lives on exactly one device: (i, j) with max(l_i, l_j) in the device's L range.
+__global__ void __launch_bounds__(256) cmix_mirror_rows_kernel(const double* __restrict__ P,
+                                                               const long long* __restrict__ colbase,
+                                                               double* __restrict__ R, long long ldR, int j_lo, int j_hi,
+                                                               const int* __restrict__ es, int div2Lp1, int interchange) {
+    __shared__ double tile[kFillT][kFillT + 1];
+    __shared__ int esr[kFillT], esc[kFillT];
+    __shared__ long long cbase[kFillT];
+    const int jb = j_lo + blockIdx.x * kFillT, rb = blockIdx.y * kFillT;
+    const int x = threadIdx.x & 31, y0 = threadIdx.x >> 5;
+    if (threadIdx.x < kFillT) esr[threadIdx.x] = (rb + threadIdx.x < j_hi) ? es[rb + threadIdx.x] : -1;
+    else if (threadIdx.x < 2 * kFillT) {
+        const int j = jb + threadIdx.x - kFillT;
+        esc[threadIdx.x - kFillT] = (j < j_hi) ? es[j] : -1;
+        cbase[threadIdx.x - kFillT] = (j < j_hi) ? colbase[j] : 0;
+    }
+    __syncthreads();
+    {   // l is sorted: nothing to do unless the tile's smallest row l is below its largest column l
+        const int jlast = min(kFillT, j_hi - jb) - 1;
+        if ((esr[0] & 0x3fffffff) >= (esc[jlast] & 0x3fffffff)) return;
+    }
+    constexpr int NK = kFillT / 8;
+    const int x2 = 2 * x;
+    const int er0 = esr[x2], er1 = esr[x2 + 1];
+    // source elements (rows rb+2x, rb+2x+1 of packed column jb+y), rows with l(r) < l(j) only
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+        const int y = y0 + 8 * k;
+        const int ec = esc[y];
+        const bool a0 = (er0 >= 0 && ec >= 0 && (er0 & 0x3fffffff) < (ec & 0x3fffffff));
+        const bool a1 = (er1 >= 0 && ec >= 0 && (er1 & 0x3fffffff) < (ec & 0x3fffffff));
+        const double* src = P + cbase[y] + rb + x2;
+        if (a1) {   // l sorted: a1 implies a0; packed columns start 32-byte aligned and rb + x2 is even
+            const double2 v = *reinterpret_cast<const double2*>(src);
+            tile[y][x2] = v.x;
+            tile[y][x2 + 1] = v.y;
+        } else if (a0) {
+            tile[y][x2] = src[0];
+        }
+    }
+    __syncthreads();
+    // destination: R[(rb+y) * ldR + (jb + 2x - j_lo)], rows j = jb+2x, jb+2x+1 of the slab
+    const int ej0 = esc[x2], ej1 = esc[x2 + 1];
+    const int lj0 = ej0 & 0x3fffffff, lj1 = ej1 & 0x3fffffff;
+    const double ifj0 = 1.0 / ((div2Lp1 ? 1.0 : 2.0 * lj0 + 1.0) * ((!interchange && (ej0 >> 30)) ? 2.0 : 1.0));
+    const double ifj1 = 1.0 / ((div2Lp1 ? 1.0 : 2.0 * lj1 + 1.0) * ((!interchange && (ej1 >> 30)) ? 2.0 : 1.0));
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+        const int y = y0 + 8 * k;
+        const int e2 = esr[y];
+        if (e2 < 0) continue;
+        const int lr = e2 & 0x3fffffff;
+        const double fr = (div2Lp1 ? 1.0 : 2.0 * lr + 1.0) * ((!interchange && (e2 >> 30)) ? 2.0 : 1.0);
+        const bool b0 = (ej0 >= 0 && lr < lj0), b1 = (ej1 >= 0 && lr < lj1);
+        double* dst = R + (size_t)(rb + y) * ldR + (jb + x2 - j_lo);
+        if (b0) dst[0] = tile[x2][y] * (fr * ifj0);
+        if (b1) dst[1] = tile[x2 + 1][y] * (fr * ifj1);
+    }
+}
+
+int cmix_mirror_rows(CmixPlan* p, const double* d_packed, int64_t j_lo, int64_t j_hi, int div2Lp1, int interchange,
+                     double* d_rows, int64_t ldR, cudaStream_t stream) {
+    SFB_REQUIRE(p && d_packed && d_rows, "cmix_mirror_rows: null pointer");
+    SFB_REQUIRE(p->ell_sorted && (int64_t)p->h_colbase.size() == p->nout + 1,
+                "cmix_mirror_rows: upper-packed storage needs an lnn table sorted by l");
+    SFB_REQUIRE(0 <= j_lo && j_lo <= j_hi && j_hi <= p->nout && ldR >= j_hi - j_lo, "cmix_mirror_rows: bad range");
+    if (j_hi == j_lo) return 0;
+    dim3 grid((unsigned)ceil_div(j_hi - j_lo, kFillT), (unsigned)ceil_div(j_hi, kFillT));
+    cmix_mirror_rows_kernel<<<grid, 256, 0, stream>>>(d_packed, p->d_colbase.p, d_rows, ldR, (int)j_lo, (int)j_hi, p->d_es.p,
+                                                      div2Lp1, interchange);
+    SFB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 template <int AT, int NT, int NW>
 static size_t regz_smem_bytes(int nmax, int max_rows) {
     constexpr int AP = AT * 8, K = NT * 8, S = K + 8;

@@ -225,6 +225,13 @@ class DevicePipeline:
         w = self.col_costs_upper / 29e12
         if balance == "mixed" and world > 1:
             w = w + (world - 1) * 8.0 * np.diff(off) / 700e9
+        if balance == "lshard":
+            # L-shaped shards: index j also owns its row below the block diagonal, mirrored locally at HBM speed
+            # (read + write of the elements in front of j's own l-block; ~4.8 TB/s measured for the mirror passes)
+            ell = np.asarray(self.ell_of_row)
+            cuts = np.concatenate([[0], np.flatnonzero(np.diff(ell)) + 1, [ell.size]])
+            lstart = np.repeat(cuts[:-1], np.diff(cuts)).astype(np.float64)
+            w = w + 16.0 * lstart / 4.8e12
         return shard_rows(w, self.ell_of_row, world)
 
     def power_win_mix_upper_packed(self, lo, hi, packed, div2Lp1=False, interchange_NN=False):
@@ -233,6 +240,50 @@ class DevicePipeline:
                                                                int(interchange_NN), lo, hi, packed.data_ptr(),
                                                                self._stream()))
         return packed
+
+    def power_win_mix_lshard(self, lo, hi, packed=None, rows=None, div2Lp1=False, interchange_NN=False, packed_slab=None):
+        """"L-shaped" shard of the L-block aligned index range [lo, hi): the blocks with l <= L of the columns [lo, hi)
+        in upper-packed storage (`packed`, the whole packed buffer) plus, mirrored locally from them, the rows [lo, hi) of
+        the part of M below the block diagonal: rows[r, j - lo] = M[j, r] for l(r) < l(j)  (tensor of shape (hi, hi - lo)).
+        Over the ranges of `packed_shard_ranges` every element of M is formed exactly once (no redundant flops, no
+        exchange): element (i, i') lives where max(l_i, l_i') falls."""
+        torch = _torch()
+        off = self.packed_offsets()
+        if packed_slab is not None:
+            # only this range's slab [off[lo], off[hi]) of the packed buffer exists: address it through a virtual base
+            assert packed_slab.is_contiguous() and packed_slab.numel() >= int(off[hi] - off[lo])
+            base = packed_slab.data_ptr() - 8 * int(off[lo])
+        else:
+            base = packed.data_ptr()
+        if rows is None:
+            rows = torch.zeros((hi, hi - lo), dtype=torch.float64, device=self.device)
+        assert rows.is_contiguous() and rows.shape[0] >= hi and rows.shape[1] == hi - lo
+        if hi > lo:
+            _lib.check(self.lib.sfb_power_win_mix_upper_packed_dev(self._cmix, self.alm.data_ptr(), int(div2Lp1),
+                                                                   int(interchange_NN), lo, hi, base, self._stream()))
+            _lib.check(self.lib.sfb_cmix_mirror_rows_dev(self._cmix, base, lo, hi, int(div2Lp1), int(interchange_NN),
+                                                         rows.data_ptr(), hi - lo, self._stream()))
+        return (packed if packed_slab is None else packed_slab), rows
+
+    def lshard_assemble_host(self, packed, rows_of_range, ranges):
+        """Full matrix (numpy, M[i, j]) from the pieces of `power_win_mix_lshard` — for checks."""
+        off = self.packed_offsets()
+        n = self.nout
+        ell = np.asarray(self.ell_of_row)
+        P = packed.cpu().numpy()
+        M = np.full((n, n), np.nan)
+        lend = np.zeros(n, dtype=np.int64)      # rend(j): end of j's own l-block
+        cuts = np.concatenate([[0], np.flatnonzero(np.diff(ell)) + 1, [n]])
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            lend[a:b] = b
+        for j in range(n):
+            M[:lend[j], j] = P[off[j]:off[j] + lend[j]]
+        for (lo, hi), rows in zip(ranges, rows_of_range):
+            R = rows.cpu().numpy()
+            for j in range(lo, hi):
+                below = ell[:hi] < ell[j]                 # columns r with l(r) < l(j)
+                M[j, :hi][below] = R[:hi, j - lo][below]
+        return M
 
     def unpack_mirror(self, packed, full=None, div2Lp1=False, interchange_NN=False):
         torch = _torch()

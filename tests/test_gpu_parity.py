@@ -267,6 +267,14 @@ def test_device_pipeline_row_shards():
         ref = pipe.power_win_mix_rows(0, pipe.nout, **kw).cpu().numpy().T
         assert np.isfinite(got).all()
         assert relerr(got, ref) < 1e-13
+        # "L-shaped" shards: upper-packed columns + locally mirrored rows cover every element exactly once
+        for world in (1, 3):
+            lr = pipe.packed_shard_ranges(world, balance="cost")
+            packed = torch.full((int(off[-1]),), float("nan"), dtype=torch.float64, device="cuda")
+            rows = [pipe.power_win_mix_lshard(lo, hi, packed, **kw)[1] for lo, hi in lr]
+            got = pipe.lshard_assemble_host(packed, rows, lr)
+            assert np.isfinite(got).all()
+            assert relerr(got, ref) < 1e-13
     pipe.close()
 
 

@@ -17,6 +17,8 @@ def main():
     ap.add_argument("--world", type=int, default=8)
     ap.add_argument("--config", default="4")
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--mode", default="lshard", choices=["lshard", "cols"],
+                    help="lshard: upper-packed columns + locally mirrored rows; cols: full-height column slabs")
     args = ap.parse_args()
     import torch
 
@@ -31,7 +33,9 @@ def main():
     W = args.world
     pipe.calc_wr_lm(d_win)
     torch.cuda.synchronize()
-    ranges = shard_rows(pipe.col_costs, pipe.ell_of_row, W)
+    off = pipe.packed_offsets()
+    ranges = (pipe.packed_shard_ranges(W, balance="lshard") if args.mode == "lshard"
+              else shard_rows(pipe.col_costs, pipe.ell_of_row, W))
     shells = shard_shells(pipe.nr, W)
 
     def ev():
@@ -39,7 +43,7 @@ def main():
 
     res = []
     maxcols = max(h - l for l, h in ranges)
-    out = torch.empty((maxcols, pipe.nout), dtype=torch.float64, device="cuda")
+    out = torch.empty((maxcols, pipe.nout), dtype=torch.float64, device="cuda") if args.mode == "cols" else None
     for g in range(W):
         lo, hi = ranges[g]
         slo, shi = shells[g]
@@ -63,16 +67,24 @@ def main():
             lib.sfb_sht_plan_destroy(plan)
         if hi > lo:
             ts, det = [], None
+            if args.mode == "lshard":
+                slab = torch.empty(int(off[hi] - off[lo]), dtype=torch.float64, device="cuda")
+                rows = torch.empty((hi, hi - lo), dtype=torch.float64, device="cuda")
             for _ in range(args.reps + 2):
                 e0, e1 = ev(), ev()
                 e0.record()
-                pipe.power_win_mix_cols(lo, hi, out=out[: hi - lo])
+                if args.mode == "lshard":
+                    pipe.power_win_mix_lshard(lo, hi, packed_slab=slab, rows=rows)
+                else:
+                    pipe.power_win_mix_cols(lo, hi, out=out[: hi - lo])
                 e1.record()
                 torch.cuda.synchronize()
                 ts.append(e0.elapsed_time(e1))
                 det = _lib.timings()
             rec["stage23_ms"] = round(float(np.median(ts[2:])), 4)
             rec.update({k: round(det[k], 4) for k in ("wl_ms", "what_ms", "block_ms", "fill_ms")})
+            if args.mode == "lshard":
+                del slab, rows
         res.append(rec)
         print(json.dumps(rec), flush=True)
     crit = max(r.get("stage1_ms", 0) for r in res) + max(r.get("stage23_ms", 0) for r in res)
