@@ -461,7 +461,8 @@ def run_b200(args):
     except OSError:
         pass
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))["kernels"]
+        tfile = [f for f in ("r02_final_traffic.json", "r02_traffic.json") if os.path.exists(os.path.join(ROOT, "profiles", f))]
+        traffic = json.load(open(os.path.join(ROOT, "profiles", tfile[0])))["kernels"]
     except (OSError, KeyError):
         pass
     nl = np.asarray(wl.amodes.nmax_l, dtype=np.float64)
@@ -471,12 +472,12 @@ def run_b200(args):
     nn = nl[ells_mine][:, None] * nl[None, :]
     f_alg_block = float(np.sum(2 * nn * wl.nr ** 2 + 2 * nn * nn * wl.nr))
     exec_tflops = collect.flops / (kern_ms * 1e-3) / 1e12
-    regz_traffic = sum(v["traffic_bytes"] for k, v in traffic.items() if k.startswith("cmix_regz_kernel")) or None
+    regz_traffic = sum(v["traffic_bytes"] for k, v in traffic.items() if k.startswith(("cmix_regz", "sfb::cmix_regz"))) or None
     if world > 1 or str(args.config) != "4":
         regz_traffic = None
     hbm = peaks.get("hbm_gbs")
     roofline = {
-        "kernel": "cmix_regz_kernel (stage 2+3 block GEMMs, FP64 DMMA, all tile classes of one step)", "bound": "tensor",
+        "kernel": "cmix_regz_persist_kernel (stage 2+3 block GEMMs, FP64 DMMA, all tile classes of one step)", "bound": "tensor",
         "achieved": exec_tflops, "peak": float(dmma[0]), "unit": "TFLOP/s", "frac": exec_tflops / float(dmma[0]),
         "traffic": regz_traffic,
         "algorithmic_bytes": 8.0 * (hi - lo) * n / (2 if world == 1 else 1),
