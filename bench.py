@@ -552,6 +552,7 @@ def run_b200(args):
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
         }
         print(json.dumps(line))
+    pipe.close()
     if world > 1:
         dist.destroy_process_group()
 

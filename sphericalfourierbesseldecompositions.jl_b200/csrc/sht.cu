@@ -785,7 +785,7 @@ __global__ void __launch_bounds__(kT) legendre_analysis_kernel(const double* __r
                                                                int kend, int lmax, int nrp, double w, int accumulate,
                                                                const double* __restrict__ add,
                                                                double* __restrict__ alm,
-                                                               const int* __restrict__ kbeg_of_m) {
+                                                               const int* __restrict__ kbeg_of_m, int dbg) {
     // kend: only the north rings [0, kend) (and their southern mirrors) contribute (kend = nhalf: all rings)
     constexpr int BW = ColTile<NI>::BW, LD = ColTile<NI>::LD;
     extern __shared__ double la_smem[];
@@ -818,6 +818,13 @@ __global__ void __launch_bounds__(kT) legendre_analysis_kernel(const double* __r
     }
     auto prefetch = [&](int k0) {
         const int kk = tid & 31;
+        if (dbg & 2) {   // timing aid (SFB_SHT_DBG): no global loads
+#pragma unroll
+            for (int q = 0; q < 8; ++q) ra[q] = 1.0;
+#pragma unroll
+            for (int u = 0; u < NB; ++u) rn[u] = rs[u] = 1.0;
+            return;
+        }
 #pragma unroll
         for (int q = 0; q < 8; ++q)
             ra[q] = (arow[q] != (size_t)-1 && k0 + kk < kend) ? lam[arow[q] + k0 + kk] : 0.0;
@@ -848,7 +855,7 @@ __global__ void __launch_bounds__(kT) legendre_analysis_kernel(const double* __r
         }
         __syncthreads();
         if (k0 + 32 < kend) prefetch(k0 + 32);
-        warp_gemm_ss<2, NI>(acc, As + wm * 16 * kLdA, kLdA, Bsel + wn * 8 * NI, LD, 32);
+        if (!(dbg & 1)) warp_gemm_ss<2, NI>(acc, As + wm * 16 * kLdA, kLdA, Bsel + wn * 8 * NI, LD, 32);
         __syncthreads();
     }
 #pragma unroll
@@ -1476,13 +1483,14 @@ static int run_legendre_analysis(ShtPlan* p, const double* Fsrc, double w, int a
     const int nil = pick_ni(2 * nrp);
     dim3 g2((unsigned)ceil_div(lmax + 1, 64), (unsigned)ceil_div(2 * nrp, 16 * nil), lmax + 1);
     const int la_smem_bytes = (64 * kLdA + 2 * 32 * (16 * nil + 4)) * (int)sizeof(double);
+    const int sht_dbg = getenv("SFB_SHT_DBG") ? atoi(getenv("SFB_SHT_DBG")) : 0;   // timing aid, results wrong when != 0
 #define SFB_LAUNCH_LA(NI_)                                                                                            \
     do {                                                                                                              \
         SFB_CUDA_OK(cudaFuncSetAttribute(legendre_analysis_kernel<NI_>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                          la_smem_bytes));                                                             \
         legendre_analysis_kernel<NI_><<<g2, kT, la_smem_bytes, st>>>(Fsrc, p->d_lam.p, p->nrings, p->nhalf, kend, lmax,  \
                                                                      nrp, w, accumulate, add, d_alm,                 \
-                                                                     p->d_kbeg_of_m.p);                              \
+                                                                     p->d_kbeg_of_m.p, sht_dbg);                     \
     } while (0)
     if (nil == 4)
         SFB_LAUNCH_LA(4);

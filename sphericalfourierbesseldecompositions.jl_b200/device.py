@@ -89,6 +89,10 @@ class DevicePipeline:
         if getattr(self, "_sht_shard", None):
             self.lib.sfb_sht_plan_destroy(self._sht_shard)
             self._sht_shard = None
+        if getattr(self, "_alm_peer", None):
+            for pb in self._alm_peer:
+                pb.close()
+            self._alm_peer = None
 
     def __del__(self):
         try:
@@ -130,12 +134,23 @@ class DevicePipeline:
         cnt = hi - lo
         nrp_g = 8 * (-(-max(h - l for l, h in ranges) // 8))
         nrp_mine = 8 * (-(-max(cnt, 1) // 8))
+        import os
+        peer = os.environ.get("SFB_ALM_GATHER", "peer") == "peer" and world <= 8
         if getattr(self, "_sht_shard", None) is None:
             self._sht_shard = C.c_void_p()
             _lib.check(self.lib.sfb_sht_plan_create(C.byref(self._sht_shard), self.nside_in, self.amodes.nside,
                                                     self.LMAX, max(cnt, 1)))
             self._alm_shard = torch.zeros(self.lmsize * 2 * nrp_mine, dtype=torch.float64, device=self.device)
-            self._alm_recv = torch.empty(world * self.lmsize * 2 * nrp_g, dtype=torch.float64, device=self.device)
+            self._alm_recv = None if peer else torch.empty(world * self.lmsize * 2 * nrp_g, dtype=torch.float64,
+                                                           device=self.device)
+            # peer gather: every rank's shard lives in an IPC-mapped buffer (two of them, alternating between calls) and
+            # the placement kernel reads the peers' shards straight over NVLink — no NCCL all-gather, no staging copy
+            self._alm_peer = [PeerBuffer(self.lmsize * 2 * nrp_mine, group) for _ in range(2)] if peer else None
+            for pb in self._alm_peer or []:
+                pb.tensor.zero_()
+            self._alm_peer_k = 0
+        if peer:
+            return self._calc_wr_lm_peer(d_win, group, niter, ranges, lo, cnt, nrp_mine)
         if cnt > 0:
             _lib.check(self.lib.sfb_calc_wr_lm_dev(self._sht_shard, d_win.data_ptr() + 8 * lo, self.nr, niter,
                                                    self._alm_shard.data_ptr(), self._stream()))
@@ -150,6 +165,30 @@ class DevicePipeline:
                                  np.asarray([r[0] for r in ranges] + [self.nr], dtype=np.int64),
                                  np.full(world, nrp_g, dtype=np.int64))
         ptrs, bounds, strides = self._gather_args
+        _lib.check(self.lib.sfb_alm_gather_shards_dev(ptrs, _lib.ptr(bounds), _lib.ptr(strides), world, self.LMAX, self.nr,
+                                                      self.alm.data_ptr(), self._stream()))
+        return self.alm
+
+    def _calc_wr_lm_peer(self, d_win, group, niter, ranges, lo, cnt, nrp_mine):
+        """Stage 1 on this rank's shells into its IPC-mapped shard, a stream-ordered barrier, then ONE kernel that places
+        all shards (the peers' read over NVLink) into the planar W_lm(r) buffer.  The shard buffers alternate between
+        calls: a rank may start its next stage 1 while a slower peer still reads the previous shard, and by the time a
+        buffer comes round again every rank has passed the barrier of the call in between, i.e. finished reading it."""
+        world = len(ranges)
+        b = self._alm_peer_k & 1
+        self._alm_peer_k += 1
+        pb = self._alm_peer[b]
+        if cnt > 0:
+            _lib.check(self.lib.sfb_calc_wr_lm_dev(self._sht_shard, d_win.data_ptr() + 8 * lo, self.nr, niter,
+                                                   pb.ptr.value, self._stream()))
+        stream_barrier(self, group)
+        if getattr(self, "_peer_gather_args", None) is None:
+            self._peer_gather_args = {}
+        if b not in self._peer_gather_args:
+            strides = np.asarray([8 * (-(-max(h - l, 1) // 8)) for l, h in ranges], dtype=np.int64)
+            self._peer_gather_args[b] = ((C.c_void_p * world)(*pb.rank_ptrs),
+                                         np.asarray([r[0] for r in ranges] + [self.nr], dtype=np.int64), strides)
+        ptrs, bounds, strides = self._peer_gather_args[b]
         _lib.check(self.lib.sfb_alm_gather_shards_dev(ptrs, _lib.ptr(bounds), _lib.ptr(strides), world, self.LMAX, self.nr,
                                                       self.alm.data_ptr(), self._stream()))
         return self.alm
@@ -444,11 +483,12 @@ class PeerBuffer:
         import torch.distributed as dist
         if self.ptr:
             _torch().cuda.synchronize()
-            if self.world > 1:
+            live = self.world > 1 and dist.is_initialized()     # at interpreter exit the group may be gone already
+            if live:
                 dist.barrier(self.group)
             for q in self._opened:
                 self.lib.sfb_ipc_close(q)
-            if self.world > 1:
+            if live:
                 dist.barrier(self.group)
             self.lib.sfb_ipc_free(self.ptr)
             self.ptr = C.c_void_p()
