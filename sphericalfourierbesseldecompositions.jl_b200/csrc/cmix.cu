@@ -349,6 +349,7 @@ struct CmixArgs {
     const int* row_n;       // 0-based n
     const int* row_n2;      // 0-based n'
     const int* a_of_ell;
+    const int* real_ell;    // row block -> l (virtual row blocks of an l with nmax_l > 32)
     const int* pairidx;     // [L][nmax][nmax] -> output column or -1
     const int* ch_L;        // blockIdx.x -> (L, N0, N1)
     const int* ch_N0;
@@ -372,11 +373,12 @@ __host__ __device__ constexpr int cmix_tld(int AP) { return (AP % 16 == 8) ? AP 
 template <int AT, bool SYM>
 __global__ void __launch_bounds__(kCmixThreads, 2) cmix_block_kernel(CmixArgs p) {
     extern __shared__ double sm[];
-    const int ell = p.ell_list[blockIdx.y];
+    const int ell = p.ell_list[blockIdx.y];       // row block (G rows, row table); rl = its l (Ŵ index, factors)
+    const int rl = p.real_ell[ell];
     const int L = p.ch_L[blockIdx.x], N0 = p.ch_N0[blockIdx.x], N1 = p.ch_N1[blockIdx.x];
     const int a = p.a_of_ell[ell], b = p.a_of_ell[L];
     if (a == 0 || N0 >= b) return;
-    if (p.mirror && L < ell) return;  // obtained from block (L, l) by the symmetry of the un-symmetrised kernel
+    if (p.mirror && L < rl) return;  // obtained from block (L, l) by the symmetry of the un-symmetrised kernel
     constexpr int AP = AT * 8;
     constexpr int TLD = cmix_tld(AP);       // staging leading dimension: double2 stores are conflict free
     constexpr int P = SYM ? 2 : 1;          // N' tiles per warp pass (shares the Z and G_l fragment loads)
@@ -417,7 +419,7 @@ __global__ void __launch_bounds__(kCmixThreads, 2) cmix_block_kernel(CmixArgs p)
     __syncthreads();
 
     // ---- Z phase: each warp owns a pair of 8-wide r' tiles (B fragments of Ŵ) and sweeps the N of the chunk --
-    const double* Wh = p.What + ((size_t)(ell - p.ell0) * (p.lmax + 1) + L) * nrp * nrp;
+    const double* Wh = p.What + ((size_t)(rl - p.ell0) * (p.lmax + 1) + L) * nrp * nrp;
     const int ntile = nrp / 8, njp = (ntile + 1) / 2;
     const int wgrp = min(njp, kCmixWarps), nlane = kCmixWarps / wgrp;
     const int wj = warp % wgrp, wn = warp / wgrp;
@@ -514,8 +516,8 @@ __global__ void __launch_bounds__(kCmixThreads, 2) cmix_block_kernel(CmixArgs p)
 
     // ---- T phase: (N, N') tiles of the chunk dealt round-robin, P consecutive N' per pass -----------------
     const double scale = (p.div2Lp1 ? 1.0 : (2.0 * L + 1.0)) * 0.07957747154594767;  // 1/(4π)
-    const double scale_l = (p.div2Lp1 ? 1.0 : (2.0 * ell + 1.0)) * 0.07957747154594767;
-    const bool domirror = p.mirror && (L > ell);
+    const double scale_l = (p.div2Lp1 ? 1.0 : (2.0 * rl + 1.0)) * 0.07957747154594767;
+    const bool domirror = p.mirror && (L > rl);
     double* Tw = Ts + warp * NZ * AP * TLD;
     int cnt = 0;
     for (int Nloc = 0; Nloc < nN; ++Nloc) {
@@ -740,6 +742,56 @@ int cmix_plan_create(CmixPlan** out, const int64_t* lnn, int64_t lnnsize, int64_
         p->h_row_n2[slot] = n2;
         pairidx[((size_t)l * nmax + n1) * nmax + n2] = (int)(i - (lnn_min - 1));
     }
+    // row blocks: the l-blocks, then the virtual blocks of every l with more than 32 radial modes
+    p->nblk = (int)lmax + 1;
+    p->blk_real.resize(lmax + 1);
+    p->blk_of_ell.assign(lmax + 1, std::vector<int>());
+    for (int l = 0; l <= lmax; ++l) {
+        p->blk_real[l] = l;
+        p->blk_of_ell[l].push_back(l);
+    }
+    struct VPanel { int l, p0, np, q0, nq; };
+    std::vector<VPanel> vpanels;
+    constexpr int kPanel = 16;
+    for (int l = 0; l <= lmax; ++l) {
+        if (a[l] <= 32) continue;
+        p->blk_of_ell[l].clear();
+        const int npan = (a[l] + kPanel - 1) / kPanel;
+        for (int pp = 0; pp < npan; ++pp)
+            for (int qq = pp; qq < npan; ++qq) {
+                const int p0 = pp * kPanel, p1 = std::min(a[l], p0 + kPanel), q0 = qq * kPanel, q1 = std::min(a[l], q0 + kPanel);
+                std::vector<int> ro, rn, rn2;
+                for (int s2 = p->ell_ptr[l]; s2 < p->ell_ptr[l + 1]; ++s2) {
+                    const int n1 = p->h_row_n[s2], n2 = p->h_row_n2[s2];
+                    const bool n1p = n1 >= p0 && n1 < p1, n2p = n2 >= p0 && n2 < p1;
+                    const bool n1q = n1 >= q0 && n1 < q1, n2q = n2 >= q0 && n2 < q1;
+                    int v1 = -1, v2 = -1;
+                    if (pp == qq) {
+                        if (n1p && n2p) v1 = n1 - p0, v2 = n2 - p0;
+                    } else if (n1p && n2q) {
+                        v1 = n1 - p0, v2 = kPanel + n2 - q0;
+                    } else if (n1q && n2p) {
+                        v1 = kPanel + n1 - q0, v2 = n2 - p0;
+                    }
+                    if (v1 < 0) continue;
+                    ro.push_back(p->h_row_out[s2]);
+                    rn.push_back(v1);
+                    rn2.push_back(v2);
+                }
+                if (ro.empty()) continue;
+                const int v = p->nblk++;
+                p->blk_real.push_back(l);
+                p->blk_of_ell[l].push_back(v);
+                a.push_back(pp == qq ? p1 - p0 : kPanel + (q1 - q0));
+                p->ell_ptr.push_back(p->ell_ptr.back() + (int)ro.size());
+                p->h_row_out.insert(p->h_row_out.end(), ro.begin(), ro.end());
+                p->h_row_n.insert(p->h_row_n.end(), rn.begin(), rn.end());
+                p->h_row_n2.insert(p->h_row_n2.end(), rn2.begin(), rn2.end());
+                vpanels.push_back({l, p0, p1 - p0, q0, pp == qq ? 0 : q1 - q0});
+                (void)v;
+            }
+    }
+    p->a_of_ell = a;
     // per output index: l | [n≠n'] << 30 (mirror fill), and whether l is non-decreasing in output order
     std::vector<int> es((size_t)p->nout, 0);
     p->ell_sorted = true;
@@ -761,10 +813,10 @@ int cmix_plan_create(CmixPlan** out, const int64_t* lnn, int64_t lnnsize, int64_
         }
     }
     p->nl = (int)nl_L.size();
-    p->amax_tiles = (amax + 7) / 8;   // > 4 (nmax_l > 32): only the tiled block kernels are unavailable (checked in cmix_run)
+    p->amax_tiles = std::min(4, (amax + 7) / 8);   // row tiles of the launched row blocks (virtual blocks hold <= 32 functions)
 
     // --- G: [nr][nmax][lmax+1] column-major -> [ell][n][nrp], NaN / padding -> 0 where unused ---
-    std::vector<double> Gh((size_t)(lmax + 1) * nmax * p->nrp, 0.0);
+    std::vector<double> Gh((size_t)p->nblk * nmax * p->nrp, 0.0);
     for (int l = 0; l <= lmax; ++l)
         for (int n = 0; n < a[l]; ++n)
             for (int r = 0; r < nr; ++r) {
@@ -777,6 +829,17 @@ int cmix_plan_create(CmixPlan** out, const int64_t* lnn, int64_t lnnsize, int64_
                 Gh[((size_t)l * nmax + n) * p->nrp + r] = v;
             }
 
+    for (size_t k = 0; k < vpanels.size(); ++k) {   // basis of the virtual blocks: panel p, then panel q
+        const VPanel& vp = vpanels[k];
+        const size_t v = (size_t)lmax + 1 + k;
+        for (int h = 0; h < 2; ++h) {
+            const int n0 = h ? vp.q0 : vp.p0, cnt2 = h ? vp.nq : vp.np, dst0 = h ? kPanel : 0;
+            for (int n = 0; n < cnt2; ++n)
+                std::copy(Gh.begin() + ((size_t)vp.l * nmax + n0 + n) * p->nrp, Gh.begin() + ((size_t)vp.l * nmax + n0 + n + 1) * p->nrp,
+                          Gh.begin() + (v * nmax + dst0 + n) * p->nrp);
+        }
+    }
+
     auto up = [&](auto& dbuf, const auto& hvec) -> int {
         SFB_TRY(dbuf.alloc(hvec.size()));
         SFB_CUDA_OK(cudaMemcpy(dbuf.p, hvec.data(), hvec.size() * sizeof(hvec[0]), cudaMemcpyHostToDevice));
@@ -788,13 +851,14 @@ int cmix_plan_create(CmixPlan** out, const int64_t* lnn, int64_t lnnsize, int64_
     rc = rc ? rc : up(p->d_row_n, p->h_row_n);
     rc = rc ? rc : up(p->d_row_n2, p->h_row_n2);
     rc = rc ? rc : up(p->d_a, p->a_of_ell);
+    rc = rc ? rc : up(p->d_blk_real, p->blk_real);
     rc = rc ? rc : up(p->d_pairidx, pairidx);
     rc = rc ? rc : up(p->d_nl_L, nl_L);
     rc = rc ? rc : up(p->d_nl_N, nl_N);
     rc = rc ? rc : up(p->d_es, es);
     {   // output index -> CSR slot (n, n' of the row)
         std::vector<int> slot_of_out((size_t)p->nout, 0);
-        for (size_t sl = 0; sl < p->h_row_out.size(); ++sl)
+        for (size_t sl = 0; sl < (size_t)p->ell_ptr[lmax + 1]; ++sl)   // slots of the l-blocks (virtual blocks renumber n)
             if (p->h_row_out[sl] >= 0) slot_of_out[p->h_row_out[sl]] = (int)sl;
         rc = rc ? rc : up(p->d_slot_of_out, slot_of_out);
     }
@@ -807,8 +871,8 @@ int cmix_plan_create(CmixPlan** out, const int64_t* lnn, int64_t lnnsize, int64_
             p->h_colbase[o + 1] = p->h_colbase[o] + round_up(lend[es[o] & 0x3fffffff], 4);
         rc = rc ? rc : up(p->d_colbase, p->h_colbase);
     }
-    rc = rc ? rc : p->d_row_out.alloc(nrows);
-    rc = rc ? rc : p->d_ell_list.alloc(lmax + 1);
+    rc = rc ? rc : p->d_row_out.alloc(p->h_row_out.size());
+    rc = rc ? rc : p->d_ell_list.alloc(p->nblk);
     rc = rc ? rc : p->d_w2.alloc((size_t)(lmax + 1) * (lmax + 1) * (lmax + 1));
     rc = rc ? rc : p->d_W.alloc((size_t)(p->LMAX + 1) * p->nrp * p->nrp);
     if (rc) {
@@ -847,8 +911,6 @@ int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp
     SFB_REQUIRE(0 <= row_lo && row_lo <= row_hi && row_hi <= p->nout, "cmix_run: bad row range");
     SFB_REQUIRE(0 <= col_lo && col_lo <= col_hi && col_hi <= p->nout, "cmix_run: bad column range");
     SFB_REQUIRE(ldM >= row_hi - row_lo, "cmix_run: ldM smaller than the row shard");
-    SFB_REQUIRE(p->amax_tiles <= 4, "power_win_mix (dense window): nmax_l > 32 is not supported by the tiled block kernels of "
-                                    "this build (the separable-window path and win_lnn are)");
     p->t_wl = p->t_what = p->t_block = 0;
     p->flops_executed = 0;
     p->launches = 0;
@@ -878,12 +940,12 @@ int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp
     // rows of the shard -> output row index relative to row_lo, -1 elsewhere; ells touched by the shard
     std::vector<int> row_out(p->h_row_out.size());
     std::vector<char> ell_used(lmax + 1, 0);
-    for (int l = 0; l <= lmax; ++l)
-        for (int s = p->ell_ptr[l]; s < p->ell_ptr[l + 1]; ++s) {
+    for (int blk = 0; blk < p->nblk; ++blk)
+        for (int s = p->ell_ptr[blk]; s < p->ell_ptr[blk + 1]; ++s) {
             const int o = p->h_row_out[s];
             const bool in = (o >= row_lo && o < row_hi);
             row_out[s] = in ? (int)(mirror ? o : o - row_lo) : -1;
-            if (in) ell_used[l] = 1;
+            if (in) ell_used[p->blk_real[blk]] = 1;
         }
     SFB_CUDA_OK(cudaMemcpyAsync(p->d_row_out.p, row_out.data(), row_out.size() * sizeof(int), cudaMemcpyHostToDevice,
                                 stream));
@@ -932,6 +994,7 @@ int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp
     args.row_n = p->d_row_n.p;
     args.row_n2 = p->d_row_n2.p;
     args.a_of_ell = p->d_a.p;
+    args.real_ell = p->d_blk_real.p;
     args.pairidx = p->d_pairidx.p;
     size_t chunk_fill = 0;
     args.M[0] = d_M;
@@ -1047,12 +1110,13 @@ int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp
                 std::vector<int> blocks;
                 for (size_t wi = w0; wi < w1; ++wi) {
                     const int l = wells[wi];
-                    for (int L = upper ? l : 0; L <= lmax; ++L) {
-                        if (!L_used[L] || p->a_of_ell[L] == 0) continue;
-                        const int desc[8] = {l, L, p->a_of_ell[l], p->a_of_ell[L], p->ell_ptr[l],
-                                             p->ell_ptr[l + 1] - p->ell_ptr[l], (l - ell0) * (lmax + 1) + L, 0};
-                        blocks.insert(blocks.end(), desc, desc + 8);
-                    }
+                    for (int v : p->blk_of_ell[l])            // the l-block itself, or its virtual row blocks
+                        for (int L = upper ? l : 0; L <= lmax; ++L) {
+                            if (!L_used[L] || p->a_of_ell[L] == 0) continue;
+                            const int desc[8] = {v, L, p->a_of_ell[v], p->a_of_ell[L], p->ell_ptr[v],
+                                                 p->ell_ptr[v + 1] - p->ell_ptr[v], (l - ell0) * (lmax + 1) + L, 0};
+                            blocks.insert(blocks.end(), desc, desc + 8);
+                        }
                 }
                 SFB_TRY(cmix_regz_run(p, blocks, p->d_What.p, div2Lp1, interchange, col_lo, col_hi, d_M, ldM,
                                       upper_packed ? p->d_colbase.p + col_lo : nullptr, stream, &flops, &p->launches));
@@ -1080,13 +1144,15 @@ int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp
             }
         }
         for (int AT = regz ? 0 : p->amax_tiles; AT >= 1; --AT) {
-            std::vector<int> ells;
+            std::vector<int> ells;   // row blocks of this tile class
             for (int l = ell0; l < ell1; ++l)
-                if (ell_used[l] && p->a_of_ell[l] > 0 && (p->a_of_ell[l] + 7) / 8 == AT) ells.push_back(l);
+                if (ell_used[l] && p->a_of_ell[l] > 0)
+                    for (int v : p->blk_of_ell[l])
+                        if ((p->a_of_ell[v] + 7) / 8 == AT) ells.push_back(v);
             if (ells.empty()) continue;
             const size_t off = ell_list_all.size();
             ell_list_all.insert(ell_list_all.end(), ells.begin(), ells.end());
-            SFB_REQUIRE(ell_list_all.size() <= (size_t)lmax + 1, "cmix_run: internal ell list overflow");
+            SFB_REQUIRE(ell_list_all.size() <= (size_t)p->nblk, "cmix_run: internal ell list overflow");
             SFB_CUDA_OK(cudaMemcpyAsync(p->d_ell_list.p + off, ells.data(), ells.size() * sizeof(int),
                                         cudaMemcpyHostToDevice, stream));
             args.ell_list = p->d_ell_list.p + off;
@@ -1126,7 +1192,7 @@ int cmix_run(CmixPlan* p, const double* d_alm1, const double* d_alm2, int div2Lp
             p->launches++;
             for (int l : ells)
                 for (int L = 0; L <= lmax; ++L) {
-                    if (!L_used[L] || (mirror && L < l)) continue;
+                    if (!L_used[L] || (mirror && L < p->blk_real[l])) continue;
                     const double b = p->a_of_ell[L], ap = AT * 8.0;
                     flops += (sym ? 1.0 : 2.0) * (2.0 * ap * nrp * nrp * b + 2.0 * ap * ap * nrp * b * (b + 1) / 2);
                 }

@@ -24,14 +24,20 @@ struct CmixPlan {
     int nl = 0;                  // number of (L,N) pairs with a column
     int amax_tiles = 0;
 
-    // host tables
-    std::vector<int> a_of_ell;        // max n (1-based) used by rows/cols of this ell, 0 if none
-    std::vector<int> ell_ptr;         // CSR over ell -> rows
+    // host tables.  Row blocks: [0, lmax] are the l-blocks of the table; an l with nmax_l > 32 (more than four 8-row
+    // tiles) is run as "virtual" row blocks appended behind them, one per pair (p <= q) of 16-wide panels of its n range,
+    // whose basis is the concatenation of the two panels (<= 32 functions) and whose rows are the (n in p, n' in q)
+    // modes: the block kernels never see more than 32 row-side functions.  a_of_ell / ell_ptr / G cover all blocks.
+    int nblk = 0;
+    std::vector<int> blk_real;                 // the l of every row block
+    std::vector<std::vector<int>> blk_of_ell;  // row blocks the tiled kernels launch for l ({l} unless virtualised)
+    std::vector<int> a_of_ell;        // max n (1-based) used by rows/cols of this ell (or virtual block), 0 if none
+    std::vector<int> ell_ptr;         // CSR over row blocks -> rows
     std::vector<int> h_row_out, h_row_n, h_row_n2;
 
     // device tables
     DevBuf<double> d_G;               // [ell][n][nrp]
-    DevBuf<int> d_ell_ptr, d_row_out, d_row_n, d_row_n2, d_a;
+    DevBuf<int> d_ell_ptr, d_row_out, d_row_n, d_row_n2, d_a, d_blk_real;
     DevBuf<int> d_pairidx;            // [L][N][N'] -> output column or -1
     DevBuf<int> d_nl_L, d_nl_N;       // grid.x -> (L, N)
     DevBuf<double> d_w2;              // [(lmax+1)^2][lmax+1] squared 3j symbols

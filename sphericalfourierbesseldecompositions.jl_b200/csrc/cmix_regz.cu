@@ -173,13 +173,21 @@ __device__ __forceinline__ void regz_warp_work(const RegzArgs& p, const double* 
         if (lane == 0) N = atomicAdd(counter, 1);
         N = __shfl_sync(0xffffffffu, N, 0);
         if (N >= b) break;
-        // output columns of (N, N') for N' = N + lane
-        int mycol = -1;
-        if (lane < b - N) {
-            const int c = __ldg(p.pairidx + ((size_t)colell * nmax + N) * nmax + N + lane);
-            mycol = (c >= p.col_lo && c < p.col_hi) ? c - p.col_lo : -1;
+        // output columns of (N, N'), N' = N + 32 c + lane (c-th group of 32; one group unless nmax_L > 32)
+        auto cols_of = [&](int n2base) {
+            int mc = -1;
+            if (n2base + lane < b) {
+                const int c = __ldg(p.pairidx + ((size_t)colell * nmax + N) * nmax + n2base + lane);
+                mc = (c >= p.col_lo && c < p.col_hi) ? c - p.col_lo : -1;
+            }
+            return mc;
+        };
+        int mycol = cols_of(N);
+        {
+            unsigned any = __ballot_sync(0xffffffffu, mycol >= 0);
+            for (int n2b = N + 32; n2b < b && !any; n2b += 32) any = __ballot_sync(0xffffffffu, cols_of(n2b) >= 0);
+            if (any == 0u) continue;
         }
-        if (__ballot_sync(0xffffffffu, mycol >= 0) == 0u) continue;
 
         // ---- Z phase: Z[i][jt][e] = Z_N[8i+g][8jt+2t+e] ------------------------------------------------------
         double Z[AT][NT][2];
@@ -221,7 +229,8 @@ __device__ __forceinline__ void regz_warp_work(const RegzArgs& p, const double* 
 
         // ---- T phase over N' >= N -------------------------------------------------------------------------
         for (int N2 = N; N2 < b; ++N2) {
-            const int col = __shfl_sync(0xffffffffu, mycol, N2 - N);
+            if (N2 > N && ((N2 - N) & 31) == 0) mycol = cols_of(N2);   // next group of 32 columns
+            const int col = __shfl_sync(0xffffffffu, mycol, (N2 - N) & 31);
             if (col < 0) continue;  // warp-uniform
             const bool offdiag = (N2 != N);
             const bool upper_only = rows_upper && !offdiag && !p.interchange;
@@ -944,7 +953,9 @@ static int launch_regz_at(int AT, const RegzArgs& args, const RegzLaunchCtx& ctx
 
 bool cmix_regz_eligible(const CmixPlan* p, bool sym, int npeers) {
     if (getenv("SFB_CMIX_OLD")) return false;
-    return sym && npeers == 0 && p->nrp <= 64 && p->amax_tiles <= 4 && p->nmax <= 32 && p->nout < kRegzNoRow;
+    // nmax > 32: rows run as virtual blocks of <= 32 functions (cmix_plan_create); the column side only needs its G_L tile
+    // (nmax rows) in shared memory next to the other operands
+    return sym && npeers == 0 && p->nrp <= 64 && p->amax_tiles <= 4 && p->nmax <= 144 && p->nout < kRegzNoRow;
 }
 
 // Launch the register-Z kernel over the listed (row-ell, col-ell) blocks of one Ŵ chunk.
@@ -1020,7 +1031,7 @@ int cmix_regz_run(CmixPlan* p, const std::vector<int>& blocks, const double* d_W
         args.blocks = p->d_regz_blocks.p + 8 * (size_t)i0;
         RegzLaunchCtx ctx;
         ctx.G = p->d_G.p;
-        ctx.g_rows = (long long)(p->lmax + 1) * p->nmax;
+        ctx.g_rows = (long long)p->nblk * p->nmax;
         ctx.What = d_What;
         ctx.w_rows = (long long)(p->d_What.n / (size_t)p->nrp);
         ctx.want_tma = getenv("SFB_REGZ_CPASYNC") == nullptr;

@@ -122,8 +122,10 @@ def test_cmix_from_wrlm_matches_oracle(kw):
 # every tile class of the block kernels: nmax_l = 5 / 12 / 20 / 26 / 32 (1..4 row tiles of 8), 24 / 40 / 64 shells
 # (register-Z kernel with 4 or 8 radial tiles) and 72 shells (shared-memory-Z kernel), dense lnn tables
 # (20, 1, 400): long radial grid (the reference's recommended nr >= 8(n+N)): G_L rows stay in global memory
+# (37, 1, 40), (48, 1, 64), (70, 0, 24): nmax_l > 32 on the register-Z kernel — rows as virtual blocks (panel pairs of 16),
+# more than 32 column-side N per block; (40, 1, 72): the same on the shared-memory-Z kernel
 @pytest.mark.parametrize("nmax,lmax,nr", [(5, 3, 24), (12, 3, 40), (20, 2, 64), (26, 2, 40), (32, 1, 64), (26, 1, 72),
-                                          (20, 1, 400), (9, 2, 200)])
+                                          (20, 1, 400), (9, 2, 200), (37, 1, 40), (48, 1, 64), (70, 0, 24), (40, 1, 72)])
 @pytest.mark.parametrize("kw", [dict(), dict(div2Lp1=True, interchange_NN=True)])
 def test_cmix_tile_classes(nmax, lmax, nr, kw):
     import warnings
@@ -147,9 +149,10 @@ def test_cmix_tile_classes(nmax, lmax, nr, kw):
     assert relerr(got, ref) < RTOL
 
 
+@pytest.mark.parametrize("nmax,lmax,nr", [(3, 4, 37), (35, 1, 24)])   # the second: cross-correlation with nmax_l > 32
 @pytest.mark.parametrize("interchange", [False, True])
-def test_cmix_two_windows(interchange):
-    sfb, oa, a, owm, wm, oc, c, rng = _setup(nmax=3, lmax=4, nr=37, dnmax=None)
+def test_cmix_two_windows(interchange, nmax, lmax, nr):
+    sfb, oa, a, owm, wm, oc, c, rng = _setup(nmax=nmax, lmax=lmax, nr=nr, dnmax=None)
     win1, _, _ = _random_window(rng, owm, smooth=False)
     win2, _, _ = _random_window(rng, owm, smooth=False)
     LMAX = 2 * oa.lmax
@@ -338,9 +341,9 @@ def test_stage1_ring_space_variants(monkeypatch, flag, nside, lmax, nr):
     assert relerr(got, base) < 1e-12
 
 
-def test_nmax_l_above_32_separable_and_win_lnn_still_work():
-    """tables with nmax_l > 32 are only unsupported by the tiled dense-window kernels; the separable-window
-    coupling matrix and win_lnn go through the same plan and must work (the dense call fails with a clear message)."""
+def test_nmax_l_above_32_every_path():
+    """Tables with nmax_l > 32 (VERDICT r1 missing #7): the separable-window coupling matrix and win_lnn go through the plan
+    directly; the dense window runs the l-blocks as virtual row blocks of <= 32 basis functions (panel pairs)."""
     import warnings
     from sfb_b200 import _lib
     sfb, oa, a, owm, wm, oc, c, rng = _setup(nmax=34, lmax=1, nr=40, dnmax=None)
@@ -353,5 +356,4 @@ def test_nmax_l_above_32_separable_and_win_lnn_still_work():
         ref = ow.power_win_mix(swin.dense(), swin.dense(), owm, oc)
         assert relerr(M, ref) < RTOL
         assert relerr(sfb.win_lnn(swin.dense(), wm, c), ow.win_lnn(swin.dense(), owm, oc)) < RTOL
-        with pytest.raises(_lib.SFBError, match="nmax_l > 32"):
-            sfb.power_win_mix(swin.dense(), wm, c)
+        assert relerr(sfb.power_win_mix(swin.dense(), wm, c), ref) < RTOL
