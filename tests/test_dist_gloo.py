@@ -1,4 +1,5 @@
-"""world_size-2 gloo test (CPU) of the multi-GPU host logic: row shards -> all-gather -> full matrix."""
+"""world_size-2 gloo test (CPU) of the multi-GPU host logic: row / column / upper-packed shards -> all-gather -> full matrix,
+and the exactly-once ownership of the L-shaped shards."""
 import os
 import sys
 
@@ -45,6 +46,23 @@ def _worker(rank, world, port, ret):
     allgather_packed_slabs(packed, [(int(off[l]), int(off[h])) for l, h in cr])
     ref = np.concatenate([M[:rend[j], j] for j in range(n)])
     ok = ok and np.array_equal(packed.numpy(), ref)
+    # L-shaped shards: rank g owns the upper-packed columns of its range and, mirrored from them, its rows of the part below
+    # the block diagonal; summed over the ranks every element of M is owned exactly once and the pieces rebuild M (here a
+    # symmetric kernel with f = 1, so the mirror image of M[r, j] is M[j, r] itself)
+    S = M + M.T
+    owned = torch.zeros((n, n), dtype=torch.float64)
+    rebuilt = torch.zeros((n, n), dtype=torch.float64)
+    rows = np.zeros((chi, chi - clo))                        # rows[r, j - lo] = S[j, r] for l(r) < l(j)
+    for j in range(clo, chi):
+        owned[:rend[j], j] += 1                              # packed column j
+        rebuilt[:rend[j], j] = torch.from_numpy(S[:rend[j], j].copy())
+        below = ell[:chi] < ell[j]
+        rows[np.flatnonzero(below), j - clo] = S[np.flatnonzero(below), j]      # what cmix_mirror_rows_kernel writes
+        owned[j, np.flatnonzero(below)] += 1                 # mirrored row j
+        rebuilt[j, np.flatnonzero(below)] = torch.from_numpy(rows[np.flatnonzero(below), j - clo].copy())
+    dist.all_reduce(owned)
+    dist.all_reduce(rebuilt)
+    ok = ok and bool((owned == 1).all()) and np.array_equal(rebuilt.numpy(), S)
     out = torch.tensor([1.0 if ok else 0.0])
     dist.all_reduce(out, op=dist.ReduceOp.MIN)
     if rank == 0:
