@@ -907,7 +907,9 @@ static int launch_regz(const RegzArgs& args, const RegzLaunchCtx& ctx, int nbloc
                        cudaStream_t stream) {
     constexpr int AP = AT * 8, S = NT * 8 + 8;
     const size_t smem = regz_smem_bytes<AT, NT, NW>(nmax, max_rows);
-    SFB_REQUIRE(smem <= 227 * 1024, "cmix_regz_kernel: shared memory footprint exceeds 227 KB");
+    // dynamic + static shared memory of a block must fit the 227 KB opt-in limit: leave 1 KB for the static part (mbarriers)
+    constexpr size_t kSmemLimit = 227 * 1024 - 1024;
+    SFB_REQUIRE(smem <= kSmemLimit, "cmix_regz_kernel: shared memory footprint exceeds 226 KB");
     RegzTmaps tm;
     std::memset(&tm, 0, sizeof(tm));
     bool tma = ctx.want_tma;
@@ -915,7 +917,7 @@ static int launch_regz(const RegzArgs& args, const RegzLaunchCtx& ctx, int nbloc
         tma = encode_2d(&tm.gl, ctx.G, args.nrp, ctx.g_rows, S, AP) && encode_2d(&tm.gL, ctx.G, args.nrp, ctx.g_rows, S, nmax) &&
               encode_2d(&tm.w, ctx.What, args.nrp, ctx.w_rows, S, args.nrp);
     const size_t psmem = regz_persist_smem_bytes<AT, NT, NWP>(nmax, max_rows);
-    if (tma && ctx.want_persist && ctx.queue && psmem <= 227 * 1024) {
+    if (tma && ctx.want_persist && ctx.queue && psmem <= kSmemLimit) {
         const int grid = std::min(nblocks, ctx.num_sms);
         SFB_CUDA_OK(cudaFuncSetAttribute(cmix_regz_persist_kernel<AT, NT, NWP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)psmem));

@@ -175,6 +175,18 @@ def test_cfg5_stage1_shells_sampled_rows_and_symmetry():
     direct = pipe.power_win_mix_rows(lo, lo + 1)
     torch.cuda.synchronize()
     assert relerr(direct[:, 0].cpu().numpy(), got[2]) < 1e-12
+    # one-row calls in l-blocks of every size class from nmax_l = 32 down to 17: the launch's row table (and with it the
+    # shared-memory footprint that decides between the persistent and the one-block kernel) follows the l-block touched —
+    # a = 26 sat 96 bytes under the opt-in limit before the static part was counted (8-GPU bench of round 2)
+    ell_of = wl.cmodes.lnn[0]
+    for a in range(32, 16, -1):
+        ls = np.flatnonzero(np.asarray(wl.amodes.nmax_l) == a)
+        if ls.size == 0:
+            continue
+        i0 = int(np.flatnonzero(ell_of == ls[0])[0])
+        one = pipe.power_win_mix_rows(i0, i0 + 1)
+        torch.cuda.synchronize()
+        assert relerr(one[:, 0].cpu().numpy(), M[:, i0].cpu().numpy()) < 1e-12
     pipe.close()
 
 
