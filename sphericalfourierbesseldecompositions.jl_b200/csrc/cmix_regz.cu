@@ -92,7 +92,9 @@ constexpr int kRegzNoRow = 0x3FFFFF;   // packed row-table marker: row not in th
 
 // per-warp tile staging stride ≡ 8 (mod 16): conflict-free 16-byte tile stores; the epilogue reads run along the diagonals
 // of the tile (the reference orders an l-block by n'-n, then n: src/modes.jl getidx), i.e. with stride TLD + 1 (odd)
-__host__ __device__ constexpr int regz_tld(int AP) { return (AP % 16 == 8) ? AP : AP + 8; }
+// (AP = 32: 34 instead of 40 — two-way conflicts on the tile stores, but the 12 KB saved let the persistent kernel's two
+//  operand stages fit next to eight staging tiles: cfg5's four-tile blocks then run persistent as well)
+__host__ __device__ constexpr int regz_tld(int AP) { return (AP % 16 == 8) ? AP : (AP == 32 ? 34 : AP + 8); }
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
