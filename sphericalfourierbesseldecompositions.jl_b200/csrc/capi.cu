@@ -179,14 +179,18 @@ private:
 struct HostStage {
     static constexpr size_t kPiece = size_t(32) << 20;
     void* buf[2] = {nullptr, nullptr};
-    cudaEvent_t ev[2] = {nullptr, nullptr};
+    cudaEvent_t evdev[64][2] = {};      // events belong to a device: one pair per device that used the ring
+    cudaEvent_t* ev = nullptr;          // the pair of the current device (set by init)
     HostPool* pool = nullptr;
     int init() {
+        int dev = 0;
+        SFB_CUDA_OK(cudaGetDevice(&dev));
+        SFB_REQUIRE(dev >= 0 && dev < 64, "device index out of range");
+        if (!evdev[dev][0])
+            for (int i = 0; i < 2; ++i) SFB_CUDA_OK(cudaEventCreateWithFlags(&evdev[dev][i], cudaEventDisableTiming));
+        ev = evdev[dev];
         if (pool) return 0;
-        for (int i = 0; i < 2; ++i) {
-            SFB_CUDA_OK(cudaHostAlloc(&buf[i], kPiece, cudaHostAllocPortable));
-            SFB_CUDA_OK(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
-        }
+        for (int i = 0; i < 2; ++i) SFB_CUDA_OK(cudaHostAlloc(&buf[i], kPiece, cudaHostAllocPortable));
         const unsigned hc = std::thread::hardware_concurrency();
         int nt = (int)std::max(1u, std::min(8u, hc ? hc : 4u));   // 8 threads saturate the host copy (16: no gain)
         if (getenv("SFB_COPY_THREADS")) nt = std::max(1, atoi(getenv("SFB_COPY_THREADS")));
@@ -389,7 +393,9 @@ struct CmixTimes {
 // mode (step k forms the blocks (l in chunk k, L >= l) and their mirror images in the full device matrix, after which
 // the columns of chunk k are complete and can leave); otherwise plain full-height column slabs.
 static int cmix_cols_to_host(CmixPlan* p, Workspace& ws, const double* a1, const double* a2, int div2Lp1, int interchange,
-                             int64_t col_lo, int64_t col_hi, int nchunks, double* M_out) {
+                             int64_t col_lo, int64_t col_hi, int nchunks, double* M_out, bool stage_ok = false) {
+    // stage_ok: single-device host path only — the staging ring and its host threads are one per process, and the workers
+    // of a multi-device call run concurrently on other devices (their pageable copies are left to the driver)
     const int64_t n = p->nout;
     if (col_hi <= col_lo) return 0;
     const bool whole = (col_lo == 0 && col_hi == n);
@@ -406,7 +412,7 @@ static int cmix_cols_to_host(CmixPlan* p, Workspace& ws, const double* a1, const
     cudaStream_t st = ws.main;
     SFB_CUDA_OK(cudaMemsetAsync(ws.flag.p, 0, sizeof(int), st));
     CmixTimes tt;
-    const bool staged = is_pageable(M_out);
+    const bool staged = stage_ok && is_pageable(M_out);
     bool have_prev = false;
     int64_t prev_c0 = 0;
     const double* prev_src = nullptr;
@@ -1065,7 +1071,7 @@ int32_t sfb_power_win_mix(const double* win1, const double* win2, int64_t nr, in
     SFB_TRY(windows_to_alm(*ws, win1, win2, nr, npix_in, ld_win, nside, 2 * lmax, &same));
     tr.mark("H2D + stage 1");
     SFB_TRY(cmix_cols_to_host(pg.p, *ws, ws->alm1.p, same ? ws->alm1.p : ws->alm2.p, div2Lp1, interchange_NN, 0,
-                              pg.p->nout, 8, M_out));
+                              pg.p->nout, 8, M_out, true));
     record_cmix_times(pg.p);
     tr.mark("stage 2+3 pipelined with D2H");
     return 0;
