@@ -65,7 +65,8 @@ static int bin_scratch(BinScratch** out) {
 
 int binned_product_to_host(const double* d_M, int64_t n, const int64_t* wt_colptr, const int64_t* wt_rowval,
                            const double* wt_nzval, int64_t LNN1, const int64_t* v_colptr, const int64_t* v_rowval,
-                           const double* v_nzval, int64_t LNN2, double* N_out, float* ms) {
+                           const double* v_nzval, int64_t LNN2, double* N_out, float* ms,
+                           int (*d2h)(void* dst, const void* src, size_t bytes)) {
     SFB_REQUIRE(d_M && N_out, "binned_product: null pointer");
     if (!wt_colptr) SFB_REQUIRE(LNN1 == n, "w̃ = I requires LNN1 == lnnsize");
     if (!v_colptr) SFB_REQUIRE(LNN2 == n, "v = I requires LNN2 == lnnsize");
@@ -80,6 +81,7 @@ int binned_product_to_host(const double* d_M, int64_t n, const int64_t* wt_colpt
     SFB_TRY(d_N.alloc((size_t)LNN1 * LNN2));
     SFB_TRY(binned_product_device(d_M, n, wt_colptr, wt_rowval, wt_nzval, LNN1, v_colptr, v_rowval, v_nzval, LNN2, d_N.p,
                                   LNN1, ms));
+    if (d2h) return d2h(N_out, d_N.p, (size_t)LNN1 * LNN2 * sizeof(double));
     SFB_CUDA_OK(cudaMemcpy(N_out, d_N.p, (size_t)LNN1 * LNN2 * sizeof(double), cudaMemcpyDeviceToHost));
     return 0;
 }

@@ -15,9 +15,11 @@ namespace sfb {
 
 // d_M: n x n (device, column-major).  w̃ / v: host CSC (1-based colptr/rowval, Julia SparseMatrixCSC);
 // NULL colptr = UniformScaling I.  N_out: host, LNN1 x LNN2 column-major.
+// d2h (optional): device -> host copy to use for the result (the library-staged copy for pageable arrays)
 int binned_product_to_host(const double* d_M, int64_t n, const int64_t* wt_colptr, const int64_t* wt_rowval,
                            const double* wt_nzval, int64_t LNN1, const int64_t* v_colptr, const int64_t* v_rowval,
-                           const double* v_nzval, int64_t LNN2, double* N_out, float* ms);
+                           const double* v_nzval, int64_t LNN2, double* N_out, float* ms,
+                           int (*d2h)(void* dst, const void* src, size_t bytes) = nullptr);
 
 int binned_product_device(const double* d_M, int64_t n, const int64_t* wt_colptr, const int64_t* wt_rowval,
                           const double* wt_nzval, int64_t LNN1, const int64_t* v_colptr, const int64_t* v_rowval,

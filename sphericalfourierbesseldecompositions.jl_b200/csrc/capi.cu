@@ -250,6 +250,17 @@ static int h2d_staged(void* dst, const void* src, size_t bytes, cudaStream_t st)
     return 0;
 }
 
+// blocking device -> host copy on the legacy stream: staged by the library when the destination is pageable
+static int d2h_auto(void* dst, const void* src, size_t bytes) {
+    if (is_pageable(dst)) {
+        SFB_CUDA_OK(cudaDeviceSynchronize());
+        SFB_TRY(d2h_staged(dst, src, bytes, 0));
+        return 0;
+    }
+    SFB_CUDA_OK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 // H2D of the Julia array win (nr x npix, leading dimension ld) -> device [pixel][nr]
 static int h2d_rows(double* dst, const double* src, int64_t nr, int64_t npix, int64_t ld, cudaStream_t st,
                     bool stage_ok = false) {   // stage_ok: single-device host path (the staging ring is not shared)
@@ -1131,7 +1142,7 @@ int32_t sfb_power_win_mix_binned(const double* win1, int64_t nr, int64_t npix_in
     tr.mark("binned: stage 2+3");
     float t_bin = 0;
     SFB_TRY(binned_product_to_host(dM.p, n, wt_colptr, wt_rowval, wt_nzval, LNN1, v_colptr, v_rowval, v_nzval, LNN2,
-                                   N_out, &t_bin));
+                                   N_out, &t_bin, d2h_auto));
     g_times[7] = t_bin;
     tr.mark("binned: w~ M v + D2H");
     return 0;
