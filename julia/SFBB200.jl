@@ -26,7 +26,8 @@ end
 set_devices(n::Integer) = check(ccall((:sfb_set_devices, libsfb), Int32, (Int32,), n))
 
 # Result arrays in page-locked memory (sfb_host_alloc), so that every GPU copies its column slab at full PCIe speed;
-# freed by a finalizer.  A plain `Matrix{Float64}(undef, ...)` works too (pageable: the driver stages the copies).
+# freed by a finalizer.  A plain `Matrix{Float64}(undef, ...)` works too (pageable: on one GPU the library stages the copies
+# itself through a pinned ring and a host thread pool, on several GPUs the driver does).
 function pinned_matrix(::Type{T}, dims::Integer...) where {T}
     p = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:sfb_host_alloc, libsfb), Int32, (Ptr{Ptr{Cvoid}}, Int64), p, max(1, prod(dims) * sizeof(T))))
