@@ -356,4 +356,19 @@ def test_nmax_l_above_32_every_path():
         ref = ow.power_win_mix(swin.dense(), swin.dense(), owm, oc)
         assert relerr(M, ref) < RTOL
         assert relerr(sfb.win_lnn(swin.dense(), wm, c), ow.win_lnn(swin.dense(), owm, oc)) < RTOL
-        assert relerr(sfb.power_win_mix(swin.dense(), wm, c), ref) < RTOL
+        dense = sfb.power_win_mix(swin.dense(), wm, c)
+        assert relerr(dense, ref) < RTOL
+        # the multi-GPU output forms on the same table: column slabs and L-shaped shards (upper-packed + mirrored rows)
+        import torch
+        from sfb_b200.device import DevicePipeline, shard_rows
+        pipe = DevicePipeline(wm, c, sfb.rsdrgnlr(a, wm))
+        pipe.calc_wr_lm(torch.from_numpy(np.ascontiguousarray(swin.dense().T)).cuda())
+        cr = shard_rows(pipe.col_costs, pipe.ell_of_row, 2)
+        cols = np.concatenate([pipe.power_win_mix_cols(lo, hi).cpu().numpy().T for lo, hi in cr], axis=1)
+        assert relerr(cols, dense) < 1e-12
+        off = pipe.packed_offsets()
+        lr = pipe.packed_shard_ranges(2, balance="lshard")
+        packed = torch.full((int(off[-1]),), float("nan"), dtype=torch.float64, device="cuda")
+        rows = [pipe.power_win_mix_lshard(lo, hi, packed)[1] for lo, hi in lr]
+        assert relerr(pipe.lshard_assemble_host(packed, rows, lr), dense) < 1e-12
+        pipe.close()
