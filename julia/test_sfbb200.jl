@@ -1,0 +1,83 @@
+# test_sfbb200.jl — the drop-in checked against the reference itself, in the reference's own test vocabulary.
+#
+# NOT EXECUTED IN THIS REPOSITORY'S CI (the build image has no Julia): a maintainer runs it on a B200 box with
+#   julia --project=<SphericalFourierBesselDecompositions checkout> julia/test_sfbb200.jl
+# and SFB_B200_LIB pointing at libsfb_b200.so.  Every assertion compares an SFBB200 method with the reference method of the
+# same signature (src/windows.jl:528,750,751,781,809,994) on the windows the reference's tests use
+# (test/test_windows.jl:181-254,365-443,540-586), at the reference's tolerances or tighter.
+using Test
+using LinearAlgebra
+import SphericalFourierBesselDecompositions as SFB
+include(joinpath(@__DIR__, "SFBB200.jl"))
+
+@testset "SFBB200 drop-in vs the reference" begin
+    rmin, rmax = 500.0, 1000.0
+
+    @testset "calc_Wr_lm + power_win_mix, non-separable window (test/test_windows.jl:365-443 sizes)" begin
+        amodes = SFB.AnlmModes(2, 5, rmin, rmax, cache=false)
+        wmodes = SFB.ConfigurationSpaceModes(rmin, rmax, 100, amodes.nside)
+        cmodes = SFB.ClnnModes(amodes, Δnmax=Inf)
+        win = SFB.make_window(wmodes, :radial, :ang_quarter, :rotate)
+        LMAX = 2 * amodes.lmax
+        @test SFBB200.calc_Wr_lm(win, LMAX, amodes.nside) ≈ SFB.Windows.calc_Wr_lm(win, LMAX, amodes.nside)  rtol=1e-10
+        M = SFB.power_win_mix(win, wmodes, cmodes)
+        @test SFBB200.power_win_mix(win, wmodes, cmodes) ≈ M  rtol=1e-10
+        for kw in ((div2Lp1=true,), (interchange_NN′=true,), (div2Lp1=true, interchange_NN′=true, lnn_min=3))
+            @test SFBB200.power_win_mix(win, win, wmodes, cmodes; kw...) ≈ SFB.power_win_mix(win, win, wmodes, cmodes; kw...)  rtol=1e-10
+        end
+        @test SFBB200.win_lnn(win, wmodes, cmodes) ≈ SFB.win_lnn(win, wmodes, cmodes)  rtol=1e-10
+        # the brute-force route of the reference's own test (:385-409)
+        wmix = SFBB200.calc_wmix(win, wmodes, amodes)
+        wmix_negm = SFBB200.calc_wmix(win, wmodes, amodes; neg_m=true)
+        @test wmix ≈ SFB.calc_wmix(win, wmodes, amodes)  rtol=1e-10
+        @test SFB.power_win_mix(wmix, wmix_negm, cmodes) ≈ M  rtol=1e-10
+    end
+
+    @testset "full sky ⇒ M = I (test/test_windows.jl:181-213)" begin
+        amodes = SFB.AnlmModes(0.05, rmin, rmax, cache=false)
+        wmodes = SFB.ConfigurationSpaceModes(rmin, rmax, 128, 8)
+        cmodes = SFB.ClnnModes(amodes, Δnmax=Inf)
+        win = SFB.make_window(wmodes, :fullsky)
+        @test SFBB200.power_win_mix(win, wmodes, cmodes) ≈ I  atol=1e-3
+    end
+
+    @testset "separable window: dense ≡ separable (test/test_windows.jl:403-409)" begin
+        amodes = SFB.AnlmModes(0.03, rmin, rmax, cache=false)
+        wmodes = SFB.ConfigurationSpaceModes(rmin, rmax, 64, amodes.nside)
+        cmodes = SFB.ClnnModes(amodes, Δnmax=Inf)
+        swin = SFB.make_window(wmodes, :radial, :ang_quarter, :separable)
+        dwin = SFB.make_window(wmodes, :radial, :ang_quarter, :separable, :dense)
+        Ms = SFBB200.power_win_mix(swin, swin, wmodes, cmodes)
+        @test Ms ≈ SFB.power_win_mix(swin, wmodes, cmodes)  rtol=1e-10
+        @test Ms ≈ SFBB200.power_win_mix(dwin, wmodes, cmodes)  rtol=1e-10
+    end
+
+    @testset "band-power binning (test/test_windows.jl:540-586)" begin
+        amodes = SFB.AnlmModes(0.03, rmin, rmax, cache=false)
+        wmodes = SFB.ConfigurationSpaceModes(rmin, rmax, 64, amodes.nside)
+        cmodes = SFB.ClnnModes(amodes, Δnmax=Inf)
+        win = SFB.make_window(wmodes, :radial, :ang_quarter, :rotate)
+        w̃, v = SFB.bandpower_binning_weights(cmodes; Δℓ=2, Δn1=1, Δn2=1)
+        bcmodes = SFB.ClnnBinnedModes(w̃, v, cmodes)
+        M = SFBB200.power_win_mix(win, wmodes, cmodes)
+        N = SFBB200.power_win_mix(win, w̃, v, wmodes, bcmodes)
+        @test N ≈ w̃ * M * v  rtol=1e-10
+        @test N ≈ SFB.power_win_mix(win, w̃, v, wmodes, bcmodes)  rtol=1e-10
+        @test SFBB200.power_win_mix(win, w̃, I, wmodes, bcmodes) ≈ w̃ * M  rtol=1e-10
+        @test SFBB200.power_win_mix(win, I, v, wmodes, bcmodes) ≈ M * v  rtol=1e-10
+        # on-device deconvolution (docs/src/tutorial_catalog.md:93-107)
+        Cobs = randn(SFB.getlnnsize(cmodes))
+        @test SFBB200.power_win_mix_solve(win, w̃, v, wmodes, bcmodes, w̃ * Cobs) ≈ N \ (w̃ * Cobs)  rtol=1e-8
+    end
+
+    @testset "several GPUs behind the same call" begin
+        amodes = SFB.AnlmModes(0.05, rmin, rmax, cache=false)
+        wmodes = SFB.ConfigurationSpaceModes(rmin, rmax, 32, amodes.nside)
+        cmodes = SFB.ClnnModes(amodes, Δnmax=Inf)
+        win = SFB.make_window(wmodes, :radial, :ang_half, :rotate)
+        M1 = SFBB200.power_win_mix(win, wmodes, cmodes)
+        SFBB200.set_devices(2)            # errors on a single-GPU box: skip this testset there
+        @test SFBB200.power_win_mix(win, wmodes, cmodes) ≈ M1  rtol=1e-12
+        SFBB200.set_devices(1)
+    end
+end
