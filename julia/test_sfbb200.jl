@@ -14,7 +14,7 @@ include(joinpath(@__DIR__, "SFBB200.jl"))
     rmin, rmax = 500.0, 1000.0
 
     @testset "calc_Wr_lm + power_win_mix, non-separable window (test/test_windows.jl:365-443 sizes)" begin
-        amodes = SFB.AnlmModes(2, 5, rmin, rmax, cache=false)
+        amodes = SFB.AnlmModes(2, 5, rmin, rmax)
         wmodes = SFB.ConfigurationSpaceModes(rmin, rmax, 100, amodes.nside)
         cmodes = SFB.ClnnModes(amodes, Δnmax=Inf)
         win = SFB.make_window(wmodes, :radial, :ang_quarter, :rotate)
