@@ -397,12 +397,17 @@ class ClnnBinnedModes:
         self.LKK = LKK
 
 
-def bandpower_binning_weights(cmodes, dl=1, dn1=1, dn2=1):
-    """Dense (wtilde, v) — the reference returns the same values as SparseMatrixCSC."""
+def bandpower_binning_weights(cmodes, dl=1, dn1=1, dn2=1, select="all"):
+    """Dense (wtilde, v) — the reference returns the same values as SparseMatrixCSC (src/modes.jl:727-768).
+    `select`: "all" or a boolean mask over the lnn modes; only selected modes get a column (w̃[1:LNNsize, select])."""
     lnnsize = getlnnsize(cmodes)
+    sel = np.ones(lnnsize, dtype=bool) if isinstance(select, str) and select == "all" else np.asarray(select, dtype=bool)
+    assert sel.shape == (lnnsize,)
     iLNN = []
     rows = []
     for i in range(1, lnnsize + 1):
+        if not sel[i - 1]:
+            continue
         l, n1, n2 = getlnn(cmodes, i)
         key = (l // dl + 1, (n1 - 1) // dn1 + 1, (n2 - 1) // dn2 + 1)
         if key not in iLNN:
@@ -410,8 +415,9 @@ def bandpower_binning_weights(cmodes, dl=1, dn1=1, dn2=1):
         rows.append(iLNN.index(key))
     LNNsize = len(iLNN)
     wt = np.zeros((LNNsize, lnnsize))
-    for i, I in enumerate(rows):
+    for i, I in zip(np.flatnonzero(sel), rows):
         wt[I, i] += 1
+    wt = wt[:, sel]
     wt = wt / wt.sum(axis=1, keepdims=True)
     v = np.linalg.pinv(wt)
     assert np.allclose(wt.sum(axis=1), 1)

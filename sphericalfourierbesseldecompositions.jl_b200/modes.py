@@ -314,21 +314,28 @@ class ClnnBinnedModes:
         self.LKK = LKK
 
 
-def bandpower_binning_weights(cmodes, dl=1, dn1=1, dn2=1):
+def bandpower_binning_weights(cmodes, dl=1, dn1=1, dn2=1, select="all"):
     """(w̃, v) as scipy CSC matrices (the reference returns SparseMatrixCSC)  (src/modes.jl:727-768).
-    Bins are numbered in order of first appearance, like getidx! at src/modes.jl:714-725."""
+    Bins are numbered in order of first appearance, like getidx! at src/modes.jl:714-725.  `select`: "all" or a boolean
+    mask over the lnn modes — only selected modes get a column, as in the reference's `w̃[1:LNNsize, select]`.
+    Built sparse from the start: a dense LNN x lnnsize array is 1 GB at cfg4."""
     lnn = cmodes.lnn
-    keys = np.stack([lnn[0] // dl + 1, (lnn[1] - 1) // dn1 + 1, (lnn[2] - 1) // dn2 + 1], axis=1)
-    seen = {}
-    rows = np.empty(keys.shape[0], dtype=np.int64)
-    for i, key in enumerate(map(tuple, keys)):
-        rows[i] = seen.setdefault(key, len(seen))
-    nb, n = len(seen), keys.shape[0]
-    wt = np.zeros((nb, n))
-    wt[rows, np.arange(n)] = 1.0
-    wt /= wt.sum(axis=1, keepdims=True)
+    n_all = lnn.shape[1]
+    sel = np.ones(n_all, dtype=bool) if isinstance(select, str) and select == "all" else np.asarray(select, dtype=bool)
+    if sel.shape != (n_all,):
+        raise ValueError("select must be \"all\" or a boolean mask over the lnn modes")
+    keys = np.stack([lnn[0] // dl + 1, (lnn[1] - 1) // dn1 + 1, (lnn[2] - 1) // dn2 + 1], axis=1)[sel]
+    # bin index in order of first appearance
+    _, first, inv = np.unique(keys, axis=0, return_index=True, return_inverse=True)
+    order = np.argsort(first, kind="stable")
+    rank = np.empty(order.size, dtype=np.int64)
+    rank[order] = np.arange(order.size)
+    rows = rank[np.asarray(inv).ravel()]
+    nb, n = order.size, keys.shape[0]
+    counts = np.bincount(rows, minlength=nb).astype(np.float64)
+    cols = np.arange(n)
+    wt = sparse.csc_matrix((1.0 / counts[rows], (rows, cols)), shape=(nb, n))
     # v = pinv(w̃).  Every mode falls in exactly one bin, so w̃ w̃ᵀ is diagonal and the pseudo-inverse is the
     # bin indicator: v[i, I] = 1 for i in bin I (what LinearAlgebra.pinv returns up to rounding noise).
-    v = np.zeros((n, nb))
-    v[np.arange(n), rows] = 1.0
-    return sparse.csc_matrix(wt), sparse.csc_matrix(v)
+    v = sparse.csc_matrix((np.ones(n), (cols, rows)), shape=(n, nb))
+    return wt, v

@@ -55,6 +55,13 @@ def test_binning_weights_and_binned_modes(sfb):
         assert np.array_equal(wt.toarray(), owt) and np.abs(v.toarray() - ov).max() < 1e-14
         b, ob = sfb.ClnnBinnedModes(wt, v, c), om.ClnnBinnedModes(owt, ov, oc)
         assert np.allclose(b.LKK, ob.LKK, rtol=1e-9) and sfb.getlnnsize(b) == wt.shape[0]
+    # select= (src/modes.jl:732-734,757): only the selected modes get a column, bins in order of first appearance
+    rng = np.random.default_rng(5)
+    mask = rng.random(c.lnn.shape[1]) < 0.6
+    wt, v = sfb.bandpower_binning_weights(c, dl=3, dn1=2, select=mask)
+    owt, ov = om.bandpower_binning_weights(oc, dl=3, dn1=2, select=mask)
+    assert wt.shape == (owt.shape[0], int(mask.sum())) and np.array_equal(wt.toarray(), owt)
+    assert np.abs(v.toarray() - ov).max() < 1e-14
     wt, _ = sfb.bandpower_binning_weights(c)
     assert np.array_equal(wt.toarray(), np.eye(wt.shape[0]))                               # test/test_modes.jl:213-214
     bI = sfb.ClnnBinnedModes(None, None, c)
